@@ -1,0 +1,121 @@
+"""Oracle restatement of SipMaskHead.get_bboxes_single (decode, NMS, mask assembly).
+
+TEST INFRASTRUCTURE ONLY - see oracle/__init__.py.
+Follows MM/mmdet/models/anchor_heads/sipmask_head.py:543-662 line by line.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops as O
+
+
+def decode_candidates(cls_scores, bbox_preds, centernesses, cof_preds, strides, img_shape,
+                      nms_pre=1000, num_classes=80):
+    """Per-level sigmoid / top-k / box decode (sipmask_head.py:556-592, before `rescale`).
+
+    Inputs are per-image CHW tensors.  Returns boxes [n,4], scores [n,C] (no bg column),
+    centerness [n], cofs [n,128], flat_index [n] (index into the level-concatenated
+    h*w grid, for cross-checking).  Top-k order: descending score, ties -> lower index."""
+    mlvl_bboxes, mlvl_scores, mlvl_ctr, mlvl_cofs, mlvl_idx = [], [], [], [], []
+    base = 0
+    for cls_score, bbox_pred, cof_pred, centerness, stride in zip(
+            cls_scores, bbox_preds, cof_preds, centernesses, strides):
+        h, w = cls_score.shape[-2:]
+        points = O.get_points_single(h, w, stride)
+        scores = cls_score.permute(1, 2, 0).reshape(-1, num_classes).sigmoid()
+        ctr = centerness.permute(1, 2, 0).reshape(-1).sigmoid()
+        bbox_pred = bbox_pred.permute(1, 2, 0).reshape(-1, 4)
+        cof_pred = cof_pred.permute(1, 2, 0).reshape(-1, 128)
+        idx = torch.arange(h * w)
+        if nms_pre > 0 and scores.shape[0] > nms_pre:
+            max_scores, _ = (scores * ctr[:, None]).max(dim=1)
+            _, topk_inds = max_scores.sort(descending=True, stable=True)
+            topk_inds = topk_inds[:nms_pre]
+            points = points[topk_inds, :]
+            bbox_pred = bbox_pred[topk_inds, :]
+            cof_pred = cof_pred[topk_inds, :]
+            scores = scores[topk_inds, :]
+            ctr = ctr[topk_inds]
+            idx = idx[topk_inds]
+        mlvl_bboxes.append(O.distance2bbox(points, bbox_pred, max_shape=img_shape))
+        mlvl_cofs.append(cof_pred)
+        mlvl_scores.append(scores)
+        mlvl_ctr.append(ctr)
+        mlvl_idx.append(idx + base)
+        base += h * w
+    return (torch.cat(mlvl_bboxes), torch.cat(mlvl_scores), torch.cat(mlvl_ctr),
+            torch.cat(mlvl_cofs), torch.cat(mlvl_idx))
+
+
+def assemble_masks(feat_mask, det_cofs, det_boxes, box_scale, up=2.0, thr=0.4, upsample=True):
+    """sipmask_head.py:609-633.  feat_mask [32,H,W], det_cofs [N,128], det_boxes [N,4].
+
+    Returns (pos_masks [N,H,W] fp32 after CropSplit, masks [N,H*up,W*up] uint8 or None)."""
+    img_mask1 = feat_mask.permute(1, 2, 0)
+    m = [torch.sigmoid(img_mask1 @ det_cofs[:, 32 * k:32 * (k + 1)].t()) for k in range(4)]
+    pos_masks = torch.stack(m, dim=0)                                   # [4,H,W,N]
+    rois = det_boxes * box_scale
+    pos_masks = O.crop_split(pos_masks, rois, 2).permute(2, 0, 1)       # [N,H,W]
+    if not upsample:
+        return pos_masks, None
+    if isinstance(up, (tuple, list)):
+        sf = tuple(float(u) for u in up)
+    else:
+        sf = float(up)
+    masks = F.interpolate(pos_masks.unsqueeze(0), scale_factor=sf, mode='bilinear',
+                          align_corners=False, recompute_scale_factor=True).squeeze(0)
+    return pos_masks, (masks > thr).to(torch.uint8)
+
+
+def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides,
+                      img_shape, ori_shape, scale_factor, cfg, rescale=False, ssd_flag=False,
+                      num_classes=80, cmp_ge=False, mask_thr=0.4, head=None):
+    """Returns dict(det_bboxes [k,5], det_labels [k], idxs_keep [k], pos_masks [k,Hm,Wm],
+    masks [k,Hi,Wi] uint8 pasted to ori/img shape, mask_scores or None)."""
+    boxes, scores, ctr, cofs, _ = decode_candidates(
+        cls_scores, bbox_preds, centernesses, cof_preds, strides, img_shape,
+        cfg.get('nms_pre', -1), num_classes)
+    sf_arr = np.atleast_1d(np.asarray(scale_factor, dtype=np.float32))
+    if rescale:
+        boxes = boxes / torch.from_numpy(sf_arr)                        # :587-588
+    scores_bg = torch.cat([scores.new_zeros(scores.shape[0], 1), scores], dim=1)
+    if not ssd_flag:
+        det_bboxes, det_labels, idxs = O.multiclass_nms_idx(
+            boxes, scores_bg, cfg['score_thr'], cfg['nms']['iou_thr'], cfg['max_per_img'],
+            score_factors=ctr, cmp_ge=cmp_ge)
+        det_cofs = cofs[idxs]
+    else:
+        s = scores * ctr.view(-1, 1)
+        det_bboxes, det_labels, det_cofs, idxs = O.fast_nms(
+            boxes, s.transpose(1, 0).contiguous(), cofs,
+            iou_threshold=cfg['nms']['iou_thr'], score_thr=cfg['score_thr'])
+    out = dict(det_bboxes=det_bboxes, det_labels=det_labels, idxs_keep=idxs,
+               pos_masks=None, masks=None, mask_scores=None)
+    if det_bboxes.shape[0] > 0:
+        scale = 2
+        sf_t = torch.from_numpy(sf_arr)
+        if rescale is None:
+            sf_t = sf_t * 0 + 1.0                                       # :621-622
+        box_scale = sf_t / scale
+        if ssd_flag:
+            up = tuple((scale / sf_arr[[3, 2]]).tolist()) if sf_arr.size == 4 else float(scale / sf_arr[0])
+        else:
+            up = float(scale / sf_arr[0]) if sf_arr.size == 1 else tuple((scale / sf_arr).tolist())
+        pos_masks, masks = assemble_masks(feat_mask, det_cofs, det_bboxes[:, :4], box_scale, up, mask_thr)
+        out['pos_masks'] = pos_masks
+        tgt = ori_shape if rescale else img_shape
+        k = masks.shape[0]
+        im = np.zeros((k, tgt[0], tgt[1]), dtype=np.uint8)              # :648-654
+        hh = min(masks.shape[1], tgt[0])
+        ww = min(masks.shape[2], tgt[1])
+        im[:, :hh, :ww] = masks.numpy()[:, :hh, :ww]
+        out['masks'] = im
+        if head is not None and getattr(head, 'rescoring_flag', False):  # :635-643
+            pred_iou = pos_masks.unsqueeze(1)
+            pred_iou = head.convs_scoring(pred_iou)
+            pred_iou = F.relu(head.mask_scoring(pred_iou))
+            pred_iou = F.max_pool2d(pred_iou, kernel_size=pred_iou.size()[2:]).squeeze(-1).squeeze(-1)
+            pred_iou = pred_iou[range(pred_iou.size(0)), det_labels]
+            out['mask_scores'] = pred_iou * det_bboxes[:, -1]
+    return out
