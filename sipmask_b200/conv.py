@@ -1,0 +1,181 @@
+"""Host side of the tcgen05 convolution engine: weight packing (BN folding, K-major fp16) and plan objects.
+
+Reference modules replaced: nn.Conv2d (+ eval BatchNorm2d, bias, residual add, ReLU) in
+MM/mmdet/models/backbones/resnet.py:203-239, MM/mmdet/models/necks/fpn.py:138-178,
+MM/mmdet/ops/conv_module.py:124-132, MM/mmdet/models/anchor_heads/sipmask_head.py:241-287.
+Activations are NHWC fp16 torch tensors; all compute happens in libsipmask_b200.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def pack_weight(w, bn=None, eps=1e-5, cout_pad=None, device=None):
+    """[Cout,Cin,kh,kw] fp32 (+ eval BN (gamma,beta,mean,var)) -> ([Cout_pad, kh*kw*Cin] fp16 K-major, bias fp32|None).
+
+    K index = (r*kw + s)*Cin + ci, matching the tap order of the TMA producer.  Frozen BN
+    (resnet.py:514-521) folds to w *= gamma/sqrt(var+eps), bias = beta - mean*gamma/sqrt(var+eps)."""
+    w = w.detach().float()
+    cout, cin, kh, kw = w.shape
+    bias = None
+    if bn is not None:
+        gamma, beta, mean, var = [t.detach().float() for t in bn]
+        s = gamma / torch.sqrt(var + eps)
+        w = w * s.view(-1, 1, 1, 1)
+        bias = beta - mean * s
+    wk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    cp = cout_pad or ((cout + 15) // 16 * 16)
+    if cp != cout:
+        wk = torch.cat([wk, wk.new_zeros(cp - cout, wk.shape[1])], 0)
+        if bias is not None:
+            bias = torch.cat([bias, bias.new_zeros(cp - cout)])
+    wk = wk.to(torch.float16).contiguous()
+    if device is not None:
+        wk = wk.to(device)
+        bias = bias.to(device) if bias is not None else None
+    return wk, bias
+
+
+def pack_stem_weight(w, bn, eps=1e-5, device=None):
+    """7x7 stem [64,3,7,7] -> [64, 7*64] : K = r*64 + s*8 + c (s<7, c<3 real, rest zero)."""
+    gamma, beta, mean, var = [t.detach().float() for t in bn]
+    s = gamma / torch.sqrt(var + eps)
+    w = w.detach().float() * s.view(-1, 1, 1, 1)
+    out = w.new_zeros(64, 7, 8, 8)
+    out[:, :, :7, :3] = w.permute(0, 2, 3, 1)           # [co, r, s, c]
+    wk = out.reshape(64, 448).to(torch.float16).contiguous()
+    bias = (beta - mean * s).contiguous()
+    if device is not None:
+        wk, bias = wk.to(device), bias.to(device)
+    return wk, bias
+
+
+class ConvPlan(object):
+    """One convolution bound to fixed input / weight / output buffers (TMA descriptors are baked at creation)."""
+
+    def __init__(self, x, weight, out, k, stride=1, relu=False, bias=None, residual=None, residual_upsample=False,
+                 gn_stats=None, cin=None, alpha=1.0):
+        assert x.is_cuda and x.dtype == torch.float16 and x.dim() == 4 and x.stride(3) == 1
+        N, H, W, _ = x.shape
+        cin = cin if cin is not None else x.shape[3]
+        in_pitch = x.stride(2)
+        assert x.stride(1) == W * in_pitch and x.stride(0) == H * W * in_pitch
+        cout = weight.shape[0]
+        assert weight.shape[1] == k * k * cin and weight.dtype == torch.float16 and weight.is_contiguous()
+        assert out.stride(3) == 1
+        out_pitch = out.stride(2)
+        d = L.ConvDesc()
+        d.N, d.H, d.W, d.Cin, d.Cout = N, H, W, cin, cout
+        d.kh = d.kw = k
+        d.stride = stride
+        d.pad = k // 2
+        d.relu = int(relu)
+        d.has_bias = int(bias is not None)
+        d.has_residual = int(residual is not None)
+        d.residual_upsample = int(residual_upsample)
+        if residual is not None:
+            d.res_h, d.res_w = residual.shape[1], residual.shape[2]
+            assert residual.dtype == torch.float16 and residual.is_contiguous() and residual.shape[3] == cout
+        d.out_dtype = L.F32 if out.dtype == torch.float32 else L.F16
+        d.gn_stats = int(gn_stats is not None)
+        d.in_pitch = in_pitch
+        d.out_pitch = out_pitch
+        self._keep = (x, weight, out, bias, residual, gn_stats)
+        self.bias, self.residual, self.gn_stats, self.alpha = bias, residual, gn_stats, float(alpha)
+        self.handle = ctypes.c_void_p()
+        L.check(L.lib().smb_conv_plan_create(ctypes.byref(d), L.ptr(x), L.ptr(weight), L.ptr(out),
+                                             ctypes.byref(self.handle)), 'smb_conv_plan_create')
+        self.out = out
+
+    def run(self, stream=None):
+        L.check(L.lib().smb_conv_run(self.handle, L.ptr(self.bias), L.ptr(self.residual), L.ptr(self.gn_stats),
+                                     ctypes.c_float(self.alpha), stream if stream is not None else L.stream_ptr()),
+                'smb_conv_run')
+        return self.out
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().smb_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class StemPlan(ConvPlan):
+    """7x7/2 stem + folded BN + ReLU on the padded NHWC8 image (resnet.py:448-460)."""
+
+    def __init__(self, img8, weight448, bias, out, N, H, W):
+        self._keep = (img8, weight448, bias, out)
+        self.bias, self.residual, self.gn_stats, self.alpha = bias, None, None, 1.0
+        self.handle = ctypes.c_void_p()
+        L.check(L.lib().smb_stem_plan_create(N, H, W, L.ptr(img8), L.ptr(weight448), L.ptr(out),
+                                             ctypes.byref(self.handle)), 'smb_stem_plan_create')
+        self.out = out
+
+
+# ------------------------------------------------------------------------------------- small wrappers
+def image_to_nhwc8(img, out=None):
+    N, _, H, W = img.shape
+    if out is None:
+        out = torch.empty((N, H + 6, W + 8, 8), dtype=torch.float16, device=img.device)
+    L.check(L.lib().smb_image_to_nhwc8(L.ptr(img.contiguous()), L.ptr(out), N, H, W, L.stream_ptr()), 'smb_image_to_nhwc8')
+    return out
+
+
+def maxpool3x3s2(x, out=None):
+    N, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C), dtype=torch.float16, device=x.device)
+    L.check(L.lib().smb_maxpool3x3s2(L.ptr(x), L.ptr(out), N, H, W, C, L.stream_ptr()), 'smb_maxpool3x3s2')
+    return out
+
+
+def groupnorm_stats(x, stats=None):
+    N, H, W, C = x.shape
+    if stats is None:
+        stats = torch.empty((N, 32, 2), dtype=torch.float32, device=x.device)
+    L.check(L.lib().smb_groupnorm_stats(L.ptr(x), N, H * W, C, x.stride(2), L.ptr(stats), L.stream_ptr()),
+            'smb_groupnorm_stats')
+    return stats
+
+
+def groupnorm_relu_apply(x, stats, gamma, beta, eps=1e-5, relu=True):
+    N, H, W, C = x.shape
+    L.check(L.lib().smb_groupnorm_relu_apply(L.ptr(x), N, H * W, C, x.stride(2), L.ptr(stats), L.ptr(gamma), L.ptr(beta),
+                                             ctypes.c_float(eps), int(relu), L.stream_ptr()), 'smb_groupnorm_relu_apply')
+    return x
+
+
+def offset_conv1x1(bbox, scale, weight, out=None):
+    """bbox [N,H,W,>=4] fp32 channel-last (pitch = stride(2)); weight [n_off,4] fp32 -> [N,H,W,n_off] fp32."""
+    N, H, W, _ = bbox.shape
+    n_off = weight.shape[0]
+    if out is None:
+        out = torch.empty((N, H, W, n_off), dtype=torch.float32, device=bbox.device)
+    L.check(L.lib().smb_offset_conv1x1(L.ptr(bbox), bbox.stride(2), ctypes.c_float(scale), L.ptr(weight), n_off, L.ptr(out),
+                                       ctypes.c_longlong(N * H * W), L.stream_ptr()), 'smb_offset_conv1x1')
+    return out
+
+
+def deform_im2col(x, offset, dg, out=None):
+    """x [N,H,W,C] fp16, offset [N,H,W,dg*18] fp32 -> col [N,H,W,9*C] fp16."""
+    N, H, W, C = x.shape
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty((N, H, W, 9 * C), dtype=torch.float16, device=x.device)
+    L.check(L.lib().smb_deform_im2col(L.ptr(x), L.ptr(offset), offset.stride(2), L.ptr(out), N, H, W, C, int(dg),
+                                      L.stream_ptr()), 'smb_deform_im2col')
+    return out
+
+
+def upsample_bilinear(x, factor, out=None, out_choff=0, relu=False):
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, H * factor, W * factor, C), dtype=torch.float16, device=x.device)
+    L.check(L.lib().smb_upsample_bilinear(L.ptr(x), x.stride(2), L.ptr(out), out.stride(2), int(out_choff), N, H, W, C,
+                                          int(factor), int(relu), L.stream_ptr()), 'smb_upsample_bilinear')
+    return out

@@ -1,0 +1,585 @@
+// Implicit-GEMM convolution for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+// Replaces every nn.Conv2d (+ folded eval BatchNorm / bias / residual add / ReLU / GroupNorm statistics)
+// on the SipMask inference path (reference: SipMask-mmdetection/mmdet/models/backbones/resnet.py:203-239,
+// models/necks/fpn.py:138-178, ops/conv_module.py:124-132, models/anchor_heads/sipmask_head.py:241-287;
+// the reference runs them through cuDNN + separate ATen kernels).
+//
+//   D[pixel, co] = sum_{tap, ci} A[pixel (+) tap, ci] * Wt[co, tap*Cin + ci]
+//
+//  * A (activations) is NHWC fp16.  One M-tile is a BH x BW patch of output pixels (BH*BW = 128); for every
+//    filter tap the producer issues ONE 4-D TMA box {64 ch, BW, BH, 1} at the tap-shifted coordinate, so
+//    im2col never exists in memory and zero padding is TMA out-of-bounds fill.  Stride-2 convolutions use
+//    parity-split tensor maps (doubled global strides), the 7x7/2 stem an 8-pixel sliding-window map.
+//  * W is [Cout, taps*Cin] fp16, K-major, loaded as {64, N_TILE} boxes.  Both operands use the 128-byte
+//    swizzle, the canonical K-major UMMA layout (8-row groups 1024 B apart).
+//  * One elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=N_TILE<=256, K=16), fp32
+//    accumulators live in TMEM (double-buffered when 2*N_TILE <= 512 columns), tcgen05.commit releases
+//    shared-memory stages and publishes finished accumulators through mbarriers.
+//  * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer,
+//    warps 2..5 = epilogue (tcgen05.ld -> scale/bias/residual/ReLU/GN statistics -> global NHWC store).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace smb {
+
+constexpr int kMaxTaps = 9;
+constexpr int kMaxMaps = 4;
+constexpr int kThreads = 192;
+constexpr int kABytes = 128 * 64 * 2;   // one A stage: 128 pixels x 64 channels fp16
+
+struct ConvParams {
+  CUtensorMap amap[kMaxMaps];
+  CUtensorMap bmap;
+  int tap_map[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];
+  int num_taps, kb_per_tap;       // k-blocks (64 channels) per tap
+  int n_img, H_out, W_out, BH, BW, tiles_x, tiles_y;
+  int Cout, n_tile, n_tiles_n, stages, tmem_cols, num_acc;
+  void* out; int out_pitch; int out_f32;
+  const float* bias; float alpha;
+  const __half* residual; int res_pitch; int res_mode; int res_h, res_w;
+  float* gn_stats; int gn_group;   // channels per group
+  int relu;
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024>>4 |
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format F16 (0),
+// a/b K-major (0), n_dim = N>>3 @17, m_dim = M>>4 @24.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // the 128-byte swizzle atoms (8 rows x 128 B) must start on 1024-byte boundaries
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b_bytes = p.n_tile * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
+    tma_prefetch_desc(&p.bmap);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
+  const int total_tiles = tiles_m * p.n_tiles_n;
+  const int kblocks = p.num_taps * p.kb_per_tap;
+  const uint32_t stage_bytes = (uint32_t)(kABytes + b_bytes);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int img = mt / p.tiles_y;
+        const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * p.n_tile;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const CUtensorMap* am = &p.amap[p.tap_map[t]];
+          const int ax = x0 + p.tap_dx[t], ay = y0 + p.tap_dy[t];
+          for (int kc = 0; kc < p.kb_per_tap; ++kc, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], stage_bytes);
+            tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, img);
+            tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], (t * p.kb_per_tap + kc) * 64, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = make_idesc(128, p.n_tile);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt % p.num_acc;
+        const uint32_t acc_ph = (lt / p.num_acc) & 1;
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = make_sdesc(smem_u32(sA + (size_t)s * kABytes));
+          const uint64_t bdesc = make_sdesc(smem_u32(sB + (size_t)s * b_bytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in the >>4 start field
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);              // frees the smem stage when these MMAs retire
+        }
+        umma_commit(&tfull_bar[acc]);              // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int lane_grp = warp & 3;                   // TMEM lanes 32*(warp%4) .. +31 are accessible to this warp
+    const int row = lane_grp * 32 + lane;
+    const int iy = row / p.BW, ix = row - iy * p.BW;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int x = tx * p.BW + ix, y = ty * p.BH + iy, n0 = nt * p.n_tile;
+      const bool valid = (x < p.W_out) && (y < p.H_out);
+      const size_t pix = ((size_t)img * p.H_out + y) * p.W_out + x;
+      const __half* res_row = nullptr;
+      if (p.res_mode == 1) {
+        res_row = p.residual + pix * p.res_pitch;
+      } else if (p.res_mode == 2) {
+        // F.interpolate(mode='nearest', size=...) : src = min(floor(dst * in/out), in-1)   (fpn.py:149-152)
+        const int sy = min((int)floorf((float)y * ((float)p.res_h / (float)p.H_out)), p.res_h - 1);
+        const int sx = min((int)floorf((float)x * ((float)p.res_w / (float)p.W_out)), p.res_w - 1);
+        res_row = p.residual + (((size_t)img * p.res_h + sy) * p.res_w + sx) * p.res_pitch;
+      }
+      const int acc = lt % p.num_acc;
+      const uint32_t acc_ph = (lt / p.num_acc) & 1;
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_base + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int ch0 = n0 + c0;
+        if (ch0 >= p.Cout) continue;                 // uniform across the CTA
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ch0 + j);
+        }
+        if (p.alpha != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] *= p.alpha;
+        }
+        if (res_row && valid) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(res_row + ch0);
+          const uint4 ra = __ldg(r4), rb = __ldg(r4 + 1);
+          const __half2* ha = reinterpret_cast<const __half2*>(&ra);
+          const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = __half22float2(ha[j]), b = __half22float2(hb[j]);
+            f[2 * j] += a.x; f[2 * j + 1] += a.y;
+            f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+          }
+        }
+        if (p.gn_stats) {
+          // per-(image, group) sum / sum of squares of the conv output (pre-activation), fp32.
+          // gn_group (channels per group) is 8 (two groups per 16-column chunk) or 16 (one group).
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s0 += f[j]; q0 += f[j] * f[j];
+              s1 += f[8 + j]; q1 += f[8 + j] * f[8 + j];
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          }
+          if (lane == 0) {
+            const int ngroups = p.Cout / p.gn_group;
+            float* st = p.gn_stats + (size_t)img * ngroups * 2;
+            if (p.gn_group == 8) {
+              const int g = ch0 >> 3;
+              atomicAdd(st + g * 2, s0); atomicAdd(st + g * 2 + 1, q0);
+              atomicAdd(st + g * 2 + 2, s1); atomicAdd(st + g * 2 + 3, q1);
+            } else {
+              const int g = ch0 >> 4;
+              atomicAdd(st + g * 2, s0 + s1); atomicAdd(st + g * 2 + 1, q0 + q1);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_pitch + ch0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4 oa, ob;
+            __half2* ha = reinterpret_cast<__half2*>(&oa);
+            __half2* hb = reinterpret_cast<__half2*>(&ob);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ha[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+              hb[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + ch0);
+            o[0] = oa;
+            o[1] = ob;
+          }
+        }
+      }
+      // this warp has drained its quarter of the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SMB_ECUDA; }
+  cuuint64_t d[5]; cuuint64_t s[4]; cuuint32_t b[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) s[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=[%llu,%llu,%llu,%llu] strides=[%llu,%llu,%llu] box=[%u,%u,%u,%u]",
+              (int)r, rank, (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)(rank > 2 ? d[2] : 0),
+              (unsigned long long)(rank > 3 ? d[3] : 0), (unsigned long long)s[0], (unsigned long long)(rank > 2 ? s[1] : 0),
+              (unsigned long long)(rank > 3 ? s[2] : 0), b[0], b[1], rank > 2 ? b[2] : 0, rank > 3 ? b[3] : 0);
+    return SMB_ECUDA;
+  }
+  return SMB_OK;
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+struct smb_conv_plan {
+  ConvParams p;
+  int grid;
+  size_t smem_bytes;
+  int has_bias, has_residual, gn_stats;
+};
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// choose the BH x BW = 128 patch with the fewest tiles (ties -> wider rows, better store coalescing)
+static void choose_patch(int H, int W, int* BH, int* BW) {
+  const int cand[5][2] = {{1, 128}, {2, 64}, {4, 32}, {8, 16}, {16, 8}};
+  long best = -1;
+  for (int i = 0; i < 5; ++i) {
+    const long t = (long)cdiv(H, cand[i][0]) * cdiv(W, cand[i][1]);
+    if (best < 0 || t < best) { best = t; *BH = cand[i][0]; *BW = cand[i][1]; }
+  }
+}
+
+static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weight) {
+  ConvParams& p = pl->p;
+  // N tile: whole Cout when <= 256 (rounded to 16), else 256 / 128 divisors
+  int n_tile;
+  if (Cout <= 256) n_tile = (Cout + 15) / 16 * 16;
+  else if (Cout % 256 == 0) n_tile = 256;
+  else if (Cout % 128 == 0) n_tile = 128;
+  else { set_error("conv plan: unsupported Cout=%d", Cout); return SMB_EINVAL; }
+  p.n_tile = n_tile;
+  p.n_tiles_n = cdiv(Cout, n_tile);
+  int cols = 32;
+  while (cols < n_tile) cols <<= 1;
+  p.num_acc = (2 * n_tile <= 512) ? 2 : 1;
+  int tc = 32;
+  while (tc < p.num_acc * n_tile) tc <<= 1;
+  p.tmem_cols = tc;
+  const size_t stage = (size_t)kABytes + (size_t)n_tile * 128;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { set_error("conv plan: tile too large for shared memory"); return SMB_EINVAL; }
+  p.stages = stages;
+  pl->smem_bytes = stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  // weights: [Cout, Ktotal] K-major
+  uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
+  uint64_t strides[1] = {(uint64_t)Ktotal * 2};
+  uint32_t box[2] = {64, (uint32_t)n_tile};
+  int rc = encode_map(&p.bmap, const_cast<void*>(weight), 2, dims, strides, box);
+  if (rc) return rc;
+  const int tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  pl->grid = tiles < num_sms() ? tiles : num_sms();
+  return SMB_OK;
+}
+
+extern "C" int smb_conv_plan_create(const smb_conv_desc_t* d, const void* in, const void* weight, void* out,
+                                    smb_conv_plan_t** plan_out) {
+  SMB_CHECK_ARG(d && in && weight && out && plan_out, "smb_conv_plan_create: null pointer");
+  SMB_CHECK_ARG(d->Cin % 64 == 0 && d->Cin > 0, "smb_conv_plan_create: Cin=%d must be a multiple of 64", d->Cin);
+  SMB_CHECK_ARG(d->Cout % 16 == 0 && d->Cout > 0, "smb_conv_plan_create: Cout=%d must be a multiple of 16", d->Cout);
+  SMB_CHECK_ARG((d->kh == 1 && d->kw == 1 && d->pad == 0) || (d->kh == 3 && d->kw == 3 && d->pad == 1),
+                "smb_conv_plan_create: only 1x1/p0 and 3x3/p1 kernels (got %dx%d pad %d)", d->kh, d->kw, d->pad);
+  SMB_CHECK_ARG(d->stride == 1 || d->stride == 2, "smb_conv_plan_create: stride %d", d->stride);
+  const int in_pitch = d->in_pitch ? d->in_pitch : d->Cin;
+  const int out_pitch = d->out_pitch ? d->out_pitch : d->Cout;
+  SMB_CHECK_ARG(in_pitch % 8 == 0 && out_pitch % 8 == 0, "smb_conv_plan_create: pitches must be multiples of 8");
+  SMB_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)weight % 16) == 0 && ((uintptr_t)out % 16) == 0,
+                "smb_conv_plan_create: pointers must be 16-byte aligned");
+  smb_conv_plan* pl = new smb_conv_plan();
+  memset(&pl->p, 0, sizeof(ConvParams));
+  ConvParams& p = pl->p;
+  const int H = d->H, W = d->W, k = d->kh, s = d->stride;
+  const int Ho = (H + 2 * d->pad - k) / s + 1, Wo = (W + 2 * d->pad - k) / s + 1;
+  p.n_img = d->N; p.H_out = Ho; p.W_out = Wo;
+  choose_patch(Ho, Wo, &p.BH, &p.BW);
+  p.tiles_x = cdiv(Wo, p.BW); p.tiles_y = cdiv(Ho, p.BH);
+  p.num_taps = k * k; p.kb_per_tap = d->Cin / 64;
+  p.Cout = d->Cout;
+  p.out = out; p.out_pitch = out_pitch; p.out_f32 = (d->out_dtype == SMB_F32);
+  p.alpha = 1.0f; p.relu = d->relu;
+  p.res_mode = d->has_residual ? (d->residual_upsample ? 2 : 1) : 0;
+  p.res_pitch = d->Cout; p.res_h = d->res_h; p.res_w = d->res_w;
+  p.gn_group = d->Cout / 32;
+  pl->has_bias = d->has_bias; pl->has_residual = d->has_residual; pl->gn_stats = d->gn_stats;
+  if (d->gn_stats && !(p.gn_group == 8 || p.gn_group == 16)) {
+    set_error("smb_conv_plan_create: gn_stats needs Cout/32 in {8,16}");
+    delete pl;
+    return SMB_EINVAL;
+  }
+  const uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+  const uint64_t px = (uint64_t)in_pitch * 2;       // bytes per pixel
+  int rc = SMB_OK;
+  if (s == 1) {
+    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
+    uint64_t strides[3] = {px, px * W, px * W * H};
+    rc = encode_map(&p.amap[0], const_cast<void*>(in), 4, dims, strides, box);
+    for (int i = 1; i < kMaxMaps; ++i) p.amap[i] = p.amap[0];
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        const int t = r * k + c;
+        p.tap_map[t] = 0; p.tap_dx[t] = c - d->pad; p.tap_dy[t] = r - d->pad;
+      }
+  } else {
+    // stride 2: input (2*oy + r - pad, 2*ox + c - pad) -> parity-split views with doubled strides
+    for (int py = 0; py < 2 && rc == SMB_OK; ++py)
+      for (int pxp = 0; pxp < 2 && rc == SMB_OK; ++pxp) {
+        const int hp = (H - py + 1) / 2, wp = (W - pxp + 1) / 2;   // rows / cols of this parity
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)(wp > 0 ? wp : 1), (uint64_t)(hp > 0 ? hp : 1), (uint64_t)d->N};
+        uint64_t strides[3] = {px * 2, px * W * 2, px * W * H};
+        const char* base = (const char*)in + ((size_t)py * W + pxp) * px;
+        rc = encode_map(&p.amap[py * 2 + pxp], const_cast<char*>(base), 4, dims, strides, box);
+      }
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        const int t = r * k + c;
+        const int oy = r - d->pad, ox = c - d->pad;            // input offset relative to 2*o
+        const int py = ((oy % 2) + 2) % 2, pxp = ((ox % 2) + 2) % 2;
+        p.tap_map[t] = py * 2 + pxp;
+        p.tap_dy[t] = (oy - py) / 2;                           // exact: oy - py is even
+        p.tap_dx[t] = (ox - pxp) / 2;
+      }
+  }
+  if (rc == SMB_OK) rc = finish_plan(pl, d->Cout, k * k * d->Cin, weight);
+  if (rc != SMB_OK) { delete pl; return rc; }
+  *plan_out = pl;
+  return SMB_OK;
+}
+
+// 7x7/2 stem on the padded NHWC8 image written by smb_image_to_nhwc8:
+//   img8 [N, H+6, W+8, 8] fp16 (pixel (y,x) stored at (y+3, x+3)); K = 7 filter rows x (8 pixels x 8 ch).
+//   Output pixel (oy,ox), filter row r reads padded row 2*oy + r, pixels 2*ox .. 2*ox+7 (128 contiguous bytes).
+extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, const void* weight448, void* out,
+                                    smb_conv_plan_t** plan_out) {
+  SMB_CHECK_ARG(img_nhwc8 && weight448 && out && plan_out, "smb_stem_plan_create: null pointer");
+  SMB_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "smb_stem_plan_create: H, W must be even (images are padded to /32)");
+  smb_conv_plan* pl = new smb_conv_plan();
+  memset(&pl->p, 0, sizeof(ConvParams));
+  ConvParams& p = pl->p;
+  const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
+  p.n_img = N; p.H_out = Ho; p.W_out = Wo;
+  choose_patch(Ho, Wo, &p.BH, &p.BW);
+  p.tiles_x = cdiv(Wo, p.BW); p.tiles_y = cdiv(Ho, p.BH);
+  p.num_taps = 7; p.kb_per_tap = 1;
+  p.Cout = 64;
+  p.out = out; p.out_pitch = 64; p.out_f32 = 0; p.alpha = 1.f; p.relu = 1;
+  p.gn_group = 2;
+  pl->has_bias = 1;
+  const uint64_t rowb = (uint64_t)Wp * 16;
+  const uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+  int rc = SMB_OK;
+  for (int par = 0; par < 2 && rc == SMB_OK; ++par) {
+    const int rows = (Hp - par + 1) / 2;
+    uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)rows, (uint64_t)N};
+    uint64_t strides[3] = {32, rowb * 2, rowb * Hp};     // 2-pixel step along x: overlapping 8-pixel windows
+    rc = encode_map(&p.amap[par], (char*)const_cast<void*>(img_nhwc8) + par * rowb, 4, dims, strides, box);
+  }
+  p.amap[2] = p.amap[0]; p.amap[3] = p.amap[1];
+  for (int r = 0; r < 7; ++r) { p.tap_map[r] = r & 1; p.tap_dy[r] = r >> 1; p.tap_dx[r] = 0; }
+  if (rc == SMB_OK) rc = finish_plan(pl, 64, 448, weight448);
+  if (rc != SMB_OK) { delete pl; return rc; }
+  *plan_out = pl;
+  return SMB_OK;
+}
+
+extern "C" void smb_conv_plan_destroy(smb_conv_plan_t* plan) { delete plan; }
+
+extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, float* gn_stats,
+                            float alpha, smb_stream_t stream) {
+  SMB_CHECK_ARG(plan, "smb_conv_run: null plan");
+  SMB_CHECK_ARG(!plan->has_bias || bias, "smb_conv_run: plan expects a bias");
+  SMB_CHECK_ARG(!plan->has_residual || residual, "smb_conv_run: plan expects a residual");
+  SMB_CHECK_ARG(!plan->gn_stats || gn_stats, "smb_conv_run: plan expects a gn_stats buffer");
+  ConvParams p = plan->p;
+  p.bias = plan->has_bias ? bias : nullptr;
+  p.residual = plan->has_residual ? (const __half*)residual : nullptr;
+  if (!plan->has_residual) p.res_mode = 0;
+  p.gn_stats = plan->gn_stats ? gn_stats : nullptr;
+  p.alpha = alpha;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  conv_gemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, (cudaStream_t)stream>>>(p);
+  SMB_LAUNCH_OK("conv_gemm_kernel");
+  return SMB_OK;
+}

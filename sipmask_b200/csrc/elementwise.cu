@@ -1,0 +1,364 @@
+// Bandwidth-bound helper kernels around the tcgen05 convolution (all NHWC fp16 unless noted), sm_100a.
+//
+// Reference (SipMask-mmdetection/mmdet/):
+//   ops/norm.py:43-49 + ops/conv_module.py:124-132            GroupNorm(32) + ReLU after tower convs
+//   ops/dcn/src/deform_conv_cuda_kernel.cu:85-115,191-243      deformable im2col (bilinear gather)
+//   models/anchor_heads/sipmask_head.py:30-33,49-50            conv_offset 1x1 (4 -> 72, no bias)
+//   models/backbones/resnet.py:460                             MaxPool2d(3, 2, 1)
+//   models/anchor_heads/sipmask_head.py:279,285                F.interpolate(bilinear, align_corners=False)
+//   datasets/pipelines/formating.py ImageToTensor              NCHW fp32 input image
+// Every kernel moves 16-byte vectors (8 fp16 channels) per thread so that a warp covers whole 128-byte lines.
+#include "common.cuh"
+
+namespace smb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm
+// stats[(img*G + g)*2 + {0,1}] = {sum, sum of squares} over hw * (C/G) elements.
+__global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C, int pitch, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu) {
+  const int vecs = C >> 3;
+  const long long total = (long long)n_img * hw * vecs;
+  const int G = 32, cpg = C / G;
+  const float inv_cnt = 1.0f / ((float)hw * (float)cpg);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int v = (int)(t % vecs);
+    const long long row = t / vecs;
+    const int img = (int)(row / hw);
+    uint4* p = reinterpret_cast<uint4*>(x + row * pitch + v * 8);
+    float f[8];
+    unpack8(*p, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cpg;
+      const float s = stats[((size_t)img * G + g) * 2], ss = stats[((size_t)img * G + g) * 2 + 1];
+      const float mean = s * inv_cnt;
+      const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float y = (f[j] - mean) * rstd * gamma[c] + beta[c];
+      f[j] = relu ? fmaxf(y, 0.f) : y;
+    }
+    *p = pack8(f);
+  }
+}
+
+// One CTA handles `rows_per_cta` pixels of one image; thread -> (row lane, 8-channel vector).
+__global__ void gn_stats_kernel(const __half* __restrict__ x, int hw, int C, int pitch, int rows_per_cta,
+                                float* __restrict__ stats) {
+  __shared__ float s_sum[32], s_sq[32];
+  const int img = blockIdx.y;
+  const int vecs = C >> 3;
+  const int cpg = C / 32;
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int v = threadIdx.x % vecs;
+  const int rl = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(r0 + rows_per_cta, hw);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (rl < rstep) {
+    for (int r = r0 + rl; r < r1; r += rstep) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)img * hw + r) * pitch + v * 8));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (v * 8 + j) / cpg;
+      atomicAdd(&s_sum[g], s[j]);
+      atomicAdd(&s_sq[g], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(stats + ((size_t)img * 32 + threadIdx.x) * 2, s_sum[threadIdx.x]);
+    atomicAdd(stats + ((size_t)img * 32 + threadIdx.x) * 2 + 1, s_sq[threadIdx.x]);
+  }
+}
+
+// ------------------------------------------------------------------------- DCN offsets + deformable im2col
+// offset[pix, o] = sum_k W[o,k] * (bbox[pix,k] * scale)      (1x1 conv 4 -> dg*18, no bias)
+__global__ void offset_conv_kernel(const float* __restrict__ bbox, int bbox_pitch, float scale, const float* __restrict__ w,
+                                   int n_off, float* __restrict__ off, long long npix) {
+  const long long total = npix * n_off;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int o = (int)(t % n_off);
+    const long long pix = t / n_off;
+    const float* b = bbox + pix * bbox_pitch;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc = fmaf(__fmul_rn(b[k], scale), w[o * 4 + k], acc);
+    off[t] = acc;
+  }
+}
+
+// One warp per (pixel, tap): lanes cover the C/8 channel vectors (C <= 256 per pass).
+// col[pix, tap*C + c] = bilinear(x[:, :, c], h + i - 1 + dh, w + j - 1 + dw), zero outside (-1,H)x(-1,W)
+// with per-corner bounds exactly as deform_conv_cuda_kernel.cu:98-109,229.
+__global__ void deform_im2col_kernel(const __half* __restrict__ x, const float* __restrict__ off, int off_pitch,
+                                     __half* __restrict__ col, int n_img, int H, int W, int C, int dg) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = (long long)n_img * H * W * 9;
+  const int vecs = C >> 3;
+  const int cpg = C / dg;
+  for (long long wq = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); wq < total;
+       wq += (long long)gridDim.x * warps_per_block) {
+    const int tap = (int)(wq % 9);
+    const long long pix = wq / 9;
+    const int w_ = (int)(pix % W);
+    const int h_ = (int)((pix / W) % H);
+    const int img = (int)(pix / ((long long)W * H));
+    const int i = tap / 3, j = tap - i * 3;
+    const __half* xim = x + (size_t)img * H * W * C;
+    for (int v = lane; v < vecs; v += 32) {
+      const int g = (v * 8) / cpg;
+      const float* o = off + pix * off_pitch + g * 18 + 2 * tap;
+      const float h_im = (float)(h_ - 1 + i) + o[0];
+      const float w_im = (float)(w_ - 1 + j) + o[1];
+      float r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = 0.f;
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+        const int h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        float f[8];
+        if (h_low >= 0 && w_low >= 0) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_low * W + w_low) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] = w1 * f[e];
+        }
+        if (h_low >= 0 && w_high <= W - 1) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_low * W + w_high) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += w2 * f[e];
+        }
+        if (h_high <= H - 1 && w_low >= 0) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_high * W + w_low) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += w3 * f[e];
+        }
+        if (h_high <= H - 1 && w_high <= W - 1) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_high * W + w_high) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += w4 * f[e];
+        }
+      }
+      *reinterpret_cast<uint4*>(col + (size_t)pix * 9 * C + (size_t)tap * C + v * 8) = pack8(r);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------- max pool
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C, int Ho,
+                                    int Wo) {
+  const int vecs = C >> 3;
+  const long long total = (long long)N * Ho * Wo * vecs;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int v = (int)(t % vecs);
+    long long q = t / vecs;
+    const int ox = (int)(q % Wo); q /= Wo;
+    const int oy = (int)(q % Ho);
+    const int n = (int)(q / Ho);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = oy * 2 - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = ox * 2 - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + iy) * W + ix) * C + v * 8)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * C + v * 8) = pack8(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------ bilinear upsample
+// PyTorch upsample_bilinear2d, align_corners=False, scale_factor = factor (integer):
+//   src = max((dst + 0.5) / factor - 0.5, 0); i0 = (int)src; i1 = i0 + (i0 < in-1); l1 = src - i0
+__global__ void upsample_bilinear_kernel(const __half* __restrict__ x, int in_pitch, __half* __restrict__ y, int out_pitch,
+                                         int out_choff, int N, int H, int W, int C, int factor, int relu) {
+  const int vecs = C >> 3;
+  const int Ho = H * factor, Wo = W * factor;
+  const float rs = 1.0f / (float)factor;
+  const long long total = (long long)N * Ho * Wo * vecs;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int v = (int)(t % vecs);
+    long long q = t / vecs;
+    const int ox = (int)(q % Wo); q /= Wo;
+    const int oy = (int)(q % Ho);
+    const int n = (int)(q / Ho);
+    float sy = ((float)oy + 0.5f) * rs - 0.5f; sy = sy < 0.f ? 0.f : sy;
+    float sx = ((float)ox + 0.5f) * rs - 0.5f; sx = sx < 0.f ? 0.f : sx;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const __half* b = x + (size_t)n * H * W * in_pitch + v * 8;
+    float f00[8], f01[8], f10[8], f11[8], r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * W + x0) * in_pitch)), f00);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y0 * W + x1) * in_pitch)), f01);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x0) * in_pitch)), f10);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x1) * in_pitch)), f11);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float val = hy * (hx * f00[e] + lx * f01[e]) + ly * (hx * f10[e] + lx * f11[e]);
+      r[e] = relu ? fmaxf(val, 0.f) : val;
+    }
+    *reinterpret_cast<uint4*>(y + (((size_t)n * Ho + oy) * Wo + ox) * out_pitch + out_choff + v * 8) = pack8(r);
+  }
+}
+
+// plain strided copy of a channel block (level 0 of the prototype concat: torch.cat is a copy in the reference)
+__global__ void copy_channels_kernel(const __half* __restrict__ x, int in_pitch, __half* __restrict__ y, int out_pitch,
+                                     int out_choff, long long npix, int C) {
+  const int vecs = C >> 3;
+  const long long total = npix * vecs;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int v = (int)(t % vecs);
+    const long long pix = t / vecs;
+    *reinterpret_cast<uint4*>(y + pix * out_pitch + out_choff + v * 8) =
+        __ldg(reinterpret_cast<const uint4*>(x + pix * in_pitch + v * 8));
+  }
+}
+
+// --------------------------------------------------------------------------------------- image -> NHWC8
+// img [N,3,H,W] fp32 -> out [N, H+6, W+8, 8] fp16, pixel (y,x) at (y+3, x+3), zeros elsewhere / in ch 3..7.
+__global__ void image_to_nhwc8_kernel(const float* __restrict__ img, __half* __restrict__ out, int N, int H, int W) {
+  const int Hp = H + 6, Wp = W + 8;
+  const long long total = (long long)N * Hp * Wp;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int xp = (int)(t % Wp);
+    const int yp = (int)((t / Wp) % Hp);
+    const int n = (int)(t / ((long long)Wp * Hp));
+    const int x = xp - 3, y = yp - 3;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      const size_t plane = (size_t)H * W;
+      const float* p = img + (size_t)n * 3 * plane + (size_t)y * W + x;
+      f[0] = p[0]; f[1] = p[plane]; f[2] = p[2 * plane];
+    }
+    *reinterpret_cast<uint4*>(out + t * 8) = pack8(f);
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 32;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" int smb_groupnorm_relu_apply(void* x, int n_img, int hw, int C, int pitch, const float* stats, const float* gamma,
+                                        const float* beta, float eps, int relu, smb_stream_t stream) {
+  SMB_CHECK_ARG(x && stats && gamma && beta, "smb_groupnorm_relu_apply: null pointer");
+  SMB_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && pitch % 8 == 0 && hw > 0 && n_img > 0, "smb_groupnorm_relu_apply: bad shape");
+  const long long total = (long long)n_img * hw * (C / 8);
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, n_img, hw, C, pitch, stats, gamma, beta,
+                                                                          eps, relu);
+  SMB_LAUNCH_OK("gn_apply_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_groupnorm_stats(const void* x, int n_img, int hw, int C, int pitch, float* stats, smb_stream_t stream) {
+  SMB_CHECK_ARG(x && stats, "smb_groupnorm_stats: null pointer");
+  SMB_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C <= 2048 && pitch % 8 == 0 && hw > 0 && n_img > 0, "smb_groupnorm_stats: bad shape");
+  SMB_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * n_img * 64, (cudaStream_t)stream));
+  const int rows_per_cta = 64;
+  dim3 grid(cdiv(hw, rows_per_cta), n_img);
+  gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, hw, C, pitch, rows_per_cta, stats);
+  SMB_LAUNCH_OK("gn_stats_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_offset_conv1x1(const float* bbox, int bbox_pitch, float scale, const float* weight, int n_off, float* off,
+                                  long long npix, smb_stream_t stream) {
+  SMB_CHECK_ARG(bbox && weight && off && npix > 0 && n_off > 0, "smb_offset_conv1x1: bad argument");
+  offset_conv_kernel<<<grid_for(npix * n_off, 256), 256, 0, (cudaStream_t)stream>>>(bbox, bbox_pitch, scale, weight, n_off, off,
+                                                                                    npix);
+  SMB_LAUNCH_OK("offset_conv_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_deform_im2col(const void* x, const float* offset, int off_pitch, void* col, int n_img, int H, int W, int C,
+                                 int deformable_groups, smb_stream_t stream) {
+  SMB_CHECK_ARG(x && offset && col, "smb_deform_im2col: null pointer");
+  SMB_CHECK_ARG(C % 8 == 0 && deformable_groups > 0 && C % deformable_groups == 0 && (C / deformable_groups) % 8 == 0,
+                "smb_deform_im2col: C=%d dg=%d unsupported", C, deformable_groups);
+  const long long warps = (long long)n_img * H * W * 9;
+  deform_im2col_kernel<<<grid_for(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, offset, off_pitch,
+                                                                                    (__half*)col, n_img, H, W, C,
+                                                                                    deformable_groups);
+  SMB_LAUNCH_OK("deform_im2col_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, smb_stream_t stream) {
+  SMB_CHECK_ARG(x && y && C % 8 == 0, "smb_maxpool3x3s2: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, N, H, W, C, Ho, Wo);
+  SMB_LAUNCH_OK("maxpool3x3s2_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_upsample_bilinear(const void* x, int in_pitch, void* y, int out_pitch, int out_choff, int N, int H, int W,
+                                     int C, int factor, int relu, smb_stream_t stream) {
+  SMB_CHECK_ARG(x && y && C % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0 && out_choff % 8 == 0 && factor >= 1,
+                "smb_upsample_bilinear: bad argument");
+  if (factor == 1) {
+    const long long npix = (long long)N * H * W;
+    copy_channels_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, in_pitch, (__half*)y,
+                                                                                          out_pitch, out_choff, npix, C);
+    SMB_LAUNCH_OK("copy_channels_kernel");
+    return SMB_OK;
+  }
+  const long long total = (long long)N * H * factor * W * factor * (C / 8);
+  upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, in_pitch, (__half*)y,
+                                                                                   out_pitch, out_choff, N, H, W, C, factor, relu);
+  SMB_LAUNCH_OK("upsample_bilinear_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_image_to_nhwc8(const float* img, void* out, int N, int H, int W, smb_stream_t stream) {
+  SMB_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "smb_image_to_nhwc8: bad argument");
+  const long long total = (long long)N * (H + 6) * (W + 8);
+  image_to_nhwc8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)out, N, H, W);
+  SMB_LAUNCH_OK("image_to_nhwc8_kernel");
+  return SMB_OK;
+}

@@ -1,0 +1,303 @@
+// Fused SipMask mask assembly for sm_100a.
+//
+// Reference (SipMask-mmdetection/mmdet/):
+//   models/anchor_heads/sipmask_head.py:609-633   4x sgemm -> 4x sigmoid -> stack -> CropSplit -> permute
+//   ops/crop/src/crop_split_cuda_kernel.cu:19-59  CropSplitKernelForward
+// The reference materialises [4,H,W,N] sigmoid maps (~2.5 GB of HBM traffic for 142 MB of
+// algorithmic bytes).  Here one kernel reads every prototype pixel once into
+// registers, and for each detection evaluates only the ONE 32-term dot product selected by the
+// CropSplit cell of that pixel, and only for pixels inside the box; everything else is a zero store.
+// HBM-bound: algorithmic bytes = protos (H*W*32*sizeof) + out (N*H*W*sizeof).
+#include "common.cuh"
+
+namespace smb {
+
+struct __align__(16) BoxP {
+  float x1, y1, x2, y2, roi_w, roi_h, pad0, pad1;
+};
+
+constexpr int MA_THREADS = 128;
+constexpr int MA_TW = 64;   // tile width  (16 threads x 4 pixels)
+constexpr int MA_TH = 8;    // tile height
+constexpr int MA_NB = 64;   // detections per shared-memory chunk
+
+template <typename PT>
+__device__ __forceinline__ float to_f(PT v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename OT>
+__device__ __forceinline__ void store4(OT* p, const float* o, bool vec, int nvalid);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float* o, bool vec, int nvalid) {
+  if (vec) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+    for (int i = 0; i < nvalid; ++i) p[i] = o[i];
+  }
+}
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, const float* o, bool vec, int nvalid) {
+  if (vec) {
+    __half2 a = __floats2half2_rn(o[0], o[1]);
+    __half2 b = __floats2half2_rn(o[2], o[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else {
+    for (int i = 0; i < nvalid; ++i) p[i] = __float2half_rn(o[i]);
+  }
+}
+
+// grid: (ceil(W/64), ceil(H/8)), block 128.
+template <typename PT, bool HWC, typename OT>
+__global__ void __launch_bounds__(MA_THREADS) mask_assemble_kernel(
+    const PT* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes,
+    float sx1, float sy1, float sx2, float sy2, OT* __restrict__ out, int H, int W, int N) {
+  __shared__ __align__(16) float s_cof[MA_NB * 128];
+  __shared__ BoxP s_box[MA_NB];
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int h = blockIdx.y * MA_TH + ty;
+  const int w0 = blockIdx.x * MA_TW + tx * 4;
+  const bool row_ok = h < H;
+  const int nvalid = row_ok ? max(0, min(4, W - w0)) : 0;
+  const bool vec = (nvalid == 4) && ((W & 3) == 0);
+
+  // ---- prototype pixels -> registers (fp32), read exactly once
+  float P[4][32];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int k = 0; k < 32; ++k) P[p][k] = 0.f;
+  if (nvalid > 0) {
+    if (HWC) {
+      const PT* base = protos + ((size_t)h * W + w0) * 32;
+      if (sizeof(PT) == 2) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          if (p < nvalid) {
+            const uint4* q = reinterpret_cast<const uint4*>(base + p * 32);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint4 u = __ldg(q + v);
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(hh[e]);
+                P[p][v * 8 + e * 2] = f.x;
+                P[p][v * 8 + e * 2 + 1] = f.y;
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          if (p < nvalid) {
+            const float4* q = reinterpret_cast<const float4*>(base + p * 32);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              float4 f = __ldg(q + v);
+              P[p][v * 4] = f.x; P[p][v * 4 + 1] = f.y; P[p][v * 4 + 2] = f.z; P[p][v * 4 + 3] = f.w;
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const PT* q = protos + ((size_t)k * H + h) * W + w0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (p < nvalid) P[p][k] = to_f<PT>(q[p]);
+      }
+    }
+  }
+
+  const float hf = (float)h;
+  for (int n0 = 0; n0 < N; n0 += MA_NB) {
+    const int nb = min(MA_NB, N - n0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * 128; i += MA_THREADS) s_cof[i] = __ldg(cofs + (size_t)n0 * 128 + i);
+    if (threadIdx.x < nb) {
+      const float* b = boxes + (size_t)(n0 + threadIdx.x) * 4;
+      BoxP bp;
+      bp.x1 = b[0] * sx1; bp.y1 = b[1] * sy1; bp.x2 = b[2] * sx2; bp.y2 = b[3] * sy2;
+      // (roi_x2-roi_x1+0.1)/num_cell: float difference, then double (0.1 is a double literal),
+      // narrowed to float on assignment (crop_split_cuda_kernel.cu:46-47).
+      bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
+      bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
+      bp.pad0 = bp.pad1 = 0.f;
+      s_box[threadIdx.x] = bp;
+    }
+    __syncthreads();
+    if (nvalid == 0) continue;
+    for (int j = 0; j < nb; ++j) {
+      const BoxP b = s_box[j];
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      if ((hf >= b.y1) & (hf < b.y2)) {
+        const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float wf = (float)(w0 + p);
+          if ((wf >= b.x1) & (wf < b.x2)) {
+            const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
+            int cell = idx_h * 2 + idx_w;
+            cell = min(max(cell, 0), 3);
+            const float4* c4 = reinterpret_cast<const float4*>(s_cof + j * 128 + cell * 32);
+            float acc = 0.f;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 c = c4[v];
+              acc = fmaf(P[p][v * 4], c.x, acc);
+              acc = fmaf(P[p][v * 4 + 1], c.y, acc);
+              acc = fmaf(P[p][v * 4 + 2], c.z, acc);
+              acc = fmaf(P[p][v * 4 + 3], c.w, acc);
+            }
+            o[p] = sigmoidf_(acc);
+          }
+        }
+      }
+      store4<OT>(out + ((size_t)(n0 + j) * H + h) * W + w0, o, vec, nvalid);
+    }
+  }
+}
+
+// x2 bilinear (align_corners=False) + threshold, top-left paste into [N,out_h,out_w] uint8.
+// sipmask_head.py:630-633,648-654.  One thread = 4 consecutive output pixels of one row.
+template <typename PT>
+__global__ void __launch_bounds__(256) upsample2_thresh_kernel(const PT* __restrict__ pos, uint8_t* __restrict__ out,
+                                                               int N, int H, int W, int out_h, int out_w, float thr) {
+  const int xq = blockIdx.x * blockDim.x + threadIdx.x;   // quad index along x
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  const int x0 = xq * 4;
+  if (x0 >= out_w) return;
+  uint8_t r[4] = {0, 0, 0, 0};
+  if (y < 2 * H) {
+    float sy = ((float)y + 0.5f) * 0.5f - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    const int y0 = (int)sy;
+    const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, hy = 1.f - ly;
+    const PT* r0 = pos + ((size_t)n * H + y0) * W;
+    const PT* r1 = pos + ((size_t)n * H + y1) * W;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + i;
+      if (x < out_w && x < 2 * W) {
+        float sx = ((float)x + 0.5f) * 0.5f - 0.5f;
+        sx = sx < 0.f ? 0.f : sx;
+        const int xa = (int)sx;
+        const int xb = xa + (xa < W - 1 ? 1 : 0);
+        const float lx = sx - (float)xa, hx = 1.f - lx;
+        const float v = hy * (hx * to_f<PT>(r0[xa]) + lx * to_f<PT>(r0[xb])) +
+                        ly * (hx * to_f<PT>(r1[xa]) + lx * to_f<PT>(r1[xb]));
+        r[i] = v > thr ? 1 : 0;
+      }
+    }
+  }
+  uint8_t* o = out + ((size_t)n * out_h + y) * out_w + x0;
+  if (x0 + 3 < out_w && ((out_w & 3) == 0)) {
+    *reinterpret_cast<uchar4*>(o) = make_uchar4(r[0], r[1], r[2], r[3]);
+  } else {
+    for (int i = 0; i < 4 && x0 + i < out_w; ++i) o[i] = r[i];
+  }
+}
+
+// CropSplit operator (ops/crop/src/crop_split_cuda_kernel.cu:19-59), c == 2.
+template <typename T>
+__global__ void crop_split_kernel(const T* __restrict__ data, const T* __restrict__ rois, T* __restrict__ out,
+                                  long long count, int H, int W, int N) {
+  for (long long index = blockIdx.x * (long long)blockDim.x + threadIdx.x; index < count;
+       index += (long long)blockDim.x * gridDim.x) {
+    const int n = (int)(index % N);
+    const int pw = (int)((index / N) % W);
+    const int ph = (int)(index / N / W);
+    const float x1 = to_f<T>(rois[n * 4 + 0]), y1 = to_f<T>(rois[n * 4 + 1]);
+    const float x2 = to_f<T>(rois[n * 4 + 2]), y2 = to_f<T>(rois[n * 4 + 3]);
+    T v = T(0.f);
+    if (((float)pw >= x1) & ((float)ph >= y1) & ((float)pw < x2) & ((float)ph < y2)) {
+      const float roi_w = (float)(((double)(x2 - x1) + 0.1) / 2);
+      const float roi_h = (float)(((double)(y2 - y1) + 0.1) / 2);
+      const int idx_w = (int)__fdiv_rn((float)pw - x1, roi_w);
+      const int idx_h = (int)__fdiv_rn((float)ph - y1, roi_h);
+      const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
+      v = data[(long long)cell * count + index];
+    }
+    out[index] = v;
+  }
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layout_hwc, const float* cofs,
+                                 const float* boxes, const float* host_box_scale4, void* out, int out_dtype,
+                                 int H, int W, int N, smb_stream_t stream) {
+  SMB_CHECK_ARG(protos && cofs && boxes && out && host_box_scale4, "smb_mask_assemble: null pointer");
+  SMB_CHECK_ARG(H > 0 && W > 0 && N >= 0, "smb_mask_assemble: bad shape H=%d W=%d N=%d", H, W, N);
+  SMB_CHECK_ARG((protos_dtype == SMB_F32 || protos_dtype == SMB_F16) && (out_dtype == SMB_F32 || out_dtype == SMB_F16),
+                "smb_mask_assemble: bad dtype");
+  if (N == 0) return SMB_OK;
+  dim3 grid(cdiv(W, MA_TW), cdiv(H, MA_TH)), block(MA_THREADS);
+  const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
+  cudaStream_t st = (cudaStream_t)stream;
+#define MA_LAUNCH(PT, HWC, OT)                                                                             \
+  mask_assemble_kernel<PT, HWC, OT><<<grid, block, 0, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, \
+                                                            (OT*)out, H, W, N)
+  const int key = (protos_dtype << 2) | ((layout_hwc ? 1 : 0) << 1) | out_dtype;
+  switch (key) {
+    case 0: MA_LAUNCH(float, false, float); break;
+    case 1: MA_LAUNCH(float, false, __half); break;
+    case 2: MA_LAUNCH(float, true, float); break;
+    case 3: MA_LAUNCH(float, true, __half); break;
+    case 4: MA_LAUNCH(__half, false, float); break;
+    case 5: MA_LAUNCH(__half, false, __half); break;
+    case 6: MA_LAUNCH(__half, true, float); break;
+    case 7: MA_LAUNCH(__half, true, __half); break;
+  }
+#undef MA_LAUNCH
+  SMB_LAUNCH_OK("mask_assemble_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W,
+                                            int out_h, int out_w, float thr, smb_stream_t stream) {
+  SMB_CHECK_ARG(pos && out_u8, "smb_mask_upsample2_threshold: null pointer");
+  SMB_CHECK_ARG(N >= 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && out_h <= 65535 && N <= 65535,
+                "smb_mask_upsample2_threshold: bad shape");
+  if (N == 0) return SMB_OK;
+  dim3 block(256), grid(cdiv(cdiv(out_w, 4), 256), out_h, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pos_dtype == SMB_F32)
+    upsample2_thresh_kernel<float><<<grid, block, 0, st>>>((const float*)pos, out_u8, N, H, W, out_h, out_w, thr);
+  else
+    upsample2_thresh_kernel<__half><<<grid, block, 0, st>>>((const __half*)pos, out_u8, N, H, W, out_h, out_w, thr);
+  SMB_LAUNCH_OK("upsample2_thresh_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_crop_split_forward(const void* data, const void* rois, void* out, int dtype, int H, int W, int c,
+                                      int N, smb_stream_t stream) {
+  SMB_CHECK_ARG(data && rois && out, "smb_crop_split_forward: null pointer");
+  SMB_CHECK_ARG(c == 2, "smb_crop_split_forward: only c == 2 is used by SipMask (got %d)", c);
+  SMB_CHECK_ARG(H > 0 && W > 0 && N >= 0, "smb_crop_split_forward: bad shape");
+  const long long count = (long long)H * W * N;
+  if (count == 0) return SMB_OK;
+  const int blocks = (int)min((long long)148 * 16, (count + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMB_F32)
+    crop_split_kernel<float><<<blocks, 256, 0, st>>>((const float*)data, (const float*)rois, (float*)out, count, H, W, N);
+  else if (dtype == SMB_F16)
+    crop_split_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)data, (const __half*)rois, (__half*)out, count, H, W, N);
+  else
+    SMB_CHECK_ARG(false, "smb_crop_split_forward: bad dtype %d", dtype);
+  SMB_LAUNCH_OK("crop_split_kernel");
+  return SMB_OK;
+}

@@ -1,0 +1,233 @@
+"""Operator API of the hot path - same names / argument meaning as the reference's `mmdet.ops`
+and `mmdet.core` entry points, backed by the C ABI (PyTorch tensors in, PyTorch tensors out).
+
+  CropSplit / crop_split   <- MM/mmdet/ops/crop/crop_split.py:12-49
+  nms                      <- MM/mmdet/ops/nms/nms_wrapper.py:7-60
+  multiclass_nms_idx       <- MM/mmdet/core/post_processing/bbox_nms.py:79-146
+  fast_nms                 <- MM/mmdet/models/anchor_heads/sipmask_head.py:868-910
+  mask_assemble            <- MM/mmdet/models/anchor_heads/sipmask_head.py:609-627 (fused)
+All tensors must be CUDA tensors on an sm_100 device; there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.SmbError('sipmask_b200 ops need CUDA tensors (no CPU fallback); got %s' % t.device)
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return L.F32
+    if t.dtype == torch.float16:
+        return L.F16
+    raise L.SmbError('unsupported dtype %s' % t.dtype)
+
+
+# ------------------------------------------------------------------------------------------ CropSplit
+def crop_split(data, rois, c=2):
+    """data [c*c,H,W,N] contiguous, rois [N,4] -> [H,W,N] (ops/crop/crop_split.py:12-25)."""
+    _need_cuda(data, rois)
+    if not data.is_contiguous():
+        raise L.SmbError('input must be contiguous')       # AT_CHECK in crop_split_cuda.cpp:17
+    cc, H, W, N = data.shape
+    rois = rois.to(data.dtype).contiguous()
+    out = torch.empty((H, W, N), dtype=data.dtype, device=data.device)
+    L.check(L.lib().smb_crop_split_forward(L.ptr(data), L.ptr(rois), L.ptr(out), _dt(data), H, W, int(c), N,
+                                           L.stream_ptr()), 'smb_crop_split_forward')
+    return out
+
+
+class CropSplit(nn.Module):
+    def __init__(self, c=2):
+        super().__init__()
+        self.c = c
+
+    def forward(self, data, rois):
+        return crop_split(data, rois, self.c)
+
+
+# ------------------------------------------------------------------------------------------------ nms
+def nms(dets, iou_thr, device_id=None, cmp_ge=False):
+    """Same contract as mmdet.ops.nms: returns (dets[inds], inds); numpy in -> numpy out."""
+    is_numpy = isinstance(dets, np.ndarray)
+    if is_numpy:
+        dev = 'cuda:%d' % (device_id if device_id is not None else torch.cuda.current_device())
+        dets_th = torch.from_numpy(dets).to(dev)
+    elif isinstance(dets, torch.Tensor):
+        dets_th = dets
+    else:
+        raise TypeError('dets must be either a Tensor or numpy array, but got {}'.format(type(dets)))
+    _need_cuda(dets_th)
+    n = dets_th.shape[0]
+    if n == 0:
+        inds = dets_th.new_zeros(0, dtype=torch.long)
+    else:
+        d = dets_th.float().contiguous()
+        keep = torch.empty(n, dtype=torch.long, device=d.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=d.device)
+        L.check(L.lib().smb_nms(L.ptr(d), n, ctypes.c_float(iou_thr), int(cmp_ge), 1, L.ptr(keep), L.ptr(cnt),
+                                L.stream_ptr()), 'smb_nms')
+        inds = keep[:int(cnt.item())]
+    if is_numpy:
+        inds = inds.cpu().numpy()
+        return dets[inds, :], inds
+    return dets[inds, :], inds
+
+
+# ------------------------------------------------------------------------------------- decode + top-k
+def decode_topk(cls_list, box_list, ctr_list, strides, img_shape, nms_pre, scale_factor=None, box_scales=None):
+    """Per-level tensors channel-last fp32: cls [h,w,C], box [h,w,4] (distances x stride), ctr [h,w,1|].
+
+    Returns cand_boxes [n,4], cand_scores [n,C], cand_ctr [n], cand_loc [n] int32."""
+    nl = len(cls_list)
+    C = cls_list[0].shape[-1]
+    lv = (L.Level * nl)()
+    keep_alive = []
+    for i in range(nl):
+        c, b, t = cls_list[i], box_list[i], ctr_list[i]
+        _need_cuda(c, b, t)
+        assert c.dtype == torch.float32 and b.dtype == torch.float32 and t.dtype == torch.float32
+        assert c.stride(-1) == 1 and b.stride(-1) == 1
+        h, w = c.shape[0], c.shape[1]
+        assert c.stride(0) == w * c.stride(1) and b.stride(0) == w * b.stride(1)
+        t2 = t.reshape(h, w, -1)
+        assert t2.stride(0) == w * t2.stride(1)
+        keep_alive.append(t2)
+        bs, bm = (1.0, 1.0) if box_scales is None else (float(box_scales[i]), float(strides[i]))
+        lv[i] = L.Level(c.data_ptr(), t2.data_ptr(), b.data_ptr(), c.stride(1), t2.stride(1), b.stride(1), h, w,
+                        int(strides[i]), bs, bm)
+    lib = L.lib()
+    dev = cls_list[0].device
+    ws_bytes = lib.smb_decode_workspace_bytes(nl, lv, int(nms_pre))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    n = sum(min(c.shape[0] * c.shape[1], nms_pre) if nms_pre > 0 else c.shape[0] * c.shape[1] for c in cls_list)
+    boxes = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n, C), dtype=torch.float32, device=dev)
+    ctr = torch.empty((n,), dtype=torch.float32, device=dev)
+    loc = torch.empty((n,), dtype=torch.int32, device=dev)
+    sf = None
+    if scale_factor is not None:
+        a = np.atleast_1d(np.asarray(scale_factor, dtype=np.float32))
+        sf = L.f4(a if a.size == 4 else [a[0]] * 4)
+    L.check(lib.smb_decode_topk(nl, lv, C, int(nms_pre), int(img_shape[0]), int(img_shape[1]), sf, L.ptr(boxes),
+                                L.ptr(scores), L.ptr(ctr), L.ptr(loc), L.ptr(ws), ctypes.c_size_t(ws_bytes),
+                                L.stream_ptr()), 'smb_decode_topk')
+    return boxes, scores, ctr, loc
+
+
+# ------------------------------------------------------------------------------------ multi-class NMS
+def multiclass_nms_idx(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None,
+                       has_bg_column=True, cmp_ge=False, return_count_tensor=False):
+    """Same contract as mmdet.core.multiclass_nms_idx (bbox_nms.py:79-146): returns
+    (dets [k,5], labels [k] int64 0-based, idxs [k] int64).  `multi_scores` carries the background
+    column 0 like the reference unless has_bg_column=False."""
+    _need_cuda(multi_bboxes, multi_scores)
+    iou_thr = nms_cfg.get('iou_thr', 0.5) if isinstance(nms_cfg, dict) else float(nms_cfg)
+    scores = multi_scores[:, 1:] if has_bg_column else multi_scores
+    scores = scores.float().contiguous()
+    boxes = multi_bboxes.float().contiguous()
+    n, C = scores.shape
+    dev = boxes.device
+    if score_factors is None:
+        score_factors = torch.ones(n, dtype=torch.float32, device=dev)
+    ctr = score_factors.float().contiguous()
+    if max_num is None or max_num <= 0:
+        max_num = 1024
+    lib = L.lib()
+    ws_bytes = lib.smb_multiclass_nms_workspace_bytes(n, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    det = torch.empty((max_num, 5), dtype=torch.float32, device=dev)
+    lab = torch.empty((max_num,), dtype=torch.long, device=dev)
+    idx = torch.empty((max_num,), dtype=torch.long, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(lib.smb_multiclass_nms(L.ptr(boxes), L.ptr(scores), L.ptr(ctr), n, C, ctypes.c_float(score_thr),
+                                   ctypes.c_float(iou_thr), int(max_num), int(cmp_ge), L.ptr(det), L.ptr(lab),
+                                   L.ptr(idx), L.ptr(cnt), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream_ptr()),
+            'smb_multiclass_nms')
+    if return_count_tensor:
+        return det, lab, idx, cnt
+    k = int(cnt.item())
+    return det[:k], lab[:k], idx[:k]
+
+
+def fast_nms(boxes, scores, ctr, iou_threshold=0.5, top_k=200, score_thr=0.1, max_num=100,
+             return_count_tensor=False):
+    """boxes [n,4], scores [n,C] sigmoid (NOT yet multiplied by ctr), ctr [n].
+    Returns (dets [k,5], classes [k], idx [k]) like SipMaskHead.fast_nms (sipmask_head.py:868-910)
+    with the coefficient gather left to the caller (`cofs[idx]`)."""
+    _need_cuda(boxes, scores, ctr)
+    boxes = boxes.float().contiguous()
+    scores = scores.float().contiguous()
+    ctr = ctr.float().contiguous()
+    n, C = scores.shape
+    dev = boxes.device
+    lib = L.lib()
+    ws_bytes = lib.smb_fast_nms_workspace_bytes(n, C, int(top_k))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    det = torch.empty((max_num, 5), dtype=torch.float32, device=dev)
+    lab = torch.empty((max_num,), dtype=torch.long, device=dev)
+    idx = torch.empty((max_num,), dtype=torch.long, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(lib.smb_fast_nms(L.ptr(boxes), L.ptr(scores), L.ptr(ctr), n, C, ctypes.c_float(score_thr),
+                             ctypes.c_float(iou_threshold), int(top_k), int(max_num), L.ptr(det), L.ptr(lab),
+                             L.ptr(idx), L.ptr(cnt), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream_ptr()),
+            'smb_fast_nms')
+    if return_count_tensor:
+        return det, lab, idx, cnt
+    k = int(cnt.item())
+    return det[:k], lab[:k], idx[:k]
+
+
+def gather_rows(src, idx, count, max_rows):
+    """dst[i] = src[idx[i]] for i < count (device int32), zeros after; src [n,E] fp32 (row pitch = stride(0))."""
+    _need_cuda(src, idx, count)
+    assert src.dtype == torch.float32 and src.stride(1) == 1
+    E = src.shape[1]
+    dst = torch.empty((max_rows, E), dtype=torch.float32, device=src.device)
+    L.check(L.lib().smb_gather_rows_f32(L.ptr(src), src.stride(0), L.ptr(idx), L.ptr(count), int(max_rows), E,
+                                        L.ptr(dst), L.stream_ptr()), 'smb_gather_rows_f32')
+    return dst
+
+
+# -------------------------------------------------------------------------------------- mask assembly
+def mask_assemble(protos, cofs, boxes, box_scale, layout='chw', out_dtype=torch.float32, out=None):
+    """protos [32,H,W] ('chw') or [H,W,32] ('hwc'), fp32/fp16; cofs [N,128] fp32; boxes [N,4] fp32
+    (image space); rois = boxes * box_scale (scalar or 4-vector).  Returns pos_masks [N,H,W]."""
+    _need_cuda(protos, cofs, boxes)
+    protos = protos.contiguous()
+    if layout == 'chw':
+        _, H, W = protos.shape
+    else:
+        H, W, _ = protos.shape
+    N = cofs.shape[0]
+    cofs = cofs.float().contiguous()
+    boxes = boxes.float().contiguous()
+    a = np.atleast_1d(np.asarray(box_scale, dtype=np.float32))
+    bs = L.f4(a if a.size == 4 else [a[0]] * 4)
+    if out is None:
+        out = torch.empty((N, H, W), dtype=out_dtype, device=protos.device)
+    L.check(L.lib().smb_mask_assemble(L.ptr(protos), _dt(protos), 1 if layout == 'hwc' else 0, L.ptr(cofs),
+                                      L.ptr(boxes), bs, L.ptr(out), _dt(out), H, W, N, L.stream_ptr()),
+            'smb_mask_assemble')
+    return out
+
+
+def mask_upsample2_threshold(pos, out_hw, thr=0.4, out=None):
+    """pos [N,H,W] -> uint8 [N,out_h,out_w]: x2 bilinear (align_corners=False), > thr, top-left paste."""
+    _need_cuda(pos)
+    pos = pos.contiguous()
+    N, H, W = pos.shape
+    if out is None:
+        out = torch.empty((N, int(out_hw[0]), int(out_hw[1])), dtype=torch.uint8, device=pos.device)
+    L.check(L.lib().smb_mask_upsample2_threshold(L.ptr(pos), _dt(pos), L.ptr(out), N, H, W, int(out_hw[0]),
+                                                 int(out_hw[1]), ctypes.c_float(thr), L.stream_ptr()),
+            'smb_mask_upsample2_threshold')
+    return out

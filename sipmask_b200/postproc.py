@@ -1,0 +1,57 @@
+"""Device-side `get_bboxes_single` (decode -> NMS -> coefficient gather -> mask assembly -> x2 upsample/threshold).
+
+Mirrors MM/mmdet/models/anchor_heads/sipmask_head.py:543-662 with every step on the GPU and no host
+synchronisation until the caller reads the fixed-shape result record:
+    det_bboxes [max,5] f32, det_labels [max] i64, count i32, masks [max,H,W] u8.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _cl(t):
+    """CHW (reference layout) or HWC tensor -> channel-last contiguous fp32 [h,w,C]."""
+    return t.float().permute(1, 2, 0).contiguous()
+
+
+def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides, img_shape, ori_shape,
+                      scale_factor, cfg, rescale=False, ssd_flag=False, cmp_ge=False, mask_thr=0.4,
+                      channel_last=False, feat_mask_layout='chw', box_scales=None, top_k=200, upsample=True):
+    """Inputs per level: CHW tensors like the reference (channel_last=False) or [h,w,C] fp32 views.
+    cfg: dict with nms_pre, score_thr, nms.iou_thr, max_per_img."""
+    if not channel_last:
+        cls_scores = [_cl(t) for t in cls_scores]
+        bbox_preds = [_cl(t) for t in bbox_preds]
+        centernesses = [_cl(t) for t in centernesses]
+        cof_preds = [_cl(t) for t in cof_preds]
+    nms_pre = cfg.get('nms_pre', -1)
+    max_num = int(cfg.get('max_per_img', 100))
+    sf = np.atleast_1d(np.asarray(scale_factor, dtype=np.float32))
+    boxes, scores, ctr, loc = ops.decode_topk(cls_scores, bbox_preds, centernesses, strides, img_shape, nms_pre,
+                                              scale_factor=(sf if rescale else None), box_scales=box_scales)
+    iou_thr = cfg['nms']['iou_thr'] if isinstance(cfg['nms'], dict) else cfg['nms'].iou_thr
+    if not ssd_flag:
+        det, lab, idx, cnt = ops.multiclass_nms_idx(boxes, scores, cfg['score_thr'], dict(iou_thr=iou_thr), max_num,
+                                                    score_factors=ctr, has_bg_column=False, cmp_ge=cmp_ge,
+                                                    return_count_tensor=True)
+    else:
+        max_num = 100                                    # hard-coded in fast_nms (sipmask_head.py:903)
+        det, lab, idx, cnt = ops.fast_nms(boxes, scores, ctr, iou_thr, top_k, cfg['score_thr'], max_num,
+                                          return_count_tensor=True)
+    # coefficient gather for the kept rows only: loc -> level-concatenated location -> cof row
+    cof_all = torch.cat([c.reshape(-1, c.shape[-1]) for c in cof_preds], 0) if len(cof_preds) > 1 else \
+        cof_preds[0].reshape(-1, cof_preds[0].shape[-1])
+    loc_kept = loc.long()[idx.clamp(min=0)]
+    det_cofs = ops.gather_rows(cof_all, loc_kept, cnt, max_num)
+    # rois = det * scale_factor / 2 (sipmask_head.py:621-623); scale_factor := 1 when rescale is None
+    s4 = (sf if sf.size == 4 else np.repeat(sf, 4)).astype(np.float32)
+    if rescale is None:
+        s4 = np.ones(4, np.float32)
+    box_scale = s4 / 2.0
+    pos = ops.mask_assemble(feat_mask, det_cofs, det[:, :4].contiguous(), box_scale, layout=feat_mask_layout)
+    out = dict(det_bboxes=det, det_labels=lab, idxs_keep=idx, count=cnt, pos_masks=pos, masks=None)
+    if upsample:
+        tgt = ori_shape if rescale else img_shape
+        out['masks'] = ops.mask_upsample2_threshold(pos, (int(tgt[0]), int(tgt[1])), mask_thr)
+    return out

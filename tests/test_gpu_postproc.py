@@ -1,0 +1,192 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA post-processing kernels, called through the
+C ABI, against the CPU oracle on the same seeded inputs and against the reference-generated fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import ops as O
+    from oracle import postproc as P
+    from oracle import cbind
+    return O, P, cbind
+
+
+def _rand_dets(n, seed, size=200.0):
+    rng = np.random.RandomState(seed)
+    xy = rng.rand(n, 2) * size
+    wh = rng.rand(n, 2) * size * 0.4 + 1
+    return np.concatenate([xy, xy + wh, rng.rand(n, 1)], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize('n', [1, 5, 63, 64, 65, 300, 1000, 4097, 8192])
+@pytest.mark.parametrize('cmp_ge', [False, True])
+def test_nms_matches_oracle(n, cmp_ge):
+    from sipmask_b200 import ops
+    O, P, cbind = _oracle()
+    dets = _rand_dets(n, n, size=60.0 if n > 1000 else 200.0)
+    keep_ref = cbind.nms(dets, 0.5, int(cmp_ge))
+    d, inds = ops.nms(torch.from_numpy(dets).cuda(), 0.5, cmp_ge=cmp_ge)
+    assert inds.dtype == torch.long
+    assert inds.cpu().numpy().tolist() == keep_ref.tolist()
+    np.testing.assert_array_equal(d.cpu().numpy(), dets[keep_ref])
+
+
+def test_nms_known_answers(golden_dir):
+    from sipmask_b200 import ops
+    g = np.load(os.path.join(golden_dir, 'nms_known_answers.npz'))
+    d, inds = ops.nms(g['mm4_dets'], float(g['mm4_thr']), device_id=0)        # numpy in -> numpy out
+    assert isinstance(inds, np.ndarray) and len(inds) == int(g['mm4_num_keep']) and inds.tolist() == [0, 2, 3]
+    d, inds = ops.nms(g['mm7_dets'], float(g['mm7_thr']), device_id=0)
+    assert len(inds) == int(g['mm7_num_keep'])
+    d, inds = ops.nms(torch.zeros(0, 5).cuda(), 0.5)
+    assert inds.numel() == 0
+
+
+def test_nms_ties_are_stable():
+    from sipmask_b200 import ops
+    O, P, cbind = _oracle()
+    dets = _rand_dets(500, 7, size=80.0)
+    dets[:, 4] = np.round(dets[:, 4] * 4) / 4          # many exact score ties
+    keep_ref = cbind.nms(dets, 0.4, 0)
+    _, inds = ops.nms(torch.from_numpy(dets).cuda(), 0.4)
+    assert inds.cpu().tolist() == keep_ref.tolist()
+
+
+@pytest.mark.parametrize('seed,n,C,thr,max_num', [(0, 3350, 80, 0.05, 100), (1, 500, 80, 0.05, 100), (2, 200, 5, 0.3, 1000),
+                                                  (3, 64, 80, 0.9999, 100), (4, 4096, 3, 0.05, 10)])
+def test_multiclass_nms_matches_oracle(seed, n, C, thr, max_num):
+    from sipmask_b200 import ops
+    O, P, cbind = _oracle()
+    g = torch.Generator().manual_seed(seed)
+    dets = _rand_dets(n, seed, size=400.0)
+    boxes = torch.from_numpy(dets[:, :4].copy())
+    scores = torch.sigmoid(torch.randn(n, C, generator=g) * 2 - 4)
+    ctr = torch.sigmoid(torch.randn(n, generator=g))
+    bg = torch.cat([scores.new_zeros(n, 1), scores], 1)
+    rb, rl, ri = O.multiclass_nms_idx(boxes, bg, thr, 0.5, max_num, score_factors=ctr)
+    db, dl, di = ops.multiclass_nms_idx(boxes.cuda(), bg.cuda(), thr, dict(type='nms', iou_thr=0.5), max_num,
+                                        score_factors=ctr.cuda())
+    assert dl.cpu().tolist() == rl.tolist()
+    assert di.cpu().tolist() == ri.tolist()
+    np.testing.assert_array_equal(db.cpu().numpy(), rb.numpy())
+
+
+@pytest.mark.parametrize('seed,n,C', [(0, 2395, 80), (1, 300, 40), (2, 150, 3)])
+def test_fast_nms_matches_oracle(seed, n, C):
+    from sipmask_b200 import ops
+    O, P, cbind = _oracle()
+    g = torch.Generator().manual_seed(seed)
+    dets = _rand_dets(n, seed + 10, size=300.0)
+    boxes = torch.from_numpy(dets[:, :4].copy())
+    scores = torch.sigmoid(torch.randn(n, C, generator=g) * 2 - 2)
+    ctr = torch.sigmoid(torch.randn(n, generator=g))
+    cofs = torch.randn(n, 128, generator=g)
+    s = (scores * ctr.view(-1, 1)).transpose(1, 0).contiguous()
+    rb, rl, rc, ri = O.fast_nms(boxes, s, cofs, 0.5, 200, 0.1, 100)
+    db, dl, di = ops.fast_nms(boxes.cuda(), scores.cuda(), ctr.cuda(), 0.5, 200, 0.1, 100)
+    assert dl.cpu().tolist() == rl.tolist()
+    assert di.cpu().tolist() == ri.tolist()
+    np.testing.assert_array_equal(db.cpu().numpy(), rb.numpy())
+
+
+@pytest.mark.parametrize('sizes,img_shape,nms_pre', [
+    ([(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)], (800, 1333), 1000),
+    ([(12, 16), (6, 8), (3, 4), (2, 2), (1, 1)], (96, 125), 60)])
+def test_decode_topk_matches_oracle(sizes, img_shape, nms_pre):
+    from sipmask_b200 import ops, synth
+    O, P, cbind = _oracle()
+    strides = (8, 16, 32, 64, 128)
+    cls, box, ctr, cof = synth.head_level_inputs(sizes, seed=3)
+    rb, rs, rc, rcof, ridx = P.decode_candidates(cls, box, ctr, cof, strides, img_shape + (3,), nms_pre)
+    cl = [c.permute(1, 2, 0).contiguous().cuda() for c in cls]
+    bl = [b.permute(1, 2, 0).contiguous().cuda() for b in box]
+    tl = [t.permute(1, 2, 0).contiguous().cuda() for t in ctr]
+    db, ds, dc, dloc = ops.decode_topk(cl, bl, tl, strides, img_shape, nms_pre, scale_factor=1.0)
+    assert dloc.cpu().tolist() == ridx.tolist()                       # bit-exact candidate selection and order
+    np.testing.assert_array_equal(db.cpu().numpy(), rb.numpy())        # box arithmetic is exact
+    np.testing.assert_allclose(ds.cpu().numpy(), rs.numpy(), rtol=2e-6, atol=1e-7)   # sigmoid: expf vs torch CPU
+    np.testing.assert_allclose(dc.cpu().numpy(), rc.numpy(), rtol=2e-6, atol=1e-7)
+
+
+def _iou(a, b):
+    inter = np.logical_and(a, b).sum((1, 2)).astype(np.float64)
+    union = np.logical_or(a, b).sum((1, 2)).astype(np.float64)
+    return (inter + 1e-9) / (union + 1e-9)
+
+
+@pytest.mark.parametrize('H,W,N,layout,dtype', [(100, 168, 17, 'chw', torch.float32), (100, 168, 17, 'hwc', torch.float16),
+                                                (37, 53, 5, 'chw', torch.float16), (37, 53, 70, 'hwc', torch.float32),
+                                                (400, 672, 100, 'hwc', torch.float16)])
+def test_mask_assemble_matches_oracle(H, W, N, layout, dtype):
+    from sipmask_b200 import ops, synth
+    O, P, cbind = _oracle()
+    g = torch.Generator().manual_seed(H + N)
+    protos = synth.prototypes(H, W, seed=N)
+    protos_in = protos.to(dtype)
+    cofs = torch.randn(N, 128, generator=g)
+    cx = torch.rand(N, generator=g) * W * 2
+    cy = torch.rand(N, generator=g) * H * 2
+    bw = torch.rand(N, generator=g) * W * 1.2 + 2
+    bh = torch.rand(N, generator=g) * H * 1.2 + 2
+    boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1).clamp(min=0)
+    boxes[0] = torch.tensor([0.0, 0.0, 2.0 * W, 2.0 * H])              # whole image
+    ref = cbind.mask_assemble(protos_in.float().numpy(), cofs.numpy(), (boxes * 0.5).numpy())
+    p_dev = (protos_in if layout == 'chw' else protos_in.permute(1, 2, 0)).contiguous().cuda()
+    out = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float32)
+    got = out.cpu().numpy()
+    assert ((got == 0) == (ref == 0)).all()                              # crop geometry is exact
+    np.testing.assert_allclose(got, ref, atol=3e-6 if dtype == torch.float32 else 3e-6, rtol=0)
+    # x2 upsample + threshold
+    m_ref = cbind.upsample2_thresh(ref, 0.4)
+    m_dev = ops.mask_upsample2_threshold(out, (2 * H - 3, 2 * W - 1), 0.4).cpu().numpy()
+    assert _iou(m_dev, m_ref[:, :2 * H - 3, :2 * W - 1]).min() >= 0.999
+    # fp16 output variant
+    out16 = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float16)
+    np.testing.assert_allclose(out16.float().cpu().numpy(), ref, atol=1e-3, rtol=0)
+
+
+def test_crop_split_operator_matches_oracle():
+    from sipmask_b200 import ops
+    O, P, cbind = _oracle()
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand(4, 40, 56, 9, generator=g)
+    rois = torch.tensor([[3.2, 4.1, 30.7, 35.2], [0, 0, 56, 40], [10, 10, 10.5, 10.5], [-5, -5, 20, 20], [50, 30, 80, 90],
+                         [7, 3, 8, 39], [0.5, 0.5, 1.5, 1.5], [20, 20, 19, 19], [55, 39, 56, 40]])
+    ref = O.crop_split(data, rois, 2)
+    got = ops.CropSplit(2)(data.cuda(), rois.cuda())
+    np.testing.assert_array_equal(got.cpu().numpy(), ref.numpy())
+    with pytest.raises(Exception):
+        ops.crop_split(data.cuda().permute(0, 2, 1, 3), rois.cuda())       # non-contiguous input raises
+
+
+@pytest.mark.parametrize('name', ['ref_head_gn4.npz', 'ref_head_ssd2.npz'])
+def test_postproc_reproduces_reference_fixture(golden_dir, name):
+    """Head outputs captured from the unmodified reference python -> device post-processing must give the
+    reference's detections (labels / kept boxes bit-exact, masks IoU >= 0.999)."""
+    from sipmask_b200 import postproc
+    g = dict(np.load(os.path.join(golden_dir, name)))
+    nl = len(g['sizes'])
+    ssd = bool(g['ssd_flag'])
+    cfg = dict(nms_pre=int(g['nms_pre']), score_thr=float(g['score_thr']), nms=dict(type='nms', iou_thr=0.5),
+               max_per_img=int(g['max_per_img']))
+    sf = g['scale_factor']
+    sf = float(sf[0]) if sf.size == 1 else sf
+    res = postproc.get_bboxes_single(
+        [torch.from_numpy(g['cls%d' % i][0]).cuda() for i in range(nl)],
+        [torch.from_numpy(g['bbox%d' % i][0]).cuda() for i in range(nl)],
+        [torch.from_numpy(g['ctr%d' % i][0]).cuda() for i in range(nl)],
+        [torch.from_numpy(g['cof%d' % i][0]).cuda() for i in range(nl)],
+        torch.from_numpy(g['feat_masks'][0]).cuda(), (8, 16, 32, 64, 128),
+        tuple(g['img_shape']), tuple(g['img_shape']), sf, cfg, rescale=True, ssd_flag=ssd,
+        cmp_ge=True)    # the fixture was produced on CPU -> nms_cpu.cpp comparator (>=)
+    k = int(res['count'])
+    assert res['det_labels'][:k].cpu().tolist() == g['det_labels'].tolist()
+    np.testing.assert_allclose(res['det_bboxes'][:k].cpu().numpy(), g['det_bboxes'], rtol=1e-6, atol=1e-6)
+    masks = res['masks'][:k].cpu().numpy()
+    assert masks.shape == g['masks'].shape
+    assert _iou(masks, g['masks']).min() >= 0.999
