@@ -64,6 +64,10 @@ int smb_mask_assemble(const void* protos, int protos_dtype, int layout_hwc,
 int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W,
                                  int out_h, int out_w, float thr, smb_stream_t stream);
 
+/* Bit-packed variant: out_bits [N,out_h,ceil(out_w/32)] uint32, pixel x = bit (x & 31) of word (x >> 5). */
+int smb_mask_upsample2_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
+                                      int out_h, int out_w, float thr, smb_stream_t stream);
+
 /* ------------------------------------------------------------------ CropSplit (operator API)
  * Replaces crop_split_cuda.crop_split_cuda_forward(data, rois, out, H, W, c, n)
  * (ops/crop/src/crop_split_cuda.cpp:14-36).  data [c*c,H,W,N], rois [N,4], out [H,W,N]; c == 2.

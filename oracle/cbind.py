@@ -50,3 +50,12 @@ def upsample2_thresh(pos, thr):
     out = np.zeros((N, 2 * H, 2 * W), np.uint8)
     lib().oracle_upsample2_thresh(_p(pos, ctypes.c_float), N, H, W, ctypes.c_float(thr), _p(out, ctypes.c_uint8))
     return out
+
+
+def crop_split(data, rois):
+    data = np.ascontiguousarray(data, np.float32)
+    rois = np.ascontiguousarray(rois, np.float32)
+    _, H, W, N = data.shape
+    out = np.zeros((H, W, N), np.float32)
+    lib().oracle_crop_split(_p(data, ctypes.c_float), _p(rois, ctypes.c_float), H, W, N, _p(out, ctypes.c_float))
+    return out

@@ -101,3 +101,33 @@ void oracle_upsample2_thresh(const float* in, int N, int H, int W, float thr, ui
       }
     }
 }
+
+/* CropSplit forward, c == 2 (ops/crop/src/crop_split_cuda_kernel.cu:19-59).
+ * data [4,H,W,N], rois [N,4], out [H,W,N] (zero outside the boxes, crop_split.py:22). */
+void oracle_crop_split(const float* data, const float* rois, int H, int W, int N, float* out) {
+  const size_t count = (size_t)H * W * N;
+  float* rw = (float*)malloc(sizeof(float) * N);
+  float* rh = (float*)malloc(sizeof(float) * N);
+  for (int n = 0; n < N; ++n) {
+    rw[n] = (float)(((double)(rois[n * 4 + 2] - rois[n * 4 + 0]) + 0.1) / 2);
+    rh[n] = (float)(((double)(rois[n * 4 + 3] - rois[n * 4 + 1]) + 0.1) / 2);
+  }
+  for (int ph = 0; ph < H; ++ph)
+    for (int pw = 0; pw < W; ++pw) {
+      const size_t base = ((size_t)ph * W + pw) * N;
+      for (int n = 0; n < N; ++n) {
+        const float x1 = rois[n * 4 + 0], y1 = rois[n * 4 + 1], x2 = rois[n * 4 + 2], y2 = rois[n * 4 + 3];
+        float v = 0.f;
+        if (((float)pw >= x1) & ((float)ph >= y1) & ((float)pw < x2) & ((float)ph < y2)) {
+          int idx_w = (int)(((float)pw - x1) / rw[n]);
+          int idx_h = (int)(((float)ph - y1) / rh[n]);
+          int cell = idx_h * 2 + idx_w;
+          if (cell < 0) cell = 0;
+          if (cell > 3) cell = 3;
+          v = data[(size_t)cell * count + base + n];
+        }
+        out[base + n] = v;
+      }
+    }
+  free(rw); free(rh);
+}

@@ -67,9 +67,17 @@ def deform_im2col(x, offset, kh, kw, stride, pad, dil, deformable_groups):
     return cols.view(B, C * kh * kw, Ho * Wo), Ho, Wo
 
 
+USE_C_CROP_SPLIT = False      # bench.py's CPU baseline: C restatement (oracle/csrc/oracle_c.c) instead of numpy
+USE_TORCHVISION_DCN = False   # bench.py's CPU baseline flips this: same arithmetic (tests/test_oracle_golden.py
+                              # ::test_deform_conv_matches_torchvision), C++ speed instead of python gathers
+
+
 def deform_conv(x, offset, weight, stride=1, padding=1, dilation=1, deformable_groups=1):
     """DeformConv forward, groups=1, no bias (MM/mmdet/ops/dcn/deform_conv.py:192-255)."""
     Cout, Cin, kh, kw = weight.shape
+    if USE_TORCHVISION_DCN and x.size(2) >= kh and x.size(3) >= kw:
+        from torchvision.ops import deform_conv2d
+        return deform_conv2d(x, offset, weight, stride=stride, padding=padding, dilation=dilation)
     # inputs smaller than the kernel are zero-padded first (deform_conv.py:242-254)
     pad_h = max(kh - x.size(2), 0)
     pad_w = max(kw - x.size(3), 0)
@@ -96,6 +104,9 @@ def crop_split(data, rois, c=2):
     (0.1 is a double literal, kernel.cu:46-47)."""
     cc, H, W, N = data.shape
     assert cc == c * c
+    if USE_C_CROP_SPLIT and c == 2:
+        from . import cbind
+        return torch.from_numpy(cbind.crop_split(data.detach().cpu().numpy(), rois.detach().cpu().numpy()))
     d = data.detach().cpu().numpy().astype(np.float32)
     r = rois.detach().cpu().numpy().astype(np.float32)
     x1, y1, x2, y2 = r[:, 0], r[:, 1], r[:, 2], r[:, 3]

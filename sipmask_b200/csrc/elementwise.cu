@@ -243,14 +243,20 @@ __global__ void upsample_bilinear_kernel(const __half* __restrict__ x, int in_pi
 
 // plain strided copy of a channel block (level 0 of the prototype concat: torch.cat is a copy in the reference)
 __global__ void copy_channels_kernel(const __half* __restrict__ x, int in_pitch, __half* __restrict__ y, int out_pitch,
-                                     int out_choff, long long npix, int C) {
+                                     int out_choff, long long npix, int C, int relu) {
   const int vecs = C >> 3;
   const long long total = npix * vecs;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
     const int v = (int)(t % vecs);
     const long long pix = t / vecs;
-    *reinterpret_cast<uint4*>(y + pix * out_pitch + out_choff + v * 8) =
-        __ldg(reinterpret_cast<const uint4*>(x + pix * in_pitch + v * 8));
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * in_pitch + v * 8));
+    if (relu) {
+      __half2* h = reinterpret_cast<__half2*>(&u);
+      const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+    }
+    *reinterpret_cast<uint4*>(y + pix * out_pitch + out_choff + v * 8) = u;
   }
 }
 
@@ -344,7 +350,7 @@ extern "C" int smb_upsample_bilinear(const void* x, int in_pitch, void* y, int o
   if (factor == 1) {
     const long long npix = (long long)N * H * W;
     copy_channels_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, in_pitch, (__half*)y,
-                                                                                          out_pitch, out_choff, npix, C);
+                                                                                          out_pitch, out_choff, npix, C, relu);
     SMB_LAUNCH_OK("copy_channels_kernel");
     return SMB_OK;
   }

@@ -1,0 +1,363 @@
+"""SipMask inference engine: the whole per-image hot path as a fixed sequence of sm_100a kernel launches.
+
+    image (NCHW fp32) -> NHWC8 fp16 -> ResNet-50/101 (caffe, folded BN) -> FPN P3..P7 -> FCOS towers (conv+GN+ReLU)
+    -> FeatureAlign (DCN) -> cls/centerness/reg/coefficient heads -> prototype branch -> decode/top-k -> NMS ->
+    mask assembly -> x2 upsample + threshold (bit-packed)
+
+Reference call stack replaced (SipMask-mmdetection/mmdet/): detectors/single_stage.py:75-93,
+backbones/resnet.py:501-512, necks/fpn.py:138-178, anchor_heads/sipmask_head.py:241-287,500-662.
+Weights come from a reference-keyed state_dict; all buffers are allocated once, TMA descriptors
+are baked into per-layer plans, and the launch sequence can be replayed as one CUDA graph.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import conv as C
+from . import ops
+
+ARCH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
+
+
+class SipMaskEngine(object):
+    def __init__(self, state_dict, img_hw, batch=1, depth=50, stacked_convs=4, gn=True, ssd_flag=False, num_classes=81,
+                 strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
+                 mask_thr=0.4, use_graph=True, pos_dtype=torch.float16):
+        L.check(L.lib().smb_check_device(), 'smb_check_device')
+        self.dev = torch.device(device)
+        self.N, (self.H, self.W) = batch, img_hw
+        assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
+        assert self.H % 32 == 0 and self.W % 32 == 0, 'images are padded to a multiple of 32 (Pad size_divisor=32)'
+        self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
+        self.ncls = num_classes - 1
+        self.strides = tuple(strides)
+        self.cfg = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
+        if test_cfg:
+            self.cfg.update(test_cfg)
+        self.img_shape = tuple(img_shape) if img_shape is not None else (self.H, self.W, 3)
+        self.scale_factor = scale_factor
+        self.mask_thr = mask_thr
+        self.pos_dtype = pos_dtype
+        self.sd = {k: v for k, v in state_dict.items()}
+        self.ops = []            # list of zero-argument callables = the launch sequence
+        self.n_launch = 0
+        self._keep = []
+        self._wcache = {}
+        self.conv_plans = []
+        self.conv_flops = 0.0
+        self._build()
+        self.graph = None
+        self.use_graph = use_graph
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _t(self, *shape, dtype=torch.float16, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.dev)
+        self._keep.append(t)
+        return t
+
+    def _w(self, key):
+        return self.sd[key].detach().float()
+
+    def _bn(self, prefix):
+        return (self._w(prefix + '.weight'), self._w(prefix + '.bias'), self._w(prefix + '.running_mean'),
+                self._w(prefix + '.running_var'))
+
+    def _add(self, fn, launches=1):
+        self.ops.append(fn)
+        self.n_launch += launches
+
+    def _conv(self, x, wkey, k, stride=1, relu=False, bn=None, bias_key=None, residual=None, residual_upsample=False,
+              gn_stats=None, out=None, out_dtype=torch.float16, cout_pad=None, weight=None, bias=None, cin=None,
+              cout_real=None):
+        if weight is None:
+            ck = (wkey, bn, bias_key, cout_pad)
+            if ck not in self._wcache:           # tower weights are shared by the five pyramid levels
+                weight, b = C.pack_weight(self._w(wkey), bn=self._bn(bn) if bn else None, cout_pad=cout_pad, device=self.dev)
+                if bias_key is not None:
+                    b = self._w(bias_key)
+                    if cout_pad and cout_pad != b.numel():
+                        b = torch.cat([b, b.new_zeros(cout_pad - b.numel())])
+                    b = b.to(self.dev).contiguous()
+                self._wcache[ck] = (weight, b)
+            weight, bias = self._wcache[ck]
+        N, H, W, _ = x.shape
+        Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+        if out is None:
+            out = self._t(N, Ho, Wo, weight.shape[0], dtype=out_dtype)
+        plan = C.ConvPlan(x, weight, out, k, stride, relu=relu, bias=bias, residual=residual,
+                          residual_upsample=residual_upsample, gn_stats=gn_stats, cin=cin)
+        self._keep.append(plan)
+        self.conv_plans.append(plan)
+        self.conv_flops += 2.0 * N * Ho * Wo * (cout_real or weight.shape[0]) * weight.shape[1]   # algorithmic FLOPs
+        self._add(plan.run)
+        return out
+
+    # -------------------------------------------------------------------------------------------- build
+    def _build(self):
+        N, H, W = self.N, self.H, self.W
+        self.img = self._t(N, 3, H, W, dtype=torch.float32)
+        # ---- stem
+        img8 = self._t(N, H + 6, W + 8, 8)
+        self._add(lambda: C.image_to_nhwc8(self.img, img8))
+        wk, b = C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'), device=self.dev)
+        s1 = self._t(N, H // 2, W // 2, 64)
+        stem = C.StemPlan(img8, wk, b, s1, N, H, W)
+        self._keep += [stem, wk, b]
+        self.conv_plans.append(stem)
+        self.conv_flops += 2.0 * N * (H // 2) * (W // 2) * 64 * 147                   # algorithmic 7x7x3 (executed K is 448)
+        self._add(stem.run)
+        x = self._t(N, H // 4, W // 4, 64)
+        self._add(lambda s1=s1, x=x: C.maxpool3x3s2(s1, x))
+        # ---- residual stages (caffe style: stride on conv1, resnet.py:125-130)
+        feats = []
+        for i, nb in enumerate(ARCH[self.depth]):
+            for j in range(nb):
+                p = 'backbone.layer%d.%d.' % (i + 1, j)
+                stride = 2 if (j == 0 and i > 0) else 1
+                t1 = self._conv(x, p + 'conv1.weight', 1, stride, relu=True, bn=p + 'bn1')
+                t2 = self._conv(t1, p + 'conv2.weight', 3, 1, relu=True, bn=p + 'bn2')
+                if j == 0:
+                    idn = self._conv(x, p + 'downsample.0.weight', 1, stride, relu=False, bn=p + 'downsample.1')
+                else:
+                    idn = x
+                x = self._conv(t2, p + 'conv3.weight', 1, 1, relu=True, bn=p + 'bn3', residual=idn)
+            feats.append(x)
+        c3, c4, c5 = feats[1], feats[2], feats[3]
+        # ---- FPN (fpn.py:138-178): laterals top-down with the nearest-upsample add fused into the epilogue
+        lat5 = self._conv(c5, 'neck.lateral_convs.2.conv.weight', 1, bias_key='neck.lateral_convs.2.conv.bias')
+        lat4 = self._conv(c4, 'neck.lateral_convs.1.conv.weight', 1, bias_key='neck.lateral_convs.1.conv.bias',
+                          residual=lat5, residual_upsample=True)
+        lat3 = self._conv(c3, 'neck.lateral_convs.0.conv.weight', 1, bias_key='neck.lateral_convs.0.conv.bias',
+                          residual=lat4, residual_upsample=True)
+        p3 = self._conv(lat3, 'neck.fpn_convs.0.conv.weight', 3, bias_key='neck.fpn_convs.0.conv.bias')
+        p4 = self._conv(lat4, 'neck.fpn_convs.1.conv.weight', 3, bias_key='neck.fpn_convs.1.conv.bias')
+        p5 = self._conv(lat5, 'neck.fpn_convs.2.conv.weight', 3, bias_key='neck.fpn_convs.2.conv.bias')
+        p6 = self._conv(p5, 'neck.fpn_convs.3.conv.weight', 3, 2, bias_key='neck.fpn_convs.3.conv.bias')
+        p6r = self._t(*p6.shape)
+        self._add(lambda: C.upsample_bilinear(p6, 1, out=p6r, relu=True))          # F.relu(outs[-1]) (fpn.py:175)
+        p7 = self._conv(p6r, 'neck.fpn_convs.4.conv.weight', 3, 2, bias_key='neck.fpn_convs.4.conv.bias')
+        self.fpn_outs = [p3, p4, p5, p6, p7]
+        self._build_head(self.fpn_outs)
+
+    def _tower_conv(self, x, wkey, gn_prefix, bias_key, stats):
+        """ConvModule: conv3x3 -> GN(32) -> ReLU (conv_module.py:124-132); GN statistics come out of the GEMM epilogue."""
+        if self.gn:
+            y = self._conv(x, wkey, 3, gn_stats=stats)
+            gamma = self._w(gn_prefix + '.weight').to(self.dev)
+            beta = self._w(gn_prefix + '.bias').to(self.dev)
+            self._keep += [gamma, beta]
+            self._add(lambda: C.groupnorm_relu_apply(y, stats, gamma, beta, 1e-5, True))
+            return y
+        return self._conv(x, wkey, 3, relu=True, bias_key=bias_key)
+
+    def _build_head(self, feats):
+        N = self.N
+        hp = 'bbox_head.'
+        sizes = [(f.shape[1], f.shape[2]) for f in feats]
+        self.level_sizes = sizes
+        tot = sum(h * w for h, w in sizes)
+        nl = len(feats)
+        n_tower = (self.stacked - 1) + self.stacked + 1
+        # one fp32 statistics arena for every (level, conv) GroupNorm, zeroed once per forward
+        self.gn_arena = self._t(nl * n_tower, N, 32, 2, dtype=torch.float32, zero=True)
+        self._add(lambda: self.gn_arena.zero_(), 0)
+        # shared (across levels) packed weights
+        ncls, CC = self.ncls, self.ncls + 128
+        CCp = (CC + 15) // 16 * 16
+        w_cls = torch.cat([self._w(hp + 'fcos_cls.weight'), self._w(hp + 'sip_cof.weight')], 0)
+        b_cls = torch.cat([self._w(hp + 'fcos_cls.bias'), self._w(hp + 'sip_cof.bias')], 0)
+        wk_cls, _ = C.pack_weight(w_cls, cout_pad=CCp, device=self.dev)
+        b_cls = torch.cat([b_cls, b_cls.new_zeros(CCp - CC)]).to(self.dev)
+        w_reg = torch.cat([self._w(hp + 'fcos_reg.weight'), self._w(hp + 'fcos_centerness.weight')], 0)
+        b_reg = torch.cat([self._w(hp + 'fcos_reg.bias'), self._w(hp + 'fcos_centerness.bias')], 0)
+        wk_reg, _ = C.pack_weight(w_reg, cout_pad=16, device=self.dev)
+        b_reg = torch.cat([b_reg, b_reg.new_zeros(16 - 5)]).to(self.dev)
+        wk_dcn, _ = C.pack_weight(self._w(hp + 'feat_align.conv_adaption.weight'), device=self.dev)
+        w_off = self._w(hp + 'feat_align.conv_offset.weight').view(72, 4).contiguous().to(self.dev)
+        self._keep += [wk_cls, b_cls, wk_reg, b_reg, wk_dcn, w_off]
+        self.scales = [float(self._w(hp + 'scales.%d.scale' % i)) for i in range(nl)]
+        # level-concatenated fp32 head outputs (channel-last): [tot, 80+128] and [tot, 16 = 4 reg | 1 ctr | pad]
+        self.clscof = self._t(N, tot, CCp, dtype=torch.float32)
+        self.regctr = self._t(N, tot, 16, dtype=torch.float32)
+        h3, w3 = sizes[0]
+        cat = self._t(N, h3, w3, 768)
+        off0 = 0
+        si = 0
+        self.level_views = []
+        for l, x in enumerate(feats):
+            h, w = sizes[l]
+            cls_feat, reg_feat = x, x
+            for i in range(self.stacked - 1):
+                cls_feat = self._tower_conv(cls_feat, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
+                                            hp + 'cls_convs.%d.conv.bias' % i, self.gn_arena[si])
+                si += 1
+            for i in range(self.stacked):
+                reg_feat = self._tower_conv(reg_feat, hp + 'reg_convs.%d.conv.weight' % i, hp + 'reg_convs.%d.gn' % i,
+                                            hp + 'reg_convs.%d.conv.bias' % i, self.gn_arena[si])
+                si += 1
+            # fcos_reg | fcos_centerness on the reg tower (sipmask_head.py:261,265), raw fp32 (Scale applied by consumers)
+            regctr_l = self.regctr[:, off0:off0 + h * w].view(N, h, w, 16)
+            self._conv(reg_feat, None, 3, weight=wk_reg, bias=b_reg, out=regctr_l, cout_real=5)
+            # FeatureAlign: offsets from scale*fcos_reg, DCN 3x3 dg=4, GN, ReLU (sipmask_head.py:49-55)
+            off = self._t(N, h, w, 72, dtype=torch.float32)
+            sc = self.scales[l]
+            self._add(lambda regctr_l=regctr_l, sc=sc, off=off: C.offset_conv1x1(regctr_l, sc, w_off, off))
+            col = self._t(N, h, w, 2304)
+            self._add(lambda cls_feat=cls_feat, off=off, col=col: C.deform_im2col(cls_feat, off, 4, col))
+            if self.gn:
+                stats = self.gn_arena[si]
+                si += 1
+                aligned = self._conv(col, None, 1, weight=wk_dcn, gn_stats=stats)
+                gamma = self._w(hp + 'feat_align.norm.weight').to(self.dev)
+                beta = self._w(hp + 'feat_align.norm.bias').to(self.dev)
+                self._keep += [gamma, beta]
+                self._add(lambda aligned=aligned, stats=stats, gamma=gamma, beta=beta:
+                          C.groupnorm_relu_apply(aligned, stats, gamma, beta, 1e-5, True))
+            else:
+                aligned = self._conv(col, None, 1, weight=wk_dcn, relu=True)
+            # fcos_cls | sip_cof on the aligned feature (sipmask_head.py:264,271)
+            clscof_l = self.clscof[:, off0:off0 + h * w].view(N, h, w, CCp)
+            self._conv(aligned, None, 3, weight=wk_cls, bias=b_cls, out=clscof_l)
+            if l < 3:   # prototype input: reg feature of levels 0..2 at P3 resolution (sipmask_head.py:275-281)
+                self._add(lambda reg_feat=reg_feat, l=l: C.upsample_bilinear(reg_feat, 2 ** l, out=cat, out_choff=256 * l))
+            self.level_views.append((clscof_l, regctr_l))
+            off0 += h * w
+        # prototype branch (sipmask_head.py:283-285)
+        m0 = self._conv(cat, hp + 'sip_mask_lat0.weight', 1, relu=True, bias_key=hp + 'sip_mask_lat0.bias')
+        m1 = self._conv(m0, hp + 'sip_mask_lat.weight', 3, relu=True, bias_key=hp + 'sip_mask_lat.bias')
+        self.protos = self._t(N, 4 * h3, 4 * w3, 32)
+        self._add(lambda: C.upsample_bilinear(m1, 4, out=self.protos))
+        self._build_postproc()
+
+    # ------------------------------------------------------------------------------- post-processing
+    def _build_postproc(self):
+        """decode -> NMS -> coefficient gather -> mask assembly -> x2 upsample/threshold/bit-pack, image by image
+        (get_bboxes loops over images, sipmask_head.py:517-540), all on device with fixed-shape outputs."""
+        N, dev = self.N, self.dev
+        cfg = self.cfg
+        nl = len(self.level_sizes)
+        CCp = self.clscof.shape[-1]
+        ncls = self.ncls
+        nms_pre = int(cfg['nms_pre'])
+        self.max_num = 100 if self.ssd else int(cfg['max_per_img'])
+        ncand = sum(min(h * w, nms_pre) if nms_pre > 0 else h * w for h, w in self.level_sizes)
+        self.ncand = ncand
+        lib = L.lib()
+        sf = np.atleast_1d(np.asarray(self.scale_factor, dtype=np.float32))
+        s4 = (sf if sf.size == 4 else np.repeat(sf, 4)).astype(np.float32)
+        self._sf4 = L.f4(s4)
+        self._box_scale4 = L.f4(s4 / 2.0)
+        Hm, Wm = self.protos.shape[1], self.protos.shape[2]
+        oh, ow = int(self.img_shape[0]), int(self.img_shape[1])        # rescale=True, ori_shape == img_shape / scale
+        self.mask_hw = (oh, ow)
+        words = (ow + 31) // 32
+        self.det = self._t(N, self.max_num, 5, dtype=torch.float32)
+        self.labels = self._t(N, self.max_num, dtype=torch.long)
+        self.idx = self._t(N, self.max_num, dtype=torch.long)
+        self.count = self._t(N, dtype=torch.int32, zero=True)
+        self.mask_bits = self._t(N, self.max_num, oh, words, dtype=torch.int32)
+        self.pos = self._t(N, self.max_num, Hm, Wm, dtype=self.pos_dtype)
+        self.cand_boxes = self._t(N, ncand, 4, dtype=torch.float32)
+        self.cand_scores = self._t(N, ncand, ncls, dtype=torch.float32)
+        self.cand_ctr = self._t(N, ncand, dtype=torch.float32)
+        self.cand_loc = self._t(N, ncand, dtype=torch.int32)
+        self.loc_kept = self._t(N, self.max_num, dtype=torch.long)
+        self.det_cofs = self._t(N, self.max_num, 128, dtype=torch.float32)
+        self.det_boxes4 = self._t(N, self.max_num, 4, dtype=torch.float32)
+        for n in range(N):
+            lv = (L.Level * nl)()
+            off0 = 0
+            for l, (h, w) in enumerate(self.level_sizes):
+                cc = self.clscof[n, off0:off0 + h * w]
+                rc = self.regctr[n, off0:off0 + h * w]
+                lv[l] = L.Level(cc.data_ptr(), rc.data_ptr() + 4 * 4, rc.data_ptr(), CCp, 16, 16, h, w, int(self.strides[l]),
+                                float(self.scales[l]), float(self.strides[l]))
+                off0 += h * w
+            ws_bytes = lib.smb_decode_workspace_bytes(nl, lv, nms_pre)
+            ws = self._t(ws_bytes, dtype=torch.uint8)
+            self._keep.append(lv)
+
+            def decode(n=n, lv=lv, ws=ws, ws_bytes=ws_bytes):
+                L.check(lib.smb_decode_topk(nl, lv, ncls, nms_pre, int(self.img_shape[0]), int(self.img_shape[1]), self._sf4,
+                                            L.ptr(self.cand_boxes[n]), L.ptr(self.cand_scores[n]), L.ptr(self.cand_ctr[n]),
+                                            L.ptr(self.cand_loc[n]), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream_ptr()),
+                        'smb_decode_topk')
+            self._add(decode, 3)
+            iou_thr = float(cfg['nms']['iou_thr'])
+            if not self.ssd:
+                nws_bytes = lib.smb_multiclass_nms_workspace_bytes(ncand, ncls)
+                nws = self._t(nws_bytes, dtype=torch.uint8)
+
+                def nms(n=n, nws=nws, nws_bytes=nws_bytes):
+                    L.check(lib.smb_multiclass_nms(L.ptr(self.cand_boxes[n]), L.ptr(self.cand_scores[n]), L.ptr(self.cand_ctr[n]),
+                                                   ncand, ncls, ctypes.c_float(cfg['score_thr']), ctypes.c_float(iou_thr),
+                                                   self.max_num, 0, L.ptr(self.det[n]), L.ptr(self.labels[n]), L.ptr(self.idx[n]),
+                                                   L.ptr(self.count[n:n + 1]), L.ptr(nws), ctypes.c_size_t(nws_bytes),
+                                                   L.stream_ptr()), 'smb_multiclass_nms')
+            else:
+                nws_bytes = lib.smb_fast_nms_workspace_bytes(ncand, ncls, 200)
+                nws = self._t(nws_bytes, dtype=torch.uint8)
+
+                def nms(n=n, nws=nws, nws_bytes=nws_bytes):
+                    L.check(lib.smb_fast_nms(L.ptr(self.cand_boxes[n]), L.ptr(self.cand_scores[n]), L.ptr(self.cand_ctr[n]), ncand,
+                                             ncls, ctypes.c_float(cfg['score_thr']), ctypes.c_float(iou_thr), 200, self.max_num,
+                                             L.ptr(self.det[n]), L.ptr(self.labels[n]), L.ptr(self.idx[n]),
+                                             L.ptr(self.count[n:n + 1]), L.ptr(nws), ctypes.c_size_t(nws_bytes), L.stream_ptr()),
+                            'smb_fast_nms')
+            self._add(nms, 2)
+            cof_src = self.clscof[n][:, ncls:ncls + 128]                       # [tot,128] view, pitch CCp
+
+            def gather(n=n, cof_src=cof_src):
+                # candidate row -> level-concatenated location -> coefficient row (mlvl_cofs[idxs_keep], sipmask_head.py:612)
+                torch.index_select(self.cand_loc[n].long(), 0, self.idx[n].clamp(min=0), out=self.loc_kept[n])
+                L.check(lib.smb_gather_rows_f32(L.ptr(cof_src), CCp, L.ptr(self.loc_kept[n]), L.ptr(self.count[n:n + 1]),
+                                                self.max_num, 128, L.ptr(self.det_cofs[n]), L.stream_ptr()), 'smb_gather_rows_f32')
+                self.det_boxes4[n].copy_(self.det[n][:, :4])
+            self._add(gather, 1)
+
+            def masks(n=n):
+                L.check(lib.smb_mask_assemble(L.ptr(self.protos[n]), L.F16, 1, L.ptr(self.det_cofs[n]), L.ptr(self.det_boxes4[n]),
+                                              self._box_scale4, L.ptr(self.pos[n]), L.F16 if self.pos_dtype == torch.float16 else L.F32,
+                                              Hm, Wm, self.max_num, L.stream_ptr()), 'smb_mask_assemble')
+                L.check(lib.smb_mask_upsample2_threshold_pack(L.ptr(self.pos[n]), L.F16 if self.pos_dtype == torch.float16 else L.F32,
+                                                              L.ptr(self.mask_bits[n]), self.max_num, Hm, Wm, oh, ow,
+                                                              ctypes.c_float(self.mask_thr), L.stream_ptr()),
+                        'smb_mask_upsample2_threshold_pack')
+            self._add(masks, 2)
+
+    # ---------------------------------------------------------------------------------------------- run
+    def _run_ops(self):
+        for f in self.ops:
+            f()
+
+    def forward(self, img=None):
+        """img: NCHW fp32 CUDA tensor (or None to reuse the resident input).  Returns the device result record."""
+        if img is not None:
+            self.img.copy_(img, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                self._run_ops()                      # warm-up: cudaFuncSetAttribute etc. must not happen under capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_ops()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._run_ops()
+        return dict(det_bboxes=self.det, det_labels=self.labels, count=self.count, mask_bits=self.mask_bits,
+                    idxs_keep=self.idx)
+
+    # head outputs in the reference's layout (for parity tests / the drop-in head)
+    def head_outputs(self):
+        outs = dict(cls=[], bbox=[], ctr=[], cof=[])
+        ncls = self.ncls
+        for l, (cc, rc) in enumerate(self.level_views):
+            outs['cls'].append(cc[..., :ncls].permute(0, 3, 1, 2))
+            outs['cof'].append(cc[..., ncls:ncls + 128].permute(0, 3, 1, 2))
+            outs['bbox'].append((rc[..., :4] * self.scales[l]).permute(0, 3, 1, 2) * self.strides[l])
+            outs['ctr'].append(rc[..., 4:5].permute(0, 3, 1, 2))
+        outs['feat_masks'] = self.protos.permute(0, 3, 1, 2)
+        return outs

@@ -231,3 +231,26 @@ def mask_upsample2_threshold(pos, out_hw, thr=0.4, out=None):
                                                  int(out_hw[1]), ctypes.c_float(thr), L.stream_ptr()),
             'smb_mask_upsample2_threshold')
     return out
+
+
+def mask_upsample2_threshold_pack(pos, out_hw, thr=0.4, out=None):
+    """Bit-packed masks: int32 [N,out_h,ceil(out_w/32)], pixel x = bit (x & 31) of word (x >> 5)."""
+    _need_cuda(pos)
+    pos = pos.contiguous()
+    N, H, W = pos.shape
+    words = (int(out_hw[1]) + 31) // 32
+    if out is None:
+        out = torch.empty((N, int(out_hw[0]), words), dtype=torch.int32, device=pos.device)
+    L.check(L.lib().smb_mask_upsample2_threshold_pack(L.ptr(pos), _dt(pos), L.ptr(out), N, H, W, int(out_hw[0]),
+                                                      int(out_hw[1]), ctypes.c_float(thr), L.stream_ptr()),
+            'smb_mask_upsample2_threshold_pack')
+    return out
+
+
+def unpack_mask_bits(bits, out_w):
+    """int32 [N,h,words] -> uint8 [N,h,out_w] (host or device tensor); used by tests and result conversion."""
+    b = bits.view(torch.uint8) if bits.dtype == torch.int32 else bits
+    b = b.reshape(bits.shape[0], bits.shape[1], -1)                     # little-endian bytes
+    sh = torch.arange(8, device=b.device, dtype=torch.uint8)
+    px = ((b.unsqueeze(-1) >> sh) & 1).reshape(b.shape[0], b.shape[1], -1)
+    return px[:, :, :out_w].contiguous()

@@ -1,0 +1,91 @@
+"""End-to-end parity of the engine against the fp32 CPU oracle on the same seeded weights and image (-m gpu).
+
+Tolerances (stated per BASELINE.json north_star):
+  * head outputs (fp16 storage / fp32 accumulate through ~70 conv layers vs fp32 oracle): relative L2 error <= 2e-2
+  * post-processing given the engine's own head outputs: kept indices / labels bit-exact vs the oracle run on the
+    same head outputs; masks IoU >= 0.999."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope='module')
+def small_case():
+    from oracle import model as M
+    from sipmask_b200 import synth
+    from sipmask_b200.engine import SipMaskEngine
+    H, W = 128, 192
+    sd = synth.detector_state_dict(depth=50, seed=1, cls_bias=-2.5)
+    img = synth.synthetic_image(H, W, seed=0)
+    net = M.SipMaskDetector(50)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    with torch.no_grad():
+        feats = net.extract_feat(img)
+        ref = net.bbox_head(feats)
+    cfg = dict(nms_pre=200, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=30)
+    eng = SipMaskEngine(sd, (H, W), test_cfg=cfg, img_shape=(H, W - 5, 3), use_graph=False)
+    out = eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    return dict(eng=eng, out=out, ref=ref, feats=feats, cfg=cfg, img=img, sd=sd, H=H, W=W)
+
+
+def test_backbone_fpn_parity(small_case):
+    eng, feats = small_case['eng'], small_case['feats']
+    for l, (p, r) in enumerate(zip(eng.fpn_outs, feats)):
+        e = _rel(p.float().cpu().permute(0, 3, 1, 2), r)
+        assert e < 1e-2, 'FPN level %d rel err %g' % (l, e)
+
+
+def test_head_outputs_parity(small_case):
+    eng, ref = small_case['eng'], small_case['ref']
+    ho = eng.head_outputs()
+    cls, bbox, ctr, cof, fm = ref
+    for l in range(5):
+        assert _rel(ho['cls'][l].cpu(), cls[l]) < 2e-2, l
+        assert _rel(ho['bbox'][l].cpu(), bbox[l]) < 2e-2, l
+        assert _rel(ho['cof'][l].cpu(), cof[l]) < 2e-2, l
+        assert (ho['ctr'][l].cpu() - ctr[l]).abs().max().item() < 5e-2 * (ctr[l].abs().max().item() + 1), l
+    assert _rel(ho['feat_masks'].float().cpu(), fm) < 2e-2
+
+
+def test_postproc_bit_exact_given_engine_head_outputs(small_case):
+    from oracle import postproc as P
+    from sipmask_b200 import ops
+    eng, out, cfg, H, W = small_case['eng'], small_case['out'], small_case['cfg'], small_case['H'], small_case['W']
+    ho = eng.head_outputs()
+    img_shape = (H, W - 5, 3)
+    res = P.get_bboxes_single([t[0].cpu() for t in ho['cls']], [t[0].cpu() for t in ho['bbox']],
+                              [t[0].cpu() for t in ho['ctr']], [t[0].cpu() for t in ho['cof']],
+                              ho['feat_masks'][0].float().cpu(), eng.strides, img_shape, img_shape, 1.0, cfg, rescale=True)
+    k = int(out['count'][0])
+    assert k == res['det_bboxes'].shape[0] and k > 0
+    assert out['det_labels'][0, :k].cpu().tolist() == res['det_labels'].tolist()
+    assert out['idxs_keep'][0, :k].cpu().tolist() == res['idxs_keep'].tolist()
+    np.testing.assert_allclose(out['det_bboxes'][0, :k].cpu().numpy(), res['det_bboxes'].numpy(), rtol=1e-5, atol=1e-5)
+    masks = ops.unpack_mask_bits(out['mask_bits'][0, :k].cpu(), img_shape[1]).numpy().astype(bool)
+    ref = res['masks'].astype(bool)
+    iou = (np.logical_and(masks, ref).sum((1, 2)) + 1e-9) / (np.logical_or(masks, ref).sum((1, 2)) + 1e-9)
+    assert iou.min() >= 0.999, iou
+
+
+def test_graph_replay_matches_eager(small_case):
+    from sipmask_b200.engine import SipMaskEngine
+    sd, cfg, H, W, img = small_case['sd'], small_case['cfg'], small_case['H'], small_case['W'], small_case['img']
+    eng = SipMaskEngine(sd, (H, W), test_cfg=cfg, img_shape=(H, W - 5, 3), use_graph=True)
+    a = eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    first = {k: v.clone() for k, v in a.items()}
+    b = eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    ref = small_case['out']
+    for k in ('det_labels', 'count', 'idxs_keep', 'mask_bits'):
+        assert torch.equal(first[k], b[k]), k
+        assert torch.equal(b[k], ref[k]), k

@@ -73,6 +73,8 @@ def test_c_oracle_matches_numpy():
     pos, masks = P.assemble_masks(protos, cofs, boxes, torch.tensor([1.0]), 2.0, 0.4)
     c_pos = cbind.mask_assemble(protos.numpy(), cofs.numpy(), boxes.numpy())
     np.testing.assert_allclose(c_pos, pos.numpy(), atol=2e-6)
+    stack = torch.rand(4, 20, 28, 5)
+    np.testing.assert_array_equal(cbind.crop_split(stack.numpy(), (boxes * 0.5).numpy()), O.crop_split(stack, boxes * 0.5).numpy())
     c_masks = cbind.upsample2_thresh(c_pos, 0.4)
     assert (c_masks != masks.numpy()).mean() < 1e-3
 
