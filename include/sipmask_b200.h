@@ -160,7 +160,8 @@ typedef struct {
   int residual_upsample;     /* residual is the coarser FPN level: nearest-neighbour gather (fpn.py:149-152) */
   int res_h, res_w;          /* residual spatial size when residual_upsample */
   int out_dtype;             /* SMB_F16 or SMB_F32 */
-  int gn_stats;              /* accumulate per-(image,group) sum / sumsq (32 groups) into stats[N*32*2] */
+  int gn_stats;              /* accumulate per-(image,group) {sum*2^20, sumsq*2^16} as int64 fixed point into stats[N*32*2]
+                                (integer atomics: bit-reproducible run to run) */
   int in_pitch, out_pitch;   /* channel pitch (elements) of input / output rows; 0 = dense */
 } smb_conv_desc_t;
 
@@ -169,16 +170,16 @@ int smb_conv_plan_create(const smb_conv_desc_t* desc, const void* in, const void
 void smb_conv_plan_destroy(smb_conv_plan_t* plan);
 /* out = relu?( (acc + bias) * alpha + residual ); alpha carries the per-level `Scale` of fcos_reg
  * (sipmask_head.py:261, ops/scale.py:12-15). */
-int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, float* gn_stats,
+int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, void* gn_stats,
                  float alpha, smb_stream_t stream);
 
 /* ------------------------------------------------------------------ elementwise / gather kernels (NHWC fp16) */
 /* GroupNorm(32 groups, eps) + ReLU applied in place from precomputed per-(image,group) sum/sumsq
  * (ops/norm.py:43-49 + conv_module.py:124-132).  x [N*HW, C] fp16. */
-int smb_groupnorm_relu_apply(void* x, int n_img, int hw, int C, int pitch, const float* stats,
+int smb_groupnorm_relu_apply(void* x, int n_img, int hw, int C, int pitch, const void* stats /* int64 [n_img*32*2] */,
                              const float* gamma, const float* beta, float eps, int relu, smb_stream_t stream);
 /* stats for a tensor that did not come out of smb_conv_run (e.g. DCN output computed elsewhere). */
-int smb_groupnorm_stats(const void* x, int n_img, int hw, int C, int pitch, float* stats, smb_stream_t stream);
+int smb_groupnorm_stats(const void* x, int n_img, int hw, int C, int pitch, void* stats /* int64 */, smb_stream_t stream);
 
 /* Deformable im2col (ops/dcn/src/deform_conv_cuda_kernel.cu:85-115,191-243), channel-last:
  *   x [H,W,C] fp16, offset [H,W,dg*18] fp32 (per dg: 2*(i*3+j)=dh, +1=dw) with pitch off_pitch

@@ -137,7 +137,7 @@ def maxpool3x3s2(x, out=None):
 def groupnorm_stats(x, stats=None):
     N, H, W, C = x.shape
     if stats is None:
-        stats = torch.empty((N, 32, 2), dtype=torch.float32, device=x.device)
+        stats = torch.empty((N, 32, 2), dtype=torch.int64, device=x.device)
     L.check(L.lib().smb_groupnorm_stats(L.ptr(x), N, H * W, C, x.stride(2), L.ptr(stats), L.stream_ptr()),
             'smb_groupnorm_stats')
     return stats

@@ -41,6 +41,10 @@ void set_error(const char* fmt, ...);
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// GroupNorm statistics are accumulated as 64-bit fixed point (deterministic integer atomics)
+constexpr float kGnSumScale = 1048576.0f;   // 2^20
+constexpr float kGnSqScale = 65536.0f;      // 2^16
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 }  // namespace smb

@@ -39,7 +39,7 @@ struct ConvParams {
   void* out; int out_pitch; int out_f32;
   const float* bias; float alpha;
   const __half* residual; int res_pitch; int res_mode; int res_h, res_w;
-  float* gn_stats; int gn_group;   // channels per group
+  long long* gn_stats; int gn_group;   // fixed-point per-(image,group) {sum * 2^20, sumsq * 2^16}; channels per group
   int relu;
 };
 
@@ -298,15 +298,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             q1 += __shfl_xor_sync(0xffffffffu, q1, o);
           }
           if (lane == 0) {
+            // integer atomics are associative: the statistics (and everything downstream) are bit-reproducible
+            // run to run, unlike float atomicAdd whose result depends on arrival order.
             const int ngroups = p.Cout / p.gn_group;
-            float* st = p.gn_stats + (size_t)img * ngroups * 2;
+            unsigned long long* st = reinterpret_cast<unsigned long long*>(p.gn_stats) + (size_t)img * ngroups * 2;
             if (p.gn_group == 8) {
               const int g = ch0 >> 3;
-              atomicAdd(st + g * 2, s0); atomicAdd(st + g * 2 + 1, q0);
-              atomicAdd(st + g * 2 + 2, s1); atomicAdd(st + g * 2 + 3, q1);
+              atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn(s0 * kGnSumScale));
+              atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn(q0 * kGnSqScale));
+              atomicAdd(st + g * 2 + 2, (unsigned long long)__float2ll_rn(s1 * kGnSumScale));
+              atomicAdd(st + g * 2 + 3, (unsigned long long)__float2ll_rn(q1 * kGnSqScale));
             } else {
               const int g = ch0 >> 4;
-              atomicAdd(st + g * 2, s0 + s1); atomicAdd(st + g * 2 + 1, q0 + q1);
+              atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn((s0 + s1) * kGnSumScale));
+              atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn((q0 + q1) * kGnSqScale));
             }
           }
         }
@@ -562,7 +567,7 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
 
 extern "C" void smb_conv_plan_destroy(smb_conv_plan_t* plan) { delete plan; }
 
-extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, float* gn_stats,
+extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, void* gn_stats,
                             float alpha, smb_stream_t stream) {
   SMB_CHECK_ARG(plan, "smb_conv_run: null plan");
   SMB_CHECK_ARG(!plan->has_bias || bias, "smb_conv_run: plan expects a bias");
@@ -572,7 +577,7 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
   p.bias = plan->has_bias ? bias : nullptr;
   p.residual = plan->has_residual ? (const __half*)residual : nullptr;
   if (!plan->has_residual) p.res_mode = 0;
-  p.gn_stats = plan->gn_stats ? gn_stats : nullptr;
+  p.gn_stats = plan->gn_stats ? (long long*)gn_stats : nullptr;
   p.alpha = alpha;
   static bool attr_done = false;
   if (!attr_done) {

@@ -30,8 +30,8 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------ GroupNorm
-// stats[(img*G + g)*2 + {0,1}] = {sum, sum of squares} over hw * (C/G) elements.
-__global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C, int pitch, const float* __restrict__ stats,
+// stats[(img*G + g)*2 + {0,1}] = {sum * 2^20, sum of squares * 2^16} as int64 over hw * (C/G) elements.
+__global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C, int pitch, const long long* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu) {
   const int vecs = C >> 3;
   const long long total = (long long)n_img * hw * vecs;
@@ -48,7 +48,8 @@ __global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C
     for (int j = 0; j < 8; ++j) {
       const int c = v * 8 + j;
       const int g = c / cpg;
-      const float s = stats[((size_t)img * G + g) * 2], ss = stats[((size_t)img * G + g) * 2 + 1];
+      const float s = (float)((double)stats[((size_t)img * G + g) * 2] * (1.0 / kGnSumScale));
+      const float ss = (float)((double)stats[((size_t)img * G + g) * 2 + 1] * (1.0 / kGnSqScale));
       const float mean = s * inv_cnt;
       const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
       const float rstd = rsqrtf(var + eps);
@@ -61,12 +62,12 @@ __global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C
 
 // One CTA handles `rows_per_cta` pixels of one image; thread -> (row lane, 8-channel vector).
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int hw, int C, int pitch, int rows_per_cta,
-                                float* __restrict__ stats) {
-  __shared__ float s_sum[32], s_sq[32];
+                                long long* __restrict__ stats) {
+  __shared__ unsigned long long s_sum[32], s_sq[32];
   const int img = blockIdx.y;
   const int vecs = C >> 3;
   const int cpg = C / 32;
-  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0ull; s_sq[threadIdx.x] = 0ull; }
   __syncthreads();
   const int v = threadIdx.x % vecs;
   const int rl = threadIdx.x / vecs;
@@ -87,14 +88,15 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int hw, int C, int
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (v * 8 + j) / cpg;
-      atomicAdd(&s_sum[g], s[j]);
-      atomicAdd(&s_sq[g], q[j]);
+      atomicAdd(&s_sum[g], (unsigned long long)__float2ll_rn(s[j] * kGnSumScale));
+      atomicAdd(&s_sq[g], (unsigned long long)__float2ll_rn(q[j] * kGnSqScale));
     }
   }
   __syncthreads();
   if (threadIdx.x < 32) {
-    atomicAdd(stats + ((size_t)img * 32 + threadIdx.x) * 2, s_sum[threadIdx.x]);
-    atomicAdd(stats + ((size_t)img * 32 + threadIdx.x) * 2 + 1, s_sq[threadIdx.x]);
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(stats);
+    atomicAdd(st + ((size_t)img * 32 + threadIdx.x) * 2, s_sum[threadIdx.x]);
+    atomicAdd(st + ((size_t)img * 32 + threadIdx.x) * 2 + 1, s_sq[threadIdx.x]);
   }
 }
 
@@ -290,24 +292,24 @@ static inline int grid_for(long long total, int block) {
 
 using namespace smb;
 
-extern "C" int smb_groupnorm_relu_apply(void* x, int n_img, int hw, int C, int pitch, const float* stats, const float* gamma,
+extern "C" int smb_groupnorm_relu_apply(void* x, int n_img, int hw, int C, int pitch, const void* stats, const float* gamma,
                                         const float* beta, float eps, int relu, smb_stream_t stream) {
   SMB_CHECK_ARG(x && stats && gamma && beta, "smb_groupnorm_relu_apply: null pointer");
   SMB_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && pitch % 8 == 0 && hw > 0 && n_img > 0, "smb_groupnorm_relu_apply: bad shape");
   const long long total = (long long)n_img * hw * (C / 8);
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, n_img, hw, C, pitch, stats, gamma, beta,
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, n_img, hw, C, pitch, (const long long*)stats, gamma, beta,
                                                                           eps, relu);
   SMB_LAUNCH_OK("gn_apply_kernel");
   return SMB_OK;
 }
 
-extern "C" int smb_groupnorm_stats(const void* x, int n_img, int hw, int C, int pitch, float* stats, smb_stream_t stream) {
+extern "C" int smb_groupnorm_stats(const void* x, int n_img, int hw, int C, int pitch, void* stats, smb_stream_t stream) {
   SMB_CHECK_ARG(x && stats, "smb_groupnorm_stats: null pointer");
   SMB_CHECK_ARG(C % 32 == 0 && C % 8 == 0 && C <= 2048 && pitch % 8 == 0 && hw > 0 && n_img > 0, "smb_groupnorm_stats: bad shape");
-  SMB_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * n_img * 64, (cudaStream_t)stream));
+  SMB_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(long long) * n_img * 64, (cudaStream_t)stream));
   const int rows_per_cta = 64;
   dim3 grid(cdiv(hw, rows_per_cta), n_img);
-  gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, hw, C, pitch, rows_per_cta, stats);
+  gn_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, hw, C, pitch, rows_per_cta, (long long*)stats);
   SMB_LAUNCH_OK("gn_stats_kernel");
   return SMB_OK;
 }

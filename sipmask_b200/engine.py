@@ -24,7 +24,7 @@ ARCH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
 class SipMaskEngine(object):
     def __init__(self, state_dict, img_hw, batch=1, depth=50, stacked_convs=4, gn=True, ssd_flag=False, num_classes=81,
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
-                 mask_thr=0.4, use_graph=True, pos_dtype=torch.float16):
+                 mask_thr=0.4, use_graph=True, pos_dtype=torch.float32):
         L.check(L.lib().smb_check_device(), 'smb_check_device')
         self.dev = torch.device(device)
         self.N, (self.H, self.W) = batch, img_hw
@@ -161,7 +161,7 @@ class SipMaskEngine(object):
         nl = len(feats)
         n_tower = (self.stacked - 1) + self.stacked + 1
         # one fp32 statistics arena for every (level, conv) GroupNorm, zeroed once per forward
-        self.gn_arena = self._t(nl * n_tower, N, 32, 2, dtype=torch.float32, zero=True)
+        self.gn_arena = self._t(nl * n_tower, N, 32, 2, dtype=torch.int64, zero=True)
         self._add(lambda: self.gn_arena.zero_(), 0)
         # shared (across levels) packed weights
         ncls, CC = self.ncls, self.ncls + 128

@@ -82,7 +82,7 @@ def test_conv_epilogue_bias_residual_relu_gnstats():
     wk, bias = conv.pack_weight(w, bn=bn, device='cuda')
     res = _nhwc(torch.randn(N, C, H, W, generator=g))
     out = torch.empty((N, H, W, C), dtype=torch.float16, device='cuda')
-    stats = torch.zeros((N, 32, 2), dtype=torch.float32, device='cuda')
+    stats = torch.zeros((N, 32, 2), dtype=torch.int64, device='cuda')
     plan = conv.ConvPlan(x, wk, out, 3, 1, relu=True, bias=bias, residual=res, gn_stats=stats)
     plan.run()
     torch.cuda.synchronize()
@@ -90,8 +90,13 @@ def test_conv_epilogue_bias_residual_relu_gnstats():
     _check(out, pre.clamp(min=0))
     # GN statistics are taken on the pre-activation value (conv + bias + residual), per (image, 8-channel group)
     grp = pre.view(N, H * W, 32, 8)
-    np.testing.assert_allclose(stats[:, :, 0].cpu().numpy(), grp.sum((1, 3)).cpu().numpy(), rtol=2e-3, atol=0.5)
-    np.testing.assert_allclose(stats[:, :, 1].cpu().numpy(), (grp * grp).sum((1, 3)).cpu().numpy(), rtol=2e-3, atol=0.5)
+    np.testing.assert_allclose(stats[:, :, 0].double().cpu().numpy() / 2 ** 20, grp.sum((1, 3)).cpu().numpy(), rtol=2e-3, atol=0.5)
+    np.testing.assert_allclose(stats[:, :, 1].double().cpu().numpy() / 2 ** 16, (grp * grp).sum((1, 3)).cpu().numpy(), rtol=2e-3, atol=0.5)
+    s1 = stats.clone()
+    stats.zero_()
+    plan.run()
+    torch.cuda.synchronize()
+    assert torch.equal(stats, s1)          # integer atomics: bit-reproducible
     # folded BN == eval BatchNorm of the reference (resnet.py:514-521)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w.cuda(), padding=1)
     y = F.batch_norm(y, bn[2].cuda(), bn[3].cuda(), bn[0].cuda(), bn[1].cuda(), False, 0.0, 1e-5)
