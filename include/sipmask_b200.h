@@ -68,6 +68,13 @@ int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8
 int smb_mask_upsample2_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
                                       int out_h, int out_w, float thr, smb_stream_t stream);
 
+/* Fully fused mask path (sipmask_head.py:609-633,648-654 in one kernel): prototypes -> selected sub-region dot
+ * product -> sigmoid -> crop -> x2 bilinear -> `> thr` -> bit-pack.  pos_masks is never written to memory.
+ * Same arguments as smb_mask_assemble; output as smb_mask_upsample2_threshold_pack. */
+int smb_mask_assemble_pack(const void* protos, int protos_dtype, int layout_hwc, const float* cofs, const float* boxes,
+                           const float* host_box_scale4, uint32_t* out_bits, int H, int W, int N, int out_h, int out_w,
+                           float thr, smb_stream_t stream);
+
 /* ------------------------------------------------------------------ CropSplit (operator API)
  * Replaces crop_split_cuda.crop_split_cuda_forward(data, rois, out, H, W, c, n)
  * (ops/crop/src/crop_split_cuda.cpp:14-36).  data [c*c,H,W,N], rois [N,4], out [H,W,N]; c == 2.
@@ -167,6 +174,17 @@ typedef struct {
 
 int smb_conv_plan_create(const smb_conv_desc_t* desc, const void* in, const void* weight, void* out,
                          smb_conv_plan_t** plan_out);
+
+/* One launch over several feature-pyramid levels that share the weights (the FCOS towers / heads are applied to
+ * P3..P7 in a python loop in the reference, sipmask_head.py:250-271).  desc->H/W are ignored; stride must be 1.
+ * Per-level residual / gn_stats pointers are baked into the plan (pass NULLs to smb_conv_run). */
+typedef struct {
+  const void* in; void* out;
+  const void* residual; void* gn_stats;
+  int H, W, res_h, res_w;
+} smb_conv_level_t;
+int smb_conv_plan_create_multi(const smb_conv_desc_t* desc, int num_levels, const smb_conv_level_t* levels,
+                               const void* weight, smb_conv_plan_t** plan_out);
 void smb_conv_plan_destroy(smb_conv_plan_t* plan);
 /* out = relu?( (acc + bias) * alpha + residual ); alpha carries the per-level `Scale` of fcos_reg
  * (sipmask_head.py:261, ops/scale.py:12-15). */
@@ -190,6 +208,18 @@ int smb_deform_im2col(const void* x, const float* offset, int off_pitch, void* c
 /* FeatureAlign.conv_offset (sipmask_head.py:30-33,50): off[pix,o] = sum_k W[o,k] * (bbox[pix,k] * scale), fp32. */
 int smb_offset_conv1x1(const float* bbox, int bbox_pitch, float scale, const float* weight, int n_off, float* off,
                        long long npix, smb_stream_t stream);
+
+/* Multi-level (batched over feature-pyramid levels, shared parameters) variants of the three kernels above:
+ * one launch instead of one per level.  Pointer arrays are HOST arrays of device pointers. */
+int smb_groupnorm_relu_apply_multi(int num_levels, void* const* xs, const void* const* stats, const int* Hs, const int* Ws,
+                                   int n_img, int C, int pitch, const float* gamma, const float* beta, float eps, int relu,
+                                   smb_stream_t stream);
+int smb_offset_conv1x1_multi(int num_levels, const float* const* bboxes, int bbox_pitch, const float* scales,
+                             const float* weight, int n_off, float* const* offs, const int* Hs, const int* Ws, int n_img,
+                             smb_stream_t stream);
+int smb_deform_im2col_multi(int num_levels, const void* const* xs, const float* const* offs, int off_pitch,
+                            void* const* cols, const int* Hs, const int* Ws, int n_img, int C, int deformable_groups,
+                            smb_stream_t stream);
 
 /* MaxPool2d(3, 2, 1) (backbones/resnet.py:460), NHWC fp16. */
 int smb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int C, smb_stream_t stream);

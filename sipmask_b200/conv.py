@@ -104,6 +104,45 @@ class ConvPlan(object):
             pass
 
 
+class ConvPlanMulti(ConvPlan):
+    """One stride-1 convolution with shared weights over several feature-pyramid levels = ONE launch
+    (the reference loops over levels in python, sipmask_head.py:250-271)."""
+
+    def __init__(self, xs, weight, outs, k, relu=False, bias=None, gn_stats=None, alpha=1.0):
+        nl = len(xs)
+        N = xs[0].shape[0]
+        cin = xs[0].shape[3]
+        in_pitch = xs[0].stride(2)
+        out_pitch = outs[0].stride(2)
+        cout = weight.shape[0]
+        assert weight.shape[1] == k * k * cin and weight.dtype == torch.float16 and weight.is_contiguous()
+        lv = (L.ConvLevel * nl)()
+        for i, (x, o) in enumerate(zip(xs, outs)):
+            assert x.is_cuda and x.dtype == torch.float16 and x.stride(3) == 1 and x.stride(2) == in_pitch
+            assert x.shape[0] == N and x.stride(1) == x.shape[2] * in_pitch and x.stride(0) == x.shape[1] * x.shape[2] * in_pitch
+            assert o.stride(3) == 1 and o.stride(2) == out_pitch and o.dtype == outs[0].dtype
+            st = gn_stats[i] if gn_stats is not None else None
+            lv[i] = L.ConvLevel(x.data_ptr(), o.data_ptr(), 0, st.data_ptr() if st is not None else 0, x.shape[1], x.shape[2], 0, 0)
+        d = L.ConvDesc()
+        d.N, d.H, d.W, d.Cin, d.Cout = N, 0, 0, cin, cout
+        d.kh = d.kw = k
+        d.stride = 1
+        d.pad = k // 2
+        d.relu = int(relu)
+        d.has_bias = int(bias is not None)
+        d.has_residual = 0
+        d.out_dtype = L.F32 if outs[0].dtype == torch.float32 else L.F16
+        d.gn_stats = int(gn_stats is not None)
+        d.in_pitch = in_pitch
+        d.out_pitch = out_pitch
+        self._keep = (xs, weight, outs, bias, gn_stats, lv)
+        self.bias, self.residual, self.gn_stats, self.alpha = bias, None, None, float(alpha)
+        self.handle = ctypes.c_void_p()
+        L.check(L.lib().smb_conv_plan_create_multi(ctypes.byref(d), nl, lv, L.ptr(weight), ctypes.byref(self.handle)),
+                'smb_conv_plan_create_multi')
+        self.out = outs
+
+
 class StemPlan(ConvPlan):
     """7x7/2 stem + folded BN + ReLU on the padded NHWC8 image (resnet.py:448-460)."""
 
@@ -179,3 +218,39 @@ def upsample_bilinear(x, factor, out=None, out_choff=0, relu=False):
     L.check(L.lib().smb_upsample_bilinear(L.ptr(x), x.stride(2), L.ptr(out), out.stride(2), int(out_choff), N, H, W, C,
                                           int(factor), int(relu), L.stream_ptr()), 'smb_upsample_bilinear')
     return out
+
+
+# ------------------------------------------------------------------------------------- multi-level wrappers
+def _parr(ts):
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def _iarr(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def groupnorm_relu_apply_multi(xs, stats, gamma, beta, eps=1e-5, relu=True):
+    N, _, _, C = xs[0].shape
+    L.check(L.lib().smb_groupnorm_relu_apply_multi(len(xs), _parr(xs), _parr(stats), _iarr([x.shape[1] for x in xs]),
+                                                   _iarr([x.shape[2] for x in xs]), N, C, xs[0].stride(2), L.ptr(gamma),
+                                                   L.ptr(beta), ctypes.c_float(eps), int(relu), L.stream_ptr()),
+            'smb_groupnorm_relu_apply_multi')
+    return xs
+
+
+def offset_conv1x1_multi(bboxes, scales, weight, offs):
+    N = bboxes[0].shape[0]
+    sc = (ctypes.c_float * len(scales))(*[float(v) for v in scales])
+    L.check(L.lib().smb_offset_conv1x1_multi(len(bboxes), _parr(bboxes), bboxes[0].stride(2), sc, L.ptr(weight),
+                                             weight.shape[0], _parr(offs), _iarr([b.shape[1] for b in bboxes]),
+                                             _iarr([b.shape[2] for b in bboxes]), N, L.stream_ptr()),
+            'smb_offset_conv1x1_multi')
+    return offs
+
+
+def deform_im2col_multi(xs, offs, dg, cols):
+    N, _, _, C = xs[0].shape
+    L.check(L.lib().smb_deform_im2col_multi(len(xs), _parr(xs), _parr(offs), offs[0].stride(2), _parr(cols),
+                                            _iarr([x.shape[1] for x in xs]), _iarr([x.shape[2] for x in xs]), N, C, int(dg),
+                                            L.stream_ptr()), 'smb_deform_im2col_multi')
+    return cols

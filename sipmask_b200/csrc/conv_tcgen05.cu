@@ -25,21 +25,37 @@
 namespace smb {
 
 constexpr int kMaxTaps = 9;
-constexpr int kMaxMaps = 4;
+constexpr int kMaxMaps = 8;
+constexpr int kMaxLevels = 5;
 constexpr int kThreads = 192;
 constexpr int kABytes = 128 * 64 * 2;   // one A stage: 128 pixels x 64 channels fp16
+
+// One pyramid level (or the only tensor) of a launch.  Convolutions whose weights are shared by several feature-pyramid
+// levels (the FCOS towers and heads, sipmask_head.py:250-257) run as ONE launch over the union of the levels' tiles.
+struct LevelDesc {
+  int H_out, W_out, BH, BW, tiles_x, tiles_y;
+  int tile_start;                 // first M-tile of this level in the launch-wide tile order
+  int map0;                       // index of this level's first A tensor map
+  void* out;
+  const __half* residual;
+  long long* gn_stats;            // fixed-point per-(image,group) {sum * 2^20, sumsq * 2^16}
+  int res_h, res_w;
+  int pad_;
+};
 
 struct ConvParams {
   CUtensorMap amap[kMaxMaps];
   CUtensorMap bmap;
+  LevelDesc lv[kMaxLevels];
+  int num_levels;
   int tap_map[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];
   int num_taps, kb_per_tap;       // k-blocks (64 channels) per tap
-  int n_img, H_out, W_out, BH, BW, tiles_x, tiles_y;
+  int n_img, tiles_m;
   int Cout, n_tile, n_tiles_n, stages, tmem_cols, num_acc;
-  void* out; int out_pitch; int out_f32;
+  int out_pitch; int out_f32;
   const float* bias; float alpha;
-  const __half* residual; int res_pitch; int res_mode; int res_h, res_w;
-  long long* gn_stats; int gn_group;   // fixed-point per-(image,group) {sum * 2^20, sumsq * 2^16}; channels per group
+  int res_pitch; int res_mode;
+  int gn_group;                   // channels per GroupNorm group (8 or 16), 0 = no statistics
   int relu;
 };
 
@@ -136,6 +152,44 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct TileCoord {
+  int lvl, img, x0, y0, n0;
+};
+
+// launch-wide tile id -> (level, image, patch origin, first output channel); N-tiles of one M-tile are adjacent so
+// that CTAs running concurrently share the same activation patch in L2.
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles_n;
+  int mt = tile / p.n_tiles_n;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxLevels; ++i)
+    if (i < p.num_levels && mt >= p.lv[i].tile_start) l = i;
+  mt -= p.lv[l].tile_start;
+  const int tx = mt % p.lv[l].tiles_x;
+  mt /= p.lv[l].tiles_x;
+  const int ty = mt % p.lv[l].tiles_y;
+  t.lvl = l;
+  t.img = mt / p.lv[l].tiles_y;
+  t.x0 = tx * p.lv[l].BW;
+  t.y0 = ty * p.lv[l].BH;
+  t.n0 = nt * p.n_tile;
+  return t;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // the 128-byte swizzle atoms (8 rows x 128 B) must start on 1024-byte boundaries
@@ -149,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [2][256] double-buffered per tile
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -163,8 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_m = p.n_img * p.tiles_y * p.tiles_x;
-  const int total_tiles = tiles_m * p.n_tiles_n;
+  const int total_tiles = p.tiles_m * p.n_tiles_n;
   const int kblocks = p.num_taps * p.kb_per_tap;
   const uint32_t stage_bytes = (uint32_t)(kABytes + b_bytes);
 
@@ -173,22 +227,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ===================== TMA producer =====================
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
-        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int img = mt / p.tiles_y;
-        const int x0 = tx * p.BW, y0 = ty * p.BH, n0 = nt * p.n_tile;
+        const TileCoord tc = decode_tile(p, tile);
+        const int map0 = p.lv[tc.lvl].map0;
         for (int t = 0; t < p.num_taps; ++t) {
-          const CUtensorMap* am = &p.amap[p.tap_map[t]];
-          const int ax = x0 + p.tap_dx[t], ay = y0 + p.tap_dy[t];
+          const CUtensorMap* am = &p.amap[map0 + p.tap_map[t]];
+          const int ax = tc.x0 + p.tap_dx[t], ay = tc.y0 + p.tap_dy[t];
           for (int kc = 0; kc < p.kb_per_tap; ++kc, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             mbar_expect_tx(&full_bar[s], stage_bytes);
-            tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, img);
-            tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], (t * p.kb_per_tap + kc) * 64, n0);
+            tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, tc.img);
+            tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], (t * p.kb_per_tap + kc) * 64, tc.n0);
           }
         }
       }
@@ -225,117 +275,132 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // ===================== epilogue warps (2..5) =====================
     const int lane_grp = warp & 3;                   // TMEM lanes 32*(warp%4) .. +31 are accessible to this warp
     const int row = lane_grp * 32 + lane;
-    const int iy = row / p.BW, ix = row - iy * p.BW;
+    const int et = threadIdx.x - 64;                 // 0..127 within the epilogue group
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
-      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int img = mt / p.tiles_y;
-      const int x = tx * p.BW + ix, y = ty * p.BH + iy, n0 = nt * p.n_tile;
-      const bool valid = (x < p.W_out) && (y < p.H_out);
-      const size_t pix = ((size_t)img * p.H_out + y) * p.W_out + x;
+      const TileCoord tc = decode_tile(p, tile);
+      const LevelDesc& L = p.lv[tc.lvl];
+      const int iy = row / L.BW, ix = row - iy * L.BW;
+      const int x = tc.x0 + ix, y = tc.y0 + iy, n0 = tc.n0;
+      const bool valid = (x < L.W_out) && (y < L.H_out);
+      const size_t pix = ((size_t)tc.img * L.H_out + y) * L.W_out + x;
       const __half* res_row = nullptr;
       if (p.res_mode == 1) {
-        res_row = p.residual + pix * p.res_pitch;
+        res_row = L.residual + pix * p.res_pitch;
       } else if (p.res_mode == 2) {
         // F.interpolate(mode='nearest', size=...) : src = min(floor(dst * in/out), in-1)   (fpn.py:149-152)
-        const int sy = min((int)floorf((float)y * ((float)p.res_h / (float)p.H_out)), p.res_h - 1);
-        const int sx = min((int)floorf((float)x * ((float)p.res_w / (float)p.W_out)), p.res_w - 1);
-        res_row = p.residual + (((size_t)img * p.res_h + sy) * p.res_w + sx) * p.res_pitch;
+        const int sy = min((int)floorf((float)y * ((float)L.res_h / (float)L.H_out)), L.res_h - 1);
+        const int sx = min((int)floorf((float)x * ((float)L.res_w / (float)L.W_out)), L.res_w - 1);
+        res_row = L.residual + (((size_t)tc.img * L.res_h + sy) * L.res_w + sx) * p.res_pitch;
       }
+      // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile)
+      float* sb = s_bias + (lt & 1) * 256;
+      if (p.bias) {
+        for (int c = et; c < p.n_tile; c += 128) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int acc = lt % p.num_acc;
       const uint32_t acc_ph = (lt / p.num_acc) & 1;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_base + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t v[32];
+        if (c0 + 32 <= p.n_tile) {
+          tmem_ld32(t_base + (uint32_t)c0, v);
+        } else {                                     // n_tile % 32 == 16: last half chunk
+          tmem_ld16(t_base + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0u;
+        }
         tmem_ld_wait();
-        const int ch0 = n0 + c0;
-        if (ch0 >= p.Cout) continue;                 // uniform across the CTA
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+        for (int h = 0; h < 2; ++h) {                // two 16-channel halves
+          const int ch0 = n0 + c0 + h * 16;
+          if (c0 + h * 16 >= p.n_tile || ch0 >= p.Cout) continue;     // uniform across the CTA
+          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ch0 + j);
-        }
-        if (p.alpha != 1.0f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] *= p.alpha;
-        }
-        if (res_row && valid) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(res_row + ch0);
-          const uint4 ra = __ldg(r4), rb = __ldg(r4 + 1);
-          const __half2* ha = reinterpret_cast<const __half2*>(&ra);
-          const __half2* hb = reinterpret_cast<const __half2*>(&rb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a = __half22float2(ha[j]), b = __half22float2(hb[j]);
-            f[2 * j] += a.x; f[2 * j + 1] += a.y;
-            f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-          }
-        }
-        if (p.gn_stats) {
-          // per-(image, group) sum / sum of squares of the conv output (pre-activation), fp32.
-          // gn_group (channels per group) is 8 (two groups per 16-column chunk) or 16 (one group).
-          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              s0 += f[j]; q0 += f[j] * f[j];
-              s1 += f[8 + j]; q1 += f[8 + j] * f[8 + j];
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-          }
-          if (lane == 0) {
-            // integer atomics are associative: the statistics (and everything downstream) are bit-reproducible
-            // run to run, unlike float atomicAdd whose result depends on arrival order.
-            const int ngroups = p.Cout / p.gn_group;
-            unsigned long long* st = reinterpret_cast<unsigned long long*>(p.gn_stats) + (size_t)img * ngroups * 2;
-            if (p.gn_group == 8) {
-              const int g = ch0 >> 3;
-              atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn(s0 * kGnSumScale));
-              atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn(q0 * kGnSqScale));
-              atomicAdd(st + g * 2 + 2, (unsigned long long)__float2ll_rn(s1 * kGnSumScale));
-              atomicAdd(st + g * 2 + 3, (unsigned long long)__float2ll_rn(q1 * kGnSqScale));
-            } else {
-              const int g = ch0 >> 4;
-              atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn((s0 + s1) * kGnSumScale));
-              atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn((q0 + q1) * kGnSqScale));
-            }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (valid) {
-          if (p.out_f32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_pitch + ch0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4 oa, ob;
-            __half2* ha = reinterpret_cast<__half2*>(&oa);
-            __half2* hb = reinterpret_cast<__half2*>(&ob);
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c0 + h * 16);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              ha[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-              hb[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+              const float4 b = b4[j];
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.out_pitch + ch0);
-            o[0] = oa;
-            o[1] = ob;
+          }
+          if (p.alpha != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= p.alpha;
+          }
+          if (res_row && valid) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(res_row + ch0);
+            const uint4 ra = __ldg(r4), rb = __ldg(r4 + 1);
+            const __half2* ha = reinterpret_cast<const __half2*>(&ra);
+            const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = __half22float2(ha[j]), b = __half22float2(hb[j]);
+              f[2 * j] += a.x; f[2 * j + 1] += a.y;
+              f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+            }
+          }
+          if (p.gn_group) {
+            // per-(image, group) sum / sum of squares of the conv output (pre-activation), fp32 in-warp, then
+            // 64-bit fixed-point integer atomics (associative -> bit-reproducible run to run).
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                s0 += f[j]; q0 += f[j] * f[j];
+                s1 += f[8 + j]; q1 += f[8 + j] * f[8 + j];
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+              q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            if (lane == 0) {
+              const int ngroups = p.Cout / p.gn_group;
+              unsigned long long* st = reinterpret_cast<unsigned long long*>(L.gn_stats) + (size_t)tc.img * ngroups * 2;
+              if (p.gn_group == 8) {
+                const int g = ch0 >> 3;
+                atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn(s0 * kGnSumScale));
+                atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn(q0 * kGnSqScale));
+                atomicAdd(st + g * 2 + 2, (unsigned long long)__float2ll_rn(s1 * kGnSumScale));
+                atomicAdd(st + g * 2 + 3, (unsigned long long)__float2ll_rn(q1 * kGnSqScale));
+              } else {
+                const int g = ch0 >> 4;
+                atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn((s0 + s1) * kGnSumScale));
+                atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn((q0 + q1) * kGnSqScale));
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (valid) {
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(L.out) + pix * p.out_pitch + ch0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+              uint4 oa, ob;
+              __half2* ha = reinterpret_cast<__half2*>(&oa);
+              __half2* hb = reinterpret_cast<__half2*>(&ob);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                ha[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                hb[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+              }
+              uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(L.out) + pix * p.out_pitch + ch0);
+              o[0] = oa;
+              o[1] = ob;
+            }
           }
         }
       }
@@ -432,101 +497,134 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   else { set_error("conv plan: unsupported Cout=%d", Cout); return SMB_EINVAL; }
   p.n_tile = n_tile;
   p.n_tiles_n = cdiv(Cout, n_tile);
-  int cols = 32;
-  while (cols < n_tile) cols <<= 1;
   p.num_acc = (2 * n_tile <= 512) ? 2 : 1;
   int tc = 32;
   while (tc < p.num_acc * n_tile) tc <<= 1;
   p.tmem_cols = tc;
   const size_t stage = (size_t)kABytes + (size_t)n_tile * 128;
-  const size_t budget = 200 * 1024;
+  const size_t budget = 196 * 1024;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv plan: tile too large for shared memory"); return SMB_EINVAL; }
   p.stages = stages;
-  pl->smem_bytes = stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  pl->smem_bytes = stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16 + 2 * 256 * sizeof(float) + 1024;
   // weights: [Cout, Ktotal] K-major
   uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
   uint64_t strides[1] = {(uint64_t)Ktotal * 2};
   uint32_t box[2] = {64, (uint32_t)n_tile};
   int rc = encode_map(&p.bmap, const_cast<void*>(weight), 2, dims, strides, box);
   if (rc) return rc;
-  const int tiles = p.n_img * p.tiles_y * p.tiles_x * p.n_tiles_n;
+  const int tiles = p.tiles_m * p.n_tiles_n;
   pl->grid = tiles < num_sms() ? tiles : num_sms();
   return SMB_OK;
 }
 
-extern "C" int smb_conv_plan_create(const smb_conv_desc_t* d, const void* in, const void* weight, void* out,
-                                    smb_conv_plan_t** plan_out) {
-  SMB_CHECK_ARG(d && in && weight && out && plan_out, "smb_conv_plan_create: null pointer");
+extern "C" int smb_conv_plan_create_multi(const smb_conv_desc_t* d, int num_levels, const smb_conv_level_t* levels,
+                                          const void* weight, smb_conv_plan_t** plan_out) {
+  SMB_CHECK_ARG(d && levels && weight && plan_out, "smb_conv_plan_create: null pointer");
+  SMB_CHECK_ARG(num_levels >= 1 && num_levels <= kMaxLevels, "smb_conv_plan_create: num_levels=%d outside [1,%d]", num_levels, kMaxLevels);
   SMB_CHECK_ARG(d->Cin % 64 == 0 && d->Cin > 0, "smb_conv_plan_create: Cin=%d must be a multiple of 64", d->Cin);
   SMB_CHECK_ARG(d->Cout % 16 == 0 && d->Cout > 0, "smb_conv_plan_create: Cout=%d must be a multiple of 16", d->Cout);
   SMB_CHECK_ARG((d->kh == 1 && d->kw == 1 && d->pad == 0) || (d->kh == 3 && d->kw == 3 && d->pad == 1),
                 "smb_conv_plan_create: only 1x1/p0 and 3x3/p1 kernels (got %dx%d pad %d)", d->kh, d->kw, d->pad);
   SMB_CHECK_ARG(d->stride == 1 || d->stride == 2, "smb_conv_plan_create: stride %d", d->stride);
+  SMB_CHECK_ARG(d->stride == 1 || num_levels == 1, "smb_conv_plan_create: strided convolutions are single-level");
   const int in_pitch = d->in_pitch ? d->in_pitch : d->Cin;
   const int out_pitch = d->out_pitch ? d->out_pitch : d->Cout;
-  SMB_CHECK_ARG(in_pitch % 8 == 0 && out_pitch % 8 == 0, "smb_conv_plan_create: pitches must be multiples of 8");
-  SMB_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)weight % 16) == 0 && ((uintptr_t)out % 16) == 0,
-                "smb_conv_plan_create: pointers must be 16-byte aligned");
+  SMB_CHECK_ARG(in_pitch % 8 == 0 && out_pitch % 4 == 0, "smb_conv_plan_create: bad pitches");
+  SMB_CHECK_ARG(((uintptr_t)weight % 16) == 0, "smb_conv_plan_create: weight must be 16-byte aligned");
   smb_conv_plan* pl = new smb_conv_plan();
   memset(&pl->p, 0, sizeof(ConvParams));
   ConvParams& p = pl->p;
-  const int H = d->H, W = d->W, k = d->kh, s = d->stride;
-  const int Ho = (H + 2 * d->pad - k) / s + 1, Wo = (W + 2 * d->pad - k) / s + 1;
-  p.n_img = d->N; p.H_out = Ho; p.W_out = Wo;
-  choose_patch(Ho, Wo, &p.BH, &p.BW);
-  p.tiles_x = cdiv(Wo, p.BW); p.tiles_y = cdiv(Ho, p.BH);
+  const int k = d->kh, s = d->stride;
+  p.n_img = d->N;
+  p.num_levels = num_levels;
   p.num_taps = k * k; p.kb_per_tap = d->Cin / 64;
   p.Cout = d->Cout;
-  p.out = out; p.out_pitch = out_pitch; p.out_f32 = (d->out_dtype == SMB_F32);
+  p.out_pitch = out_pitch; p.out_f32 = (d->out_dtype == SMB_F32);
   p.alpha = 1.0f; p.relu = d->relu;
   p.res_mode = d->has_residual ? (d->residual_upsample ? 2 : 1) : 0;
-  p.res_pitch = d->Cout; p.res_h = d->res_h; p.res_w = d->res_w;
-  p.gn_group = d->Cout / 32;
+  p.res_pitch = d->Cout;
+  p.gn_group = d->gn_stats ? d->Cout / 32 : 0;
   pl->has_bias = d->has_bias; pl->has_residual = d->has_residual; pl->gn_stats = d->gn_stats;
   if (d->gn_stats && !(p.gn_group == 8 || p.gn_group == 16)) {
     set_error("smb_conv_plan_create: gn_stats needs Cout/32 in {8,16}");
     delete pl;
     return SMB_EINVAL;
   }
-  const uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
   const uint64_t px = (uint64_t)in_pitch * 2;       // bytes per pixel
   int rc = SMB_OK;
-  if (s == 1) {
-    uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
-    uint64_t strides[3] = {px, px * W, px * W * H};
-    rc = encode_map(&p.amap[0], const_cast<void*>(in), 4, dims, strides, box);
-    for (int i = 1; i < kMaxMaps; ++i) p.amap[i] = p.amap[0];
-    for (int r = 0; r < k; ++r)
-      for (int c = 0; c < k; ++c) {
-        const int t = r * k + c;
-        p.tap_map[t] = 0; p.tap_dx[t] = c - d->pad; p.tap_dy[t] = r - d->pad;
-      }
-  } else {
-    // stride 2: input (2*oy + r - pad, 2*ox + c - pad) -> parity-split views with doubled strides
-    for (int py = 0; py < 2 && rc == SMB_OK; ++py)
-      for (int pxp = 0; pxp < 2 && rc == SMB_OK; ++pxp) {
-        const int hp = (H - py + 1) / 2, wp = (W - pxp + 1) / 2;   // rows / cols of this parity
-        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)(wp > 0 ? wp : 1), (uint64_t)(hp > 0 ? hp : 1), (uint64_t)d->N};
-        uint64_t strides[3] = {px * 2, px * W * 2, px * W * H};
-        const char* base = (const char*)in + ((size_t)py * W + pxp) * px;
-        rc = encode_map(&p.amap[py * 2 + pxp], const_cast<char*>(base), 4, dims, strides, box);
-      }
-    for (int r = 0; r < k; ++r)
-      for (int c = 0; c < k; ++c) {
-        const int t = r * k + c;
-        const int oy = r - d->pad, ox = c - d->pad;            // input offset relative to 2*o
-        const int py = ((oy % 2) + 2) % 2, pxp = ((ox % 2) + 2) % 2;
-        p.tap_map[t] = py * 2 + pxp;
-        p.tap_dy[t] = (oy - py) / 2;                           // exact: oy - py is even
-        p.tap_dx[t] = (ox - pxp) / 2;
-      }
+  int tile_start = 0;
+  for (int l = 0; l < num_levels && rc == SMB_OK; ++l) {
+    const smb_conv_level_t& lv = levels[l];
+    LevelDesc& L = p.lv[l];
+    const int H = lv.H, W = lv.W;
+    if (!lv.in || !lv.out || H <= 0 || W <= 0 || ((uintptr_t)lv.in % 16) || ((uintptr_t)lv.out % 16) ||
+        (d->has_residual && !lv.residual) || (d->gn_stats && !lv.gn_stats)) {
+      set_error("smb_conv_plan_create: level %d has a null / misaligned pointer or empty shape", l);
+      rc = SMB_EINVAL;
+      break;
+    }
+    const int Ho = (H + 2 * d->pad - k) / s + 1, Wo = (W + 2 * d->pad - k) / s + 1;
+    L.H_out = Ho; L.W_out = Wo;
+    choose_patch(Ho, Wo, &L.BH, &L.BW);
+    L.tiles_x = cdiv(Wo, L.BW); L.tiles_y = cdiv(Ho, L.BH);
+    L.tile_start = tile_start;
+    tile_start += d->N * L.tiles_x * L.tiles_y;
+    L.out = lv.out; L.residual = (const __half*)lv.residual; L.gn_stats = (long long*)lv.gn_stats;
+    L.res_h = lv.res_h; L.res_w = lv.res_w;
+    const uint32_t box[4] = {64, (uint32_t)L.BW, (uint32_t)L.BH, 1};
+    if (s == 1) {
+      L.map0 = l;
+      uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
+      uint64_t strides[3] = {px, px * W, px * W * H};
+      rc = encode_map(&p.amap[l], const_cast<void*>(lv.in), 4, dims, strides, box);
+    } else {
+      // stride 2: input (2*oy + r - pad, 2*ox + c - pad) -> parity-split views with doubled strides
+      L.map0 = 0;
+      for (int py = 0; py < 2 && rc == SMB_OK; ++py)
+        for (int pxp = 0; pxp < 2 && rc == SMB_OK; ++pxp) {
+          const int hp = (H - py + 1) / 2, wp = (W - pxp + 1) / 2;   // rows / cols of this parity
+          uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)(wp > 0 ? wp : 1), (uint64_t)(hp > 0 ? hp : 1), (uint64_t)d->N};
+          uint64_t strides[3] = {px * 2, px * W * 2, px * W * H};
+          const char* base = (const char*)lv.in + ((size_t)py * W + pxp) * px;
+          rc = encode_map(&p.amap[py * 2 + pxp], const_cast<char*>(base), 4, dims, strides, box);
+        }
+    }
   }
-  if (rc == SMB_OK) rc = finish_plan(pl, d->Cout, k * k * d->Cin, weight);
+  if (rc == SMB_OK) {
+    p.tiles_m = tile_start;
+    for (int i = (s == 1 ? num_levels : 4); i < kMaxMaps; ++i) p.amap[i] = p.amap[0];
+    for (int r = 0; r < k; ++r)
+      for (int c = 0; c < k; ++c) {
+        const int t = r * k + c;
+        if (s == 1) {
+          p.tap_map[t] = 0; p.tap_dx[t] = c - d->pad; p.tap_dy[t] = r - d->pad;
+        } else {
+          const int oy = r - d->pad, ox = c - d->pad;            // input offset relative to 2*o
+          const int py = ((oy % 2) + 2) % 2, pxp = ((ox % 2) + 2) % 2;
+          p.tap_map[t] = py * 2 + pxp;
+          p.tap_dy[t] = (oy - py) / 2;                           // exact: oy - py is even
+          p.tap_dx[t] = (ox - pxp) / 2;
+        }
+      }
+    rc = finish_plan(pl, d->Cout, k * k * d->Cin, weight);
+  }
   if (rc != SMB_OK) { delete pl; return rc; }
   *plan_out = pl;
   return SMB_OK;
+}
+
+extern "C" int smb_conv_plan_create(const smb_conv_desc_t* d, const void* in, const void* weight, void* out,
+                                    smb_conv_plan_t** plan_out) {
+  SMB_CHECK_ARG(d, "smb_conv_plan_create: null desc");
+  // single tensor; residual / gn_stats pointers are supplied at run time (placeholders keep the level non-null)
+  smb_conv_level_t lv;
+  lv.in = in; lv.out = out;
+  lv.residual = d->has_residual ? out : nullptr;
+  lv.gn_stats = d->gn_stats ? out : nullptr;
+  lv.H = d->H; lv.W = d->W; lv.res_h = d->res_h; lv.res_w = d->res_w;
+  return smb_conv_plan_create_multi(d, 1, &lv, weight, plan_out);
 }
 
 // 7x7/2 stem on the padded NHWC8 image written by smb_image_to_nhwc8:
@@ -539,17 +637,21 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
   smb_conv_plan* pl = new smb_conv_plan();
   memset(&pl->p, 0, sizeof(ConvParams));
   ConvParams& p = pl->p;
+  LevelDesc& L = p.lv[0];
   const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
-  p.n_img = N; p.H_out = Ho; p.W_out = Wo;
-  choose_patch(Ho, Wo, &p.BH, &p.BW);
-  p.tiles_x = cdiv(Wo, p.BW); p.tiles_y = cdiv(Ho, p.BH);
+  p.n_img = N; p.num_levels = 1;
+  L.H_out = Ho; L.W_out = Wo;
+  choose_patch(Ho, Wo, &L.BH, &L.BW);
+  L.tiles_x = cdiv(Wo, L.BW); L.tiles_y = cdiv(Ho, L.BH);
+  L.tile_start = 0; L.map0 = 0; L.out = out;
+  p.tiles_m = N * L.tiles_x * L.tiles_y;
   p.num_taps = 7; p.kb_per_tap = 1;
   p.Cout = 64;
-  p.out = out; p.out_pitch = 64; p.out_f32 = 0; p.alpha = 1.f; p.relu = 1;
-  p.gn_group = 2;
+  p.out_pitch = 64; p.out_f32 = 0; p.alpha = 1.f; p.relu = 1;
+  p.gn_group = 0;
   pl->has_bias = 1;
   const uint64_t rowb = (uint64_t)Wp * 16;
-  const uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+  const uint32_t box[4] = {64, (uint32_t)L.BW, (uint32_t)L.BH, 1};
   int rc = SMB_OK;
   for (int par = 0; par < 2 && rc == SMB_OK; ++par) {
     const int rows = (Hp - par + 1) / 2;
@@ -557,7 +659,7 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
     uint64_t strides[3] = {32, rowb * 2, rowb * Hp};     // 2-pixel step along x: overlapping 8-pixel windows
     rc = encode_map(&p.amap[par], (char*)const_cast<void*>(img_nhwc8) + par * rowb, 4, dims, strides, box);
   }
-  p.amap[2] = p.amap[0]; p.amap[3] = p.amap[1];
+  for (int i = 2; i < kMaxMaps; ++i) p.amap[i] = p.amap[i & 1];
   for (int r = 0; r < 7; ++r) { p.tap_map[r] = r & 1; p.tap_dy[r] = r >> 1; p.tap_dx[r] = 0; }
   if (rc == SMB_OK) rc = finish_plan(pl, 64, 448, weight448);
   if (rc != SMB_OK) { delete pl; return rc; }
@@ -571,13 +673,19 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
                             float alpha, smb_stream_t stream) {
   SMB_CHECK_ARG(plan, "smb_conv_run: null plan");
   SMB_CHECK_ARG(!plan->has_bias || bias, "smb_conv_run: plan expects a bias");
-  SMB_CHECK_ARG(!plan->has_residual || residual, "smb_conv_run: plan expects a residual");
-  SMB_CHECK_ARG(!plan->gn_stats || gn_stats, "smb_conv_run: plan expects a gn_stats buffer");
   ConvParams p = plan->p;
   p.bias = plan->has_bias ? bias : nullptr;
-  p.residual = plan->has_residual ? (const __half*)residual : nullptr;
-  if (!plan->has_residual) p.res_mode = 0;
-  p.gn_stats = plan->gn_stats ? (long long*)gn_stats : nullptr;
+  // single-level plans take residual / statistics pointers at run time; multi-level plans bake them per level
+  if (p.num_levels == 1) {
+    if (plan->has_residual) {
+      SMB_CHECK_ARG(residual, "smb_conv_run: plan expects a residual");
+      p.lv[0].residual = (const __half*)residual;
+    }
+    if (plan->gn_stats) {
+      SMB_CHECK_ARG(gn_stats, "smb_conv_run: plan expects a gn_stats buffer");
+      p.lv[0].gn_stats = (long long*)gn_stats;
+    }
+  }
   p.alpha = alpha;
   static bool attr_done = false;
   if (!attr_done) {

@@ -282,6 +282,141 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, __half* __r
   }
 }
 
+// ------------------------------------------------------------------------------- multi-level (batched) variants
+// The FCOS towers run on five pyramid levels with shared weights; these kernels process all levels in one launch.
+constexpr int kMaxLv = 5;
+struct MultiDesc {
+  int num;
+  long long start[kMaxLv + 1];      // prefix of work items per level
+  const void* a[kMaxLv];
+  const void* b[kMaxLv];
+  void* c[kMaxLv];
+  int H[kMaxLv], W[kMaxLv];
+  float scale[kMaxLv];
+};
+
+__device__ __forceinline__ int find_level(const MultiDesc& d, long long t) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxLv; ++i)
+    if (i < d.num && t >= d.start[i]) l = i;
+  return l;
+}
+
+// GroupNorm(32) + ReLU in place; a[l] = x (fp16 [n_img*hw, C]), b[l] = stats (int64 fixed point).  C/32 % 8 == 0.
+__global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, int relu) {
+  const int vecs = C >> 3;
+  const int cpg = C / 32;
+  const long long total = d.start[d.num];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int l = find_level(d, t);
+    const long long q = t - d.start[l];
+    const int hw = d.H[l] * d.W[l];
+    const int v = (int)(q % vecs);
+    const long long row = q / vecs;
+    const int img = (int)(row / hw);
+    const int g = (v * 8) / cpg;
+    const long long* st = reinterpret_cast<const long long*>(d.b[l]) + ((size_t)img * 32 + g) * 2;
+    const float inv_cnt = 1.0f / ((float)hw * (float)cpg);
+    const float mean = (float)((double)st[0] * (1.0 / kGnSumScale)) * inv_cnt;
+    const float ex2 = (float)((double)st[1] * (1.0 / kGnSqScale)) * inv_cnt;
+    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + eps);
+    uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.c[l]) + row * pitch + v * 8);
+    float f[8];
+    unpack8(*p, f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = (f[j] - mean) * rstd * ga[j] + be[j];
+      f[j] = relu ? fmaxf(y, 0.f) : y;
+    }
+    *p = pack8(f);
+  }
+}
+
+// offsets for all levels: a[l] = raw fcos_reg (fp32, pitch bbox_pitch), c[l] = offsets fp32 [hw, n_off], scale[l] = Scale_l
+__global__ void offset_conv_multi_kernel(MultiDesc d, int bbox_pitch, const float* __restrict__ w, int n_off) {
+  const long long total = d.start[d.num];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int l = find_level(d, t);
+    const long long q = t - d.start[l];
+    const int o = (int)(q % n_off);
+    const long long pix = q / n_off;
+    const float* b = reinterpret_cast<const float*>(d.a[l]) + pix * bbox_pitch;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc = fmaf(__fmul_rn(b[k], d.scale[l]), w[o * 4 + k], acc);
+    reinterpret_cast<float*>(d.c[l])[q] = acc;
+  }
+}
+
+// deformable im2col for all levels: a[l] = x fp16 [n,H,W,C], b[l] = offsets fp32 [n,H,W,dg*18], c[l] = col fp16 [n,H,W,9C]
+// work item = (pixel, tap) handled by one warp.
+__global__ void deform_im2col_multi_kernel(MultiDesc d, int off_pitch, int C, int dg) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = d.start[d.num];
+  const int vecs = C >> 3;
+  const int cpg = C / dg;
+  for (long long wq0 = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); wq0 < total;
+       wq0 += (long long)gridDim.x * warps_per_block) {
+    const int l = find_level(d, wq0);
+    const long long wq = wq0 - d.start[l];
+    const int H = d.H[l], W = d.W[l];
+    const int tap = (int)(wq % 9);
+    const long long pix = wq / 9;
+    const int w_ = (int)(pix % W);
+    const int h_ = (int)((pix / W) % H);
+    const int img = (int)(pix / ((long long)W * H));
+    const int i = tap / 3, j = tap - i * 3;
+    const __half* xim = reinterpret_cast<const __half*>(d.a[l]) + (size_t)img * H * W * C;
+    const float* off = reinterpret_cast<const float*>(d.b[l]);
+    __half* col = reinterpret_cast<__half*>(d.c[l]);
+    for (int v = lane; v < vecs; v += 32) {
+      const int g = (v * 8) / cpg;
+      const float* o = off + pix * off_pitch + g * 18 + 2 * tap;
+      const float h_im = (float)(h_ - 1 + i) + o[0];
+      const float w_im = (float)(w_ - 1 + j) + o[1];
+      float r[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = 0.f;
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+        const int h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        float f[8];
+        if (h_low >= 0 && w_low >= 0) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_low * W + w_low) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] = w1 * f[e];
+        }
+        if (h_low >= 0 && w_high <= W - 1) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_low * W + w_high) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += w2 * f[e];
+        }
+        if (h_high <= H - 1 && w_low >= 0) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_high * W + w_low) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += w3 * f[e];
+        }
+        if (h_high <= H - 1 && w_high <= W - 1) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_high * W + w_high) * C + v * 8)), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] += w4 * f[e];
+        }
+      }
+      *reinterpret_cast<uint4*>(col + (size_t)pix * 9 * C + (size_t)tap * C + v * 8) = pack8(r);
+    }
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 32;
@@ -368,5 +503,60 @@ extern "C" int smb_image_to_nhwc8(const float* img, void* out, int N, int H, int
   const long long total = (long long)N * (H + 6) * (W + 8);
   image_to_nhwc8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)out, N, H, W);
   SMB_LAUNCH_OK("image_to_nhwc8_kernel");
+  return SMB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------ multi-level C ABI
+static int fill_multi(MultiDesc* d, int num, const int* Hs, const int* Ws, long long items_per_pixel, int n_img) {
+  if (num < 1 || num > kMaxLv) return -1;
+  d->num = num;
+  d->start[0] = 0;
+  for (int l = 0; l < num; ++l) {
+    if (Hs[l] <= 0 || Ws[l] <= 0) return -1;
+    d->H[l] = Hs[l]; d->W[l] = Ws[l];
+    d->start[l + 1] = d->start[l] + (long long)n_img * Hs[l] * Ws[l] * items_per_pixel;
+  }
+  return 0;
+}
+
+extern "C" int smb_groupnorm_relu_apply_multi(int num_levels, void* const* xs, const void* const* stats, const int* Hs,
+                                              const int* Ws, int n_img, int C, int pitch, const float* gamma,
+                                              const float* beta, float eps, int relu, smb_stream_t stream) {
+  SMB_CHECK_ARG(xs && stats && Hs && Ws && gamma && beta, "smb_groupnorm_relu_apply_multi: null pointer");
+  SMB_CHECK_ARG(C % 256 == 0 && pitch % 8 == 0 && n_img > 0, "smb_groupnorm_relu_apply_multi: C must be a multiple of 256");
+  MultiDesc d;
+  SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, C / 8, n_img) == 0, "smb_groupnorm_relu_apply_multi: bad levels");
+  for (int l = 0; l < num_levels; ++l) { d.c[l] = xs[l]; d.b[l] = stats[l]; d.a[l] = nullptr; d.scale[l] = 1.f; }
+  gn_apply_multi_kernel<<<grid_for(d.start[num_levels], 256), 256, 0, (cudaStream_t)stream>>>(d, n_img, C, pitch, gamma, beta, eps,
+                                                                                           relu);
+  SMB_LAUNCH_OK("gn_apply_multi_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_offset_conv1x1_multi(int num_levels, const float* const* bboxes, int bbox_pitch, const float* scales,
+                                        const float* weight, int n_off, float* const* offs, const int* Hs, const int* Ws,
+                                        int n_img, smb_stream_t stream) {
+  SMB_CHECK_ARG(bboxes && scales && weight && offs && Hs && Ws && n_off > 0, "smb_offset_conv1x1_multi: bad argument");
+  MultiDesc d;
+  SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, n_off, n_img) == 0, "smb_offset_conv1x1_multi: bad levels");
+  for (int l = 0; l < num_levels; ++l) { d.a[l] = bboxes[l]; d.c[l] = offs[l]; d.b[l] = nullptr; d.scale[l] = scales[l]; }
+  offset_conv_multi_kernel<<<grid_for(d.start[num_levels], 256), 256, 0, (cudaStream_t)stream>>>(d, bbox_pitch, weight, n_off);
+  SMB_LAUNCH_OK("offset_conv_multi_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_deform_im2col_multi(int num_levels, const void* const* xs, const float* const* offs, int off_pitch,
+                                       void* const* cols, const int* Hs, const int* Ws, int n_img, int C,
+                                       int deformable_groups, smb_stream_t stream) {
+  SMB_CHECK_ARG(xs && offs && cols && Hs && Ws, "smb_deform_im2col_multi: null pointer");
+  SMB_CHECK_ARG(C % 8 == 0 && deformable_groups > 0 && C % deformable_groups == 0 && (C / deformable_groups) % 8 == 0,
+                "smb_deform_im2col_multi: C=%d dg=%d unsupported", C, deformable_groups);
+  MultiDesc d;
+  SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, 9, n_img) == 0, "smb_deform_im2col_multi: bad levels");
+  for (int l = 0; l < num_levels; ++l) { d.a[l] = xs[l]; d.b[l] = offs[l]; d.c[l] = cols[l]; d.scale[l] = 1.f; }
+  deform_im2col_multi_kernel<<<grid_for(d.start[num_levels] * 32, 256), 256, 0, (cudaStream_t)stream>>>(d, off_pitch, C,
+                                                                                                    deformable_groups);
+  SMB_LAUNCH_OK("deform_im2col_multi_kernel");
   return SMB_OK;
 }

@@ -96,6 +96,40 @@ __device__ int block_exscan(int v, int* s_warp /* [33] */, int* total) {
   return s_warp[wid] + inc - v;
 }
 
+
+// Radix-select helper: given a 256-bin histogram in shared memory and the rank `need` (1-based) still wanted,
+// warp 0 finds the digit d with sum(hist[0..d-1]) < need <= sum(hist[0..d]) and the rank inside that bin.
+// All threads must call it (contains __syncthreads).
+__device__ __forceinline__ void select_digit(const unsigned* s_hist, int* s_k, unsigned long long* s_prefix,
+                                             unsigned long long prefix, int shift) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int c[8];
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = (int)s_hist[lane * 8 + j]; sum += c[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int excl = incl - sum;
+    const int need = *s_k;
+    if (need > excl && need <= incl) {
+      int r = need - excl, d = lane * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (r > c[j]) { r -= c[j]; ++d; } else break;
+      }
+      *s_k = r;
+      *s_prefix = prefix | ((unsigned long long)d << shift);
+    }
+  }
+  __syncthreads();
+}
+
 // Greedy NMS sweep over `m` boxes already sorted by descending score in shared memory.
 // On return bit r of rem[] is set iff sorted row r is suppressed.  `plus_one`/`cmp_ge` select the
 // reference comparator (nms_kernel.cu:61 `>` vs nms_cpu.cpp:56 `>=`).
@@ -363,17 +397,7 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const float* __restrict__ 
         const unsigned long long k = gkey[g];
         if ((k & himask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int need = s_k, d = 0;
-        for (; d < 256; ++d) {
-          if ((int)s_hist[d] >= need) break;
-          need -= (int)s_hist[d];
-        }
-        s_k = need;
-        s_prefix = prefix | ((unsigned long long)d << shift);
-      }
-      __syncthreads();
+      select_digit(s_hist, &s_k, &s_prefix, prefix, shift);
     }
   } else {
     if (threadIdx.x == 0) s_prefix = ~0ull;
@@ -523,17 +547,7 @@ __global__ void __launch_bounds__(NT) level_topk_kernel(Levels L, int nms_pre, c
       const unsigned long long k = desc_key(sl[i], (unsigned)i);
       if ((k & himask) == prefix) atomicAdd(&s_hist[(unsigned)(k >> shift) & 255u], 1u);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int need = s_k, d = 0;
-      for (; d < 256; ++d) {
-        if ((int)s_hist[d] >= need) break;
-        need -= (int)s_hist[d];
-      }
-      s_k = need;
-      s_prefix = prefix | ((unsigned long long)d << shift);
-    }
-    __syncthreads();
+    select_digit(s_hist, &s_k, &s_prefix, prefix, shift);
   }
   const unsigned long long kth = s_prefix;
   if (threadIdx.x == 0) s_nsel = 0;

@@ -141,16 +141,41 @@ class SipMaskEngine(object):
         self.fpn_outs = [p3, p4, p5, p6, p7]
         self._build_head(self.fpn_outs)
 
-    def _tower_conv(self, x, wkey, gn_prefix, bias_key, stats):
-        """ConvModule: conv3x3 -> GN(32) -> ReLU (conv_module.py:124-132); GN statistics come out of the GEMM epilogue."""
+    def _packed(self, wkey, bias_key=None, cout_pad=None):
+        ck = (wkey, None, bias_key, cout_pad)
+        if ck not in self._wcache:
+            weight, b = C.pack_weight(self._w(wkey), cout_pad=cout_pad, device=self.dev)
+            if bias_key is not None:
+                b = self._w(bias_key).to(self.dev).contiguous()
+            self._wcache[ck] = (weight, b)
+        return self._wcache[ck]
+
+    def _conv_multi(self, xs, weight, k, outs=None, relu=False, bias=None, gn_stats=None, out_dtype=torch.float16,
+                    cout_real=None):
+        N = xs[0].shape[0]
+        if outs is None:
+            outs = [self._t(N, x.shape[1], x.shape[2], weight.shape[0], dtype=out_dtype) for x in xs]
+        plan = C.ConvPlanMulti(xs, weight, outs, k, relu=relu, bias=bias, gn_stats=gn_stats)
+        self._keep.append(plan)
+        self.conv_plans.append(plan)
+        npix = sum(x.shape[1] * x.shape[2] for x in xs)
+        self.conv_flops += 2.0 * N * npix * (cout_real or weight.shape[0]) * weight.shape[1]
+        self._add(plan.run)
+        return outs
+
+    def _tower_conv(self, xs, wkey, gn_prefix, bias_key, stats):
+        """ConvModule: conv3x3 -> GN(32) -> ReLU (conv_module.py:124-132) for all pyramid levels in one launch;
+        GN statistics come out of the GEMM epilogue (per level, per image)."""
         if self.gn:
-            y = self._conv(x, wkey, 3, gn_stats=stats)
+            w, _ = self._packed(wkey)
+            ys = self._conv_multi(xs, w, 3, gn_stats=stats)
             gamma = self._w(gn_prefix + '.weight').to(self.dev)
             beta = self._w(gn_prefix + '.bias').to(self.dev)
             self._keep += [gamma, beta]
-            self._add(lambda: C.groupnorm_relu_apply(y, stats, gamma, beta, 1e-5, True))
-            return y
-        return self._conv(x, wkey, 3, relu=True, bias_key=bias_key)
+            self._add(lambda: C.groupnorm_relu_apply_multi(ys, stats, gamma, beta, 1e-5, True))
+            return ys
+        w, b = self._packed(wkey, bias_key)
+        return self._conv_multi(xs, w, 3, relu=True, bias=b)
 
     def _build_head(self, feats):
         N = self.N
@@ -160,10 +185,9 @@ class SipMaskEngine(object):
         tot = sum(h * w for h, w in sizes)
         nl = len(feats)
         n_tower = (self.stacked - 1) + self.stacked + 1
-        # one fp32 statistics arena for every (level, conv) GroupNorm, zeroed once per forward
-        self.gn_arena = self._t(nl * n_tower, N, 32, 2, dtype=torch.int64, zero=True)
+        # one int64 fixed-point statistics arena for every (conv, level) GroupNorm, zeroed once per forward
+        self.gn_arena = self._t(n_tower, nl, N, 32, 2, dtype=torch.int64, zero=True)
         self._add(lambda: self.gn_arena.zero_(), 0)
-        # shared (across levels) packed weights
         ncls, CC = self.ncls, self.ncls + 128
         CCp = (CC + 15) // 16 * 16
         w_cls = torch.cat([self._w(hp + 'fcos_cls.weight'), self._w(hp + 'sip_cof.weight')], 0)
@@ -181,49 +205,45 @@ class SipMaskEngine(object):
         # level-concatenated fp32 head outputs (channel-last): [tot, 80+128] and [tot, 16 = 4 reg | 1 ctr | pad]
         self.clscof = self._t(N, tot, CCp, dtype=torch.float32)
         self.regctr = self._t(N, tot, 16, dtype=torch.float32)
+        offs0 = [sum(h * w for h, w in sizes[:l]) for l in range(nl)]
+        clscof_l = [self.clscof[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], CCp)
+                    for l in range(nl)]
+        regctr_l = [self.regctr[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], 16)
+                    for l in range(nl)]
+        self.level_views = list(zip(clscof_l, regctr_l))
+        si = 0
+        cls_feats, reg_feats = list(feats), list(feats)
+        for i in range(self.stacked - 1):
+            cls_feats = self._tower_conv(cls_feats, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
+                                         hp + 'cls_convs.%d.conv.bias' % i, [self.gn_arena[si, l] for l in range(nl)])
+            si += 1
+        for i in range(self.stacked):
+            reg_feats = self._tower_conv(reg_feats, hp + 'reg_convs.%d.conv.weight' % i, hp + 'reg_convs.%d.gn' % i,
+                                         hp + 'reg_convs.%d.conv.bias' % i, [self.gn_arena[si, l] for l in range(nl)])
+            si += 1
+        # fcos_reg | fcos_centerness on the reg tower (sipmask_head.py:261,265), raw fp32 (Scale applied by consumers)
+        self._conv_multi(reg_feats, wk_reg, 3, outs=regctr_l, bias=b_reg, cout_real=5)
+        # FeatureAlign: offsets from scale*fcos_reg, DCN 3x3 dg=4, GN, ReLU (sipmask_head.py:49-55)
+        offs = [self._t(N, h, w, 72, dtype=torch.float32) for h, w in sizes]
+        self._add(lambda: C.offset_conv1x1_multi(regctr_l, self.scales, w_off, offs))
+        cols = [self._t(N, h, w, 2304) for h, w in sizes]
+        self._add(lambda: C.deform_im2col_multi(cls_feats, offs, 4, cols))
+        if self.gn:
+            stats = [self.gn_arena[si, l] for l in range(nl)]
+            aligned = self._conv_multi(cols, wk_dcn, 1, gn_stats=stats)
+            gamma = self._w(hp + 'feat_align.norm.weight').to(self.dev)
+            beta = self._w(hp + 'feat_align.norm.bias').to(self.dev)
+            self._keep += [gamma, beta]
+            self._add(lambda: C.groupnorm_relu_apply_multi(aligned, stats, gamma, beta, 1e-5, True))
+        else:
+            aligned = self._conv_multi(cols, wk_dcn, 1, relu=True)
+        # fcos_cls | sip_cof on the aligned feature (sipmask_head.py:264,271)
+        self._conv_multi(aligned, wk_cls, 3, outs=clscof_l, bias=b_cls)
+        # prototype input: reg feature of levels 0..2 at P3 resolution (sipmask_head.py:275-281)
         h3, w3 = sizes[0]
         cat = self._t(N, h3, w3, 768)
-        off0 = 0
-        si = 0
-        self.level_views = []
-        for l, x in enumerate(feats):
-            h, w = sizes[l]
-            cls_feat, reg_feat = x, x
-            for i in range(self.stacked - 1):
-                cls_feat = self._tower_conv(cls_feat, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
-                                            hp + 'cls_convs.%d.conv.bias' % i, self.gn_arena[si])
-                si += 1
-            for i in range(self.stacked):
-                reg_feat = self._tower_conv(reg_feat, hp + 'reg_convs.%d.conv.weight' % i, hp + 'reg_convs.%d.gn' % i,
-                                            hp + 'reg_convs.%d.conv.bias' % i, self.gn_arena[si])
-                si += 1
-            # fcos_reg | fcos_centerness on the reg tower (sipmask_head.py:261,265), raw fp32 (Scale applied by consumers)
-            regctr_l = self.regctr[:, off0:off0 + h * w].view(N, h, w, 16)
-            self._conv(reg_feat, None, 3, weight=wk_reg, bias=b_reg, out=regctr_l, cout_real=5)
-            # FeatureAlign: offsets from scale*fcos_reg, DCN 3x3 dg=4, GN, ReLU (sipmask_head.py:49-55)
-            off = self._t(N, h, w, 72, dtype=torch.float32)
-            sc = self.scales[l]
-            self._add(lambda regctr_l=regctr_l, sc=sc, off=off: C.offset_conv1x1(regctr_l, sc, w_off, off))
-            col = self._t(N, h, w, 2304)
-            self._add(lambda cls_feat=cls_feat, off=off, col=col: C.deform_im2col(cls_feat, off, 4, col))
-            if self.gn:
-                stats = self.gn_arena[si]
-                si += 1
-                aligned = self._conv(col, None, 1, weight=wk_dcn, gn_stats=stats)
-                gamma = self._w(hp + 'feat_align.norm.weight').to(self.dev)
-                beta = self._w(hp + 'feat_align.norm.bias').to(self.dev)
-                self._keep += [gamma, beta]
-                self._add(lambda aligned=aligned, stats=stats, gamma=gamma, beta=beta:
-                          C.groupnorm_relu_apply(aligned, stats, gamma, beta, 1e-5, True))
-            else:
-                aligned = self._conv(col, None, 1, weight=wk_dcn, relu=True)
-            # fcos_cls | sip_cof on the aligned feature (sipmask_head.py:264,271)
-            clscof_l = self.clscof[:, off0:off0 + h * w].view(N, h, w, CCp)
-            self._conv(aligned, None, 3, weight=wk_cls, bias=b_cls, out=clscof_l)
-            if l < 3:   # prototype input: reg feature of levels 0..2 at P3 resolution (sipmask_head.py:275-281)
-                self._add(lambda reg_feat=reg_feat, l=l: C.upsample_bilinear(reg_feat, 2 ** l, out=cat, out_choff=256 * l))
-            self.level_views.append((clscof_l, regctr_l))
-            off0 += h * w
+        for l in range(3):
+            self._add(lambda l=l: C.upsample_bilinear(reg_feats[l], 2 ** l, out=cat, out_choff=256 * l))
         # prototype branch (sipmask_head.py:283-285)
         m0 = self._conv(cat, hp + 'sip_mask_lat0.weight', 1, relu=True, bias_key=hp + 'sip_mask_lat0.bias')
         m1 = self._conv(m0, hp + 'sip_mask_lat.weight', 3, relu=True, bias_key=hp + 'sip_mask_lat.bias')
@@ -258,7 +278,6 @@ class SipMaskEngine(object):
         self.idx = self._t(N, self.max_num, dtype=torch.long)
         self.count = self._t(N, dtype=torch.int32, zero=True)
         self.mask_bits = self._t(N, self.max_num, oh, words, dtype=torch.int32)
-        self.pos = self._t(N, self.max_num, Hm, Wm, dtype=self.pos_dtype)
         self.cand_boxes = self._t(N, ncand, 4, dtype=torch.float32)
         self.cand_scores = self._t(N, ncand, ncls, dtype=torch.float32)
         self.cand_ctr = self._t(N, ncand, dtype=torch.float32)
@@ -318,14 +337,11 @@ class SipMaskEngine(object):
             self._add(gather, 1)
 
             def masks(n=n):
-                L.check(lib.smb_mask_assemble(L.ptr(self.protos[n]), L.F16, 1, L.ptr(self.det_cofs[n]), L.ptr(self.det_boxes4[n]),
-                                              self._box_scale4, L.ptr(self.pos[n]), L.F16 if self.pos_dtype == torch.float16 else L.F32,
-                                              Hm, Wm, self.max_num, L.stream_ptr()), 'smb_mask_assemble')
-                L.check(lib.smb_mask_upsample2_threshold_pack(L.ptr(self.pos[n]), L.F16 if self.pos_dtype == torch.float16 else L.F32,
-                                                              L.ptr(self.mask_bits[n]), self.max_num, Hm, Wm, oh, ow,
-                                                              ctypes.c_float(self.mask_thr), L.stream_ptr()),
-                        'smb_mask_upsample2_threshold_pack')
-            self._add(masks, 2)
+                # fused: prototypes -> sub-region dot/sigmoid/crop -> x2 bilinear -> threshold -> bit-pack (no pos_masks tensor)
+                L.check(lib.smb_mask_assemble_pack(L.ptr(self.protos[n]), L.F16, 1, L.ptr(self.det_cofs[n]), L.ptr(self.det_boxes4[n]),
+                                                   self._box_scale4, L.ptr(self.mask_bits[n]), Hm, Wm, self.max_num, oh, ow,
+                                                   ctypes.c_float(self.mask_thr), L.stream_ptr()), 'smb_mask_assemble_pack')
+            self._add(masks, 1)
 
     # ---------------------------------------------------------------------------------------------- run
     def _run_ops(self):

@@ -247,6 +247,28 @@ def mask_upsample2_threshold_pack(pos, out_hw, thr=0.4, out=None):
     return out
 
 
+def mask_assemble_pack(protos, cofs, boxes, box_scale, out_hw, thr=0.4, layout='chw', out=None):
+    """Fused mask path: prototypes -> bit-packed thresholded masks int32 [N,out_h,ceil(out_w/32)] (no pos_masks tensor)."""
+    _need_cuda(protos, cofs, boxes)
+    protos = protos.contiguous()
+    if layout == 'chw':
+        _, H, W = protos.shape
+    else:
+        H, W, _ = protos.shape
+    N = cofs.shape[0]
+    cofs = cofs.float().contiguous()
+    boxes = boxes.float().contiguous()
+    a = np.atleast_1d(np.asarray(box_scale, dtype=np.float32))
+    bs = L.f4(a if a.size == 4 else [a[0]] * 4)
+    words = (int(out_hw[1]) + 31) // 32
+    if out is None:
+        out = torch.empty((N, int(out_hw[0]), words), dtype=torch.int32, device=protos.device)
+    L.check(L.lib().smb_mask_assemble_pack(L.ptr(protos), _dt(protos), 1 if layout == 'hwc' else 0, L.ptr(cofs), L.ptr(boxes),
+                                           bs, L.ptr(out), H, W, N, int(out_hw[0]), int(out_hw[1]), ctypes.c_float(thr),
+                                           L.stream_ptr()), 'smb_mask_assemble_pack')
+    return out
+
+
 def unpack_mask_bits(bits, out_w):
     """int32 [N,h,words] -> uint8 [N,h,out_w] (host or device tensor); used by tests and result conversion."""
     b = bits.view(torch.uint8) if bits.dtype == torch.int32 else bits

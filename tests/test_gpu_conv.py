@@ -201,3 +201,57 @@ def test_upsample_bilinear_matches_torch():
     out = torch.zeros((1, 13, 21, 768), dtype=torch.float16, device='cuda')
     conv.upsample_bilinear(x, 1, out=out, out_choff=0)
     assert torch.equal(out[..., :256], x)
+
+
+def test_multi_level_conv_and_helpers_match_single_level():
+    """One launch over five pyramid levels == five single-level launches, bit for bit (shared tower weights)."""
+    from sipmask_b200 import conv
+    g = torch.Generator().manual_seed(11)
+    sizes = [(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)]
+    xs = [_nhwc(torch.randn(1, 256, h, w, generator=g)) for h, w in sizes]
+    w = torch.randn(256, 256, 3, 3, generator=g) / 48.0
+    wk, _ = conv.pack_weight(w, device='cuda')
+    st_m = [torch.zeros((1, 32, 2), dtype=torch.int64, device='cuda') for _ in sizes]
+    outs = [torch.empty((1, h, w_, 256), dtype=torch.float16, device='cuda') for h, w_ in sizes]
+    conv.ConvPlanMulti(xs, wk, outs, 3, gn_stats=st_m).run()
+    gamma = (torch.rand(256, generator=g) + 0.5).cuda()
+    beta = torch.randn(256, generator=g).cuda()
+    raw = [o.clone() for o in outs]
+    conv.groupnorm_relu_apply_multi(outs, st_m, gamma, beta)
+    torch.cuda.synchronize()
+    for i, (h, w_) in enumerate(sizes):
+        st = torch.zeros((1, 32, 2), dtype=torch.int64, device='cuda')
+        o = torch.empty((1, h, w_, 256), dtype=torch.float16, device='cuda')
+        conv.ConvPlan(xs[i], wk, o, 3, 1, gn_stats=st).run()
+        torch.cuda.synchronize()
+        assert torch.equal(o, raw[i]) and torch.equal(st, st_m[i]), i
+        _check(o, _ref_conv(xs[i], wk, 3, 1))
+        conv.groupnorm_relu_apply(o, st, gamma, beta)
+        torch.cuda.synchronize()
+        assert (o.float() - outs[i].float()).abs().max().item() <= 2e-3 * (o.float().abs().max().item() + 1)
+    # fp32 multi-level heads with bias into pitch-208 / pitch-16 slices of level-concatenated buffers
+    tot = sum(h * w_ for h, w_ in sizes)
+    big = torch.zeros((1, tot, 208), dtype=torch.float32, device='cuda')
+    offs0 = [sum(h * w_ for h, w_ in sizes[:l]) for l in range(len(sizes))]
+    views = [big[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(1, sizes[l][0], sizes[l][1], 208) for l in range(len(sizes))]
+    w2 = torch.randn(208, 256, 3, 3, generator=g) / 48.0
+    b2 = torch.randn(208, generator=g).cuda()
+    wk2, _ = conv.pack_weight(w2, device='cuda')
+    conv.ConvPlanMulti(xs, wk2, views, 3, bias=b2).run()
+    torch.cuda.synchronize()
+    for i in range(len(sizes)):
+        _check(views[i], _ref_conv(xs[i], wk2, 3, 1, bias=b2), tol=1e-4)
+    # batched offsets + deformable im2col == per-level kernels
+    bbs = [torch.randn(1, h, w_, 16, generator=g).cuda() * 3 for h, w_ in sizes]
+    scales = [1.0, 1.1, 1.2, 1.3, 1.4]
+    w_off = (torch.randn(72, 4, generator=g) * 0.3).cuda()
+    offs = [torch.empty((1, h, w_, 72), dtype=torch.float32, device='cuda') for h, w_ in sizes]
+    cols = [torch.empty((1, h, w_, 2304), dtype=torch.float16, device='cuda') for h, w_ in sizes]
+    conv.offset_conv1x1_multi(bbs, scales, w_off, offs)
+    conv.deform_im2col_multi(xs, offs, 4, cols)
+    torch.cuda.synchronize()
+    for i in range(len(sizes)):
+        o1 = conv.offset_conv1x1(bbs[i], scales[i], w_off)
+        c1 = conv.deform_im2col(xs[i], o1, 4)
+        torch.cuda.synchronize()
+        assert torch.equal(o1, offs[i]) and torch.equal(c1, cols[i]), i

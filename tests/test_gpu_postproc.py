@@ -145,6 +145,17 @@ def test_mask_assemble_matches_oracle(H, W, N, layout, dtype):
     m_ref = cbind.upsample2_thresh(ref, 0.4)
     m_dev = ops.mask_upsample2_threshold(out, (2 * H - 3, 2 * W - 1), 0.4).cpu().numpy()
     assert _iou(m_dev, m_ref[:, :2 * H - 3, :2 * W - 1]).min() >= 0.999
+    # bit-packed variant and the fully fused kernel must agree with the two-step path bit for bit
+    oh, ow = 2 * H - 3, 2 * W - 1
+    packed = ops.unpack_mask_bits(ops.mask_upsample2_threshold_pack(out, (oh, ow), 0.4), ow).cpu().numpy()
+    assert _iou(packed, m_ref[:, :oh, :ow]).min() >= 0.999
+    fused = ops.unpack_mask_bits(ops.mask_assemble_pack(p_dev, cofs.cuda(), boxes.cuda(), 0.5, (oh, ow), 0.4, layout=layout), ow).cpu().numpy()
+    assert _iou(fused, m_ref[:, :oh, :ow]).min() >= 0.999
+    assert (fused != packed).mean() < 1e-5
+    fused_full = ops.unpack_mask_bits(ops.mask_assemble_pack(p_dev, cofs.cuda(), boxes.cuda(), 0.5, (2 * H + 5, 2 * W + 40), 0.4,
+                                                             layout=layout), 2 * W + 40).cpu().numpy()
+    assert fused_full[:, 2 * H:].sum() == 0 and fused_full[:, :, 2 * W:].sum() == 0       # beyond the x2 frame: zeros
+    assert _iou(fused_full[:, :2 * H, :2 * W], m_ref).min() >= 0.999
     # fp16 output variant
     out16 = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float16)
     np.testing.assert_allclose(out16.float().cpu().numpy(), ref, atol=1e-3, rtol=0)
