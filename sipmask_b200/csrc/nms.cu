@@ -249,11 +249,110 @@ __device__ void greedy_sweep_n(const float4* sb, int m, float thr, int cmp_ge, f
 //   ws_score[C][n] float : their score*ctr
 //   ws_count[C]          : number kept
 // ---------------------------------------------------------------------------------------------
-struct McSmem {
+// Multi-class NMS, stage 1a: one CTA per class - candidate compaction (raw score > thr), score *= ctr, stable
+// descending sort.  Writes, per class c (row pitch n):
+//   w_cidx[c][pos]   candidate row (ascending)          w_cscore[c][pos]  score*ctr
+//   w_keys[c][r]     sorted composite keys (low 32 bits = pos)    w_sbox[c][r]  boxes in sorted order
+//   w_m[c]           number of candidates
+struct McPrepSmem {
   unsigned long long keys[MAXN];
-  float4 sb[MAXN];
   int cidx[MAXN];
   float cscore[MAXN];
+  int warp[33];
+};
+
+__global__ void __launch_bounds__(NT) mc_prepare_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
+                                                        const float* __restrict__ ctr, int n, int C, float score_thr,
+                                                        int* __restrict__ w_cidx, float* __restrict__ w_cscore,
+                                                        unsigned long long* __restrict__ w_keys, float4* __restrict__ w_sbox,
+                                                        int* __restrict__ w_m) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  McPrepSmem& S = *reinterpret_cast<McPrepSmem*>(smem_raw);
+  const int c = blockIdx.x;
+  int m = 0;
+  for (int base = 0; base < n; base += NT) {
+    const int i = base + threadIdx.x;
+    float s = 0.f;
+    int f = 0;
+    if (i < n) { s = scores[(size_t)i * C + c]; f = s > score_thr; }       // bbox_nms.py:111
+    int tot;
+    const int ex = block_exscan(f, S.warp, &tot);
+    if (f) { S.cidx[m + ex] = i; S.cscore[m + ex] = __fmul_rn(s, ctr[i]); }  // bbox_nms.py:122
+    m += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) w_m[c] = m;
+  if (m == 0) return;
+  int P = 1;
+  while (P < m) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += NT) S.keys[i] = (i < m) ? desc_key(S.cscore[i], (unsigned)i) : ~0ull;
+  bitonic_sort(S.keys, P);
+  for (int r = threadIdx.x; r < m; r += NT) {
+    const unsigned long long k = S.keys[r];
+    const int pos = (int)(k & 0xffffffffu);
+    w_keys[(size_t)c * n + r] = k;
+    w_sbox[(size_t)c * n + r] = *reinterpret_cast<const float4*>(boxes + (size_t)S.cidx[pos] * 4);
+    w_cidx[(size_t)c * n + r] = S.cidx[r];          // by position (r < m covers all positions)
+    w_cscore[(size_t)c * n + r] = S.cscore[r];
+  }
+}
+
+// Stage 1b: suppression bit-matrix, spread over the whole GPU.  Work item = one 64x64 tile (class c, row block rb,
+// column block cb >= rb); bit t of mask[c][rb*64 + r][cb] is set iff IoU(sorted r, sorted cb*64+t) exceeds the
+// threshold and the column comes later in the sorted order (ops/nms/src/nms_kernel.cu:24-68, all classes at once).
+__global__ void __launch_bounds__(64) mc_mask_kernel(const float4* __restrict__ w_sbox, const int* __restrict__ w_m, int n, int C,
+                                                     int nbmax, float iou_thr, int cmp_ge,
+                                                     unsigned long long* __restrict__ mask) {
+  __shared__ int s_pref[1025];
+  __shared__ float4 s_col[64];
+  __shared__ int s_tile[3];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < C; ++c) {
+      s_pref[c] = acc;
+      const int nb = (w_m[c] + 63) >> 6;
+      acc += nb * (nb + 1) / 2;
+    }
+    s_pref[C] = acc;
+  }
+  __syncthreads();
+  const int total = s_pref[C];
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    if (threadIdx.x == 0) {
+      int c = 0;
+      while (s_pref[c + 1] <= t) ++c;
+      int u = t - s_pref[c];
+      const int nb = (w_m[c] + 63) >> 6;
+      int rb = 0;
+      while (u >= nb - rb) { u -= nb - rb; ++rb; }
+      s_tile[0] = c; s_tile[1] = rb; s_tile[2] = rb + u;
+    }
+    __syncthreads();
+    const int c = s_tile[0], rb = s_tile[1], cb = s_tile[2];
+    const int m = w_m[c];
+    const float4* sb = w_sbox + (size_t)c * n;
+    const int col = cb * 64 + threadIdx.x;
+    s_col[threadIdx.x] = (col < m) ? sb[col] : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int row = rb * 64 + threadIdx.x;
+    if (row < m) {
+      const float4 a = sb[row];
+      unsigned long long bits = 0ull;
+      const int lim = min(64, m - cb * 64);
+      const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+      for (int q = start; q < lim; ++q) {
+        const float v = iou_ref(a, s_col[q], 1.0f);
+        if (cmp_ge ? (v >= iou_thr) : (v > iou_thr)) bits |= 1ull << q;
+      }
+      mask[((size_t)c * n + row) * nbmax + cb] = bits;
+    }
+    __syncthreads();
+  }
+}
+
+// Stage 1c: one CTA per class - sequential sweep over the bit-matrix (the reference does this on the host after a
+// D2H copy, nms_kernel.cu:105-131), then kept rows in ascending candidate order (nms_kernel.cu:135-138).
+struct McSweepSmem {
   unsigned long long rem[MAXN / 64];
   unsigned long long diag[64];
   unsigned long long keepbits;
@@ -261,48 +360,55 @@ struct McSmem {
   unsigned char kept[MAXN];
 };
 
-__global__ void __launch_bounds__(NT) mc_nms_class_kernel(const float* __restrict__ boxes, const float* __restrict__ scores,
-                                                          const float* __restrict__ ctr, int n, int C, float score_thr,
-                                                          float iou_thr, int cmp_ge, int* __restrict__ ws_idx,
-                                                          float* __restrict__ ws_score, int* __restrict__ ws_count) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  McSmem& S = *reinterpret_cast<McSmem*>(smem_raw);
+__global__ void __launch_bounds__(NT) mc_sweep_kernel(const unsigned long long* __restrict__ mask,
+                                                      const unsigned long long* __restrict__ w_keys,
+                                                      const int* __restrict__ w_cidx, const float* __restrict__ w_cscore,
+                                                      const int* __restrict__ w_m, int n, int nbmax, int* __restrict__ ws_idx,
+                                                      float* __restrict__ ws_score, int* __restrict__ ws_count) {
+  __shared__ McSweepSmem S;
   const int c = blockIdx.x;
-  // 1. ordered compaction of candidates: raw score > score_thr (bbox_nms.py:111), then *= ctr (:122)
-  int m = 0;
-  for (int base = 0; base < n; base += NT) {
-    const int i = base + threadIdx.x;
-    float s = 0.f;
-    int f = 0;
-    if (i < n) { s = scores[(size_t)i * C + c]; f = s > score_thr; }
-    int tot;
-    const int ex = block_exscan(f, S.warp, &tot);
-    if (f) { S.cidx[m + ex] = i; S.cscore[m + ex] = __fmul_rn(s, ctr[i]); }
-    m += tot;
-    __syncthreads();
-  }
+  const int m = w_m[c];
   if (m == 0) {
     if (threadIdx.x == 0) ws_count[c] = 0;
     return;
   }
-  // 2. sort by descending score, ties -> lower row first
-  int P = 1;
-  while (P < m) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += NT) S.keys[i] = (i < m) ? desc_key(S.cscore[i], (unsigned)i) : ~0ull;
-  bitonic_sort(S.keys, P);
-  for (int r = threadIdx.x; r < m; r += NT) {
-    const int i = S.cidx[(int)(S.keys[r] & 0xffffffffu)];
-    S.sb[r] = *reinterpret_cast<const float4*>(boxes + (size_t)i * 4);
-  }
+  const int nb = (m + 63) >> 6;
+  const unsigned long long* mk = mask + (size_t)c * n * nbmax;
+  for (int i = threadIdx.x; i < MAXN / 64; i += NT) S.rem[i] = 0ull;
   __syncthreads();
-  // 3. greedy sweep (legacy +1 IoU)
-  greedy_sweep(S.sb, m, iou_thr, cmp_ge, 1.0f, S.rem, S.diag, &S.keepbits);
+  for (int b = 0; b < nb; ++b) {
+    const int base = b << 6;
+    if (threadIdx.x < 64) S.diag[threadIdx.x] = (base + threadIdx.x < m) ? mk[(size_t)(base + threadIdx.x) * nbmax + b] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = S.rem[b], keep = 0ull;
+      const int lim = min(64, m - base);
+      for (int t = 0; t < lim; ++t)
+        if (!((cur >> t) & 1ull)) { keep |= 1ull << t; cur |= S.diag[t]; }
+      S.rem[b] = cur;
+      S.keepbits = keep;
+    }
+    __syncthreads();
+    // OR the rows of the kept boxes into the later column words: thread = (column word j, row slice)
+    const unsigned long long keep = S.keepbits;
+    const int nlater = nb - (b + 1);
+    if (nlater > 0) {
+      const int j = b + 1 + (threadIdx.x % nlater);
+      const int slice = threadIdx.x / nlater, nslices = NT / nlater;
+      if (slice < nslices) {
+        unsigned long long acc = 0ull;
+        for (int t = slice; t < 64; t += nslices)
+          if ((keep >> t) & 1ull) acc |= mk[(size_t)(base + t) * nbmax + j];
+        if (acc) atomicOr(&S.rem[j], acc);
+      }
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < m; i += NT) S.kept[i] = 0;
   __syncthreads();
   for (int r = threadIdx.x; r < m; r += NT)
-    if (!((S.rem[r >> 6] >> (r & 63)) & 1ull)) S.kept[(int)(S.keys[r] & 0xffffffffu)] = 1;
+    if (!((S.rem[r >> 6] >> (r & 63)) & 1ull)) S.kept[(int)(w_keys[(size_t)c * n + r] & 0xffffffffu)] = 1;
   __syncthreads();
-  // 4. kept rows in ascending candidate order (nms_kernel.cu:135-138)
   int running = 0;
   for (int base = 0; base < m; base += NT) {
     const int p = base + threadIdx.x;
@@ -310,8 +416,8 @@ __global__ void __launch_bounds__(NT) mc_nms_class_kernel(const float* __restric
     int tot;
     const int ex = block_exscan(f, S.warp, &tot);
     if (f) {
-      ws_idx[(size_t)c * n + running + ex] = S.cidx[p];
-      ws_score[(size_t)c * n + running + ex] = S.cscore[p];
+      ws_idx[(size_t)c * n + running + ex] = w_cidx[(size_t)c * n + p];
+      ws_score[(size_t)c * n + running + ex] = w_cscore[(size_t)c * n + p];
     }
     running += tot;
     __syncthreads();
@@ -649,19 +755,34 @@ extern "C" int smb_nms(const float* dets, int n, float iou_thr, int cmp_ge, int 
   return SMB_OK;
 }
 
-static size_t mc_ws_layout(int n, int C, size_t* o_idx, size_t* o_score, size_t* o_count, size_t* o_gkey, size_t* o_gval) {
+struct McWs {
+  size_t idx, score, count, gkey, gval, cidx, cscore, keys, sbox, m, mask, total;
+};
+
+static McWs mc_ws_layout(int n, int C, bool with_mask) {
+  McWs w;
   size_t off = 0;
-  *o_idx = off;   off = align_up(off + (size_t)C * n * sizeof(int), 256);
-  *o_score = off; off = align_up(off + (size_t)C * n * sizeof(float), 256);
-  *o_count = off; off = align_up(off + (size_t)(C + 1) * sizeof(int), 256);
-  *o_gkey = off;  off = align_up(off + (size_t)C * n * sizeof(unsigned long long), 256);
-  *o_gval = off;  off = align_up(off + (size_t)C * n * sizeof(int), 256);
-  return off;
+  w.idx = off;    off = align_up(off + (size_t)C * n * sizeof(int), 256);
+  w.score = off;  off = align_up(off + (size_t)C * n * sizeof(float), 256);
+  w.count = off;  off = align_up(off + (size_t)(C + 1) * sizeof(int), 256);
+  w.gkey = off;   off = align_up(off + (size_t)C * n * sizeof(unsigned long long), 256);
+  w.gval = off;   off = align_up(off + (size_t)C * n * sizeof(int), 256);
+  w.cidx = w.cscore = w.keys = w.sbox = w.m = w.mask = off;
+  if (with_mask) {
+    const int nbmax = (n + 63) / 64;
+    w.cidx = off;   off = align_up(off + (size_t)C * n * sizeof(int), 256);
+    w.cscore = off; off = align_up(off + (size_t)C * n * sizeof(float), 256);
+    w.keys = off;   off = align_up(off + (size_t)C * n * sizeof(unsigned long long), 256);
+    w.sbox = off;   off = align_up(off + (size_t)C * n * sizeof(float4), 256);
+    w.m = off;      off = align_up(off + (size_t)(C + 1) * sizeof(int), 256);
+    w.mask = off;   off = align_up(off + (size_t)C * n * nbmax * sizeof(unsigned long long), 256);
+  }
+  w.total = off;
+  return w;
 }
 
 extern "C" size_t smb_multiclass_nms_workspace_bytes(int n, int num_classes) {
-  size_t a, b, c, d, e;
-  return mc_ws_layout(n > 0 ? n : 1, num_classes, &a, &b, &c, &d, &e);
+  return mc_ws_layout(n > 0 ? n : 1, num_classes, true).total;
 }
 
 extern "C" int smb_multiclass_nms(const float* boxes, const float* scores, const float* ctr, int n, int num_classes,
@@ -672,38 +793,46 @@ extern "C" int smb_multiclass_nms(const float* boxes, const float* scores, const
   SMB_CHECK_ARG(num_classes >= 1 && num_classes <= 1024, "smb_multiclass_nms: num_classes=%d", num_classes);
   SMB_CHECK_ARG(max_num >= 1 && max_num <= 1024, "smb_multiclass_nms: max_num=%d outside [1,1024]", max_num);
   SMB_CHECK_ARG(det_out && label_out && idx_out && count_out && workspace, "smb_multiclass_nms: null pointer");
-  size_t o_idx, o_score, o_count, o_gkey, o_gval;
-  const size_t need = mc_ws_layout(n > 0 ? n : 1, num_classes, &o_idx, &o_score, &o_count, &o_gkey, &o_gval);
-  if (workspace_bytes < need) {
-    set_error("smb_multiclass_nms: workspace %zu < %zu", workspace_bytes, need);
+  const int nn = n > 0 ? n : 1;
+  const McWs w = mc_ws_layout(nn, num_classes, true);
+  if (workspace_bytes < w.total) {
+    set_error("smb_multiclass_nms: workspace %zu < %zu", workspace_bytes, w.total);
     return SMB_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  int* ws_count = (int*)(ws + o_count);
+  int* ws_count = (int*)(ws + w.count);
   static bool attr_done = false;
   if (!attr_done) {
-    SMB_CUDA_OK(cudaFuncSetAttribute(mc_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McSmem)));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McPrepSmem)));
     attr_done = true;
   }
   if (n == 0) {
     SMB_CUDA_OK(cudaMemsetAsync(ws_count, 0, sizeof(int) * (num_classes + 1), st));
   } else {
-    mc_nms_class_kernel<<<num_classes, NT, sizeof(McSmem), st>>>(boxes, scores, ctr, n, num_classes, score_thr, iou_thr,
-                                                                 cmp_ge, (int*)(ws + o_idx), (float*)(ws + o_score), ws_count);
-    SMB_LAUNCH_OK("mc_nms_class_kernel");
+    const int nbmax = (n + 63) / 64;
+    mc_prepare_kernel<<<num_classes, NT, sizeof(McPrepSmem), st>>>(boxes, scores, ctr, n, num_classes, score_thr, (int*)(ws + w.cidx),
+                                                                   (float*)(ws + w.cscore), (unsigned long long*)(ws + w.keys),
+                                                                   (float4*)(ws + w.sbox), (int*)(ws + w.m));
+    SMB_LAUNCH_OK("mc_prepare_kernel");
+    mc_mask_kernel<<<148 * 16, 64, 0, st>>>((const float4*)(ws + w.sbox), (const int*)(ws + w.m), n, num_classes, nbmax, iou_thr,
+                                            cmp_ge, (unsigned long long*)(ws + w.mask));
+    SMB_LAUNCH_OK("mc_mask_kernel");
+    mc_sweep_kernel<<<num_classes, NT, 0, st>>>((const unsigned long long*)(ws + w.mask), (const unsigned long long*)(ws + w.keys),
+                                                (const int*)(ws + w.cidx), (const float*)(ws + w.cscore), (const int*)(ws + w.m), n,
+                                                nbmax, (int*)(ws + w.idx), (float*)(ws + w.score), ws_count);
+    SMB_LAUNCH_OK("mc_sweep_kernel");
   }
-  finalize_kernel<<<1, NT, 0, st>>>(boxes, n, num_classes, max_num, 0, (const int*)(ws + o_idx), (const float*)(ws + o_score),
-                                    ws_count, n > 0 ? n : 1, (unsigned long long*)(ws + o_gkey), (int*)(ws + o_gval), det_out,
+  finalize_kernel<<<1, NT, 0, st>>>(boxes, n, num_classes, max_num, 0, (const int*)(ws + w.idx), (const float*)(ws + w.score),
+                                    ws_count, nn, (unsigned long long*)(ws + w.gkey), (int*)(ws + w.gval), det_out,
                                     (long long*)label_out, (long long*)idx_out, count_out);
   SMB_LAUNCH_OK("finalize_kernel");
   return SMB_OK;
 }
 
 extern "C" size_t smb_fast_nms_workspace_bytes(int n, int num_classes, int top_k) {
-  size_t a, b, c, d, e;
   (void)n;
-  return mc_ws_layout(top_k, num_classes, &a, &b, &c, &d, &e);
+  return mc_ws_layout(top_k, num_classes, false).total;
 }
 
 extern "C" int smb_fast_nms(const float* boxes, const float* scores, const float* ctr, int n, int num_classes,
@@ -713,10 +842,10 @@ extern "C" int smb_fast_nms(const float* boxes, const float* scores, const float
   SMB_CHECK_ARG(top_k >= 1 && top_k <= 256, "smb_fast_nms: top_k=%d outside [1,256]", top_k);
   SMB_CHECK_ARG(num_classes >= 1 && num_classes <= 1024 && max_num >= 1 && max_num <= 1024, "smb_fast_nms: bad sizes");
   SMB_CHECK_ARG(det_out && label_out && idx_out && count_out && workspace, "smb_fast_nms: null pointer");
-  size_t o_idx, o_score, o_count, o_gkey, o_gval;
-  const size_t need = mc_ws_layout(top_k, num_classes, &o_idx, &o_score, &o_count, &o_gkey, &o_gval);
-  if (workspace_bytes < need) {
-    set_error("smb_fast_nms: workspace %zu < %zu", workspace_bytes, need);
+  const McWs w = mc_ws_layout(top_k, num_classes, false);
+  const size_t o_idx = w.idx, o_score = w.score, o_count = w.count, o_gkey = w.gkey, o_gval = w.gval;
+  if (workspace_bytes < w.total) {
+    set_error("smb_fast_nms: workspace %zu < %zu", workspace_bytes, w.total);
     return SMB_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;

@@ -46,6 +46,7 @@ class SipMaskEngine(object):
         self._keep = []
         self._wcache = {}
         self.conv_plans = []
+        self.conv_meta = []
         self.conv_flops = 0.0
         self._build()
         self.graph = None
@@ -90,7 +91,10 @@ class SipMaskEngine(object):
                           residual_upsample=residual_upsample, gn_stats=gn_stats, cin=cin)
         self._keep.append(plan)
         self.conv_plans.append(plan)
-        self.conv_flops += 2.0 * N * Ho * Wo * (cout_real or weight.shape[0]) * weight.shape[1]   # algorithmic FLOPs
+        fl = 2.0 * N * Ho * Wo * (cout_real or weight.shape[0]) * weight.shape[1]                 # algorithmic FLOPs
+        self.conv_flops += fl
+        self.conv_meta.append(dict(name=wkey or 'shared', M=N * Ho * Wo, N=weight.shape[0], K=weight.shape[1], k=k, stride=stride,
+                                   flops=fl, res=residual is not None, gn=gn_stats is not None))
         self._add(plan.run)
         return out
 
@@ -106,7 +110,9 @@ class SipMaskEngine(object):
         stem = C.StemPlan(img8, wk, b, s1, N, H, W)
         self._keep += [stem, wk, b]
         self.conv_plans.append(stem)
-        self.conv_flops += 2.0 * N * (H // 2) * (W // 2) * 64 * 147                   # algorithmic 7x7x3 (executed K is 448)
+        fl = 2.0 * N * (H // 2) * (W // 2) * 64 * 147                                 # algorithmic 7x7x3 (executed K is 448)
+        self.conv_flops += fl
+        self.conv_meta.append(dict(name='stem', M=N * (H // 2) * (W // 2), N=64, K=448, k=7, stride=2, flops=fl, res=False, gn=False))
         self._add(stem.run)
         x = self._t(N, H // 4, W // 4, 64)
         self._add(lambda s1=s1, x=x: C.maxpool3x3s2(s1, x))
@@ -159,7 +165,10 @@ class SipMaskEngine(object):
         self._keep.append(plan)
         self.conv_plans.append(plan)
         npix = sum(x.shape[1] * x.shape[2] for x in xs)
-        self.conv_flops += 2.0 * N * npix * (cout_real or weight.shape[0]) * weight.shape[1]
+        fl = 2.0 * N * npix * (cout_real or weight.shape[0]) * weight.shape[1]
+        self.conv_flops += fl
+        self.conv_meta.append(dict(name='multi-level x%d' % len(xs), M=N * npix, N=weight.shape[0], K=weight.shape[1], k=k, stride=1,
+                                   flops=fl, res=False, gn=gn_stats is not None))
         self._add(plan.run)
         return outs
 
