@@ -19,6 +19,7 @@
 //  * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer,
 //    warps 2..5 = epilogue (tcgen05.ld -> scale/bias/residual/ReLU/GN statistics -> global NHWC store).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,7 +28,8 @@ namespace smb {
 constexpr int kMaxTaps = 9;
 constexpr int kMaxMaps = 8;
 constexpr int kMaxLevels = 5;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue (2 per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
 constexpr int kABytes = 128 * 64 * 2;   // one A stage: 128 pixels x 64 channels fp16
 
 // One pyramid level (or the only tensor) of a launch.  Convolutions whose weights are shared by several feature-pyramid
@@ -52,6 +54,7 @@ struct ConvParams {
   int num_taps, kb_per_tap;       // k-blocks (64 channels) per tap
   int n_img, tiles_m;
   int Cout, n_tile, n_tiles_n, stages, tmem_cols, num_acc;
+  int cluster;                    // CTAs per cluster sharing (multicasting) the weight tile: 1, 2 or 4
   int out_pitch; int out_f32;
   const float* bias; float alpha;
   int res_pitch; int res_mode;
@@ -97,6 +100,28 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -164,16 +189,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+
+// work unit -> tile.  A unit is a group of `cluster` consecutive M-tiles that share one N-tile (their CTAs multicast the
+// weight tile to each other); units of the same M-group with different N-tiles are adjacent so concurrently running
+// clusters share the activation patches in L2.  A CTA whose M-tile index runs past the end gets a clamped tile and
+// active == false (it still takes part in the multicast / barrier protocol but stores nothing).
 struct TileCoord {
   int lvl, img, x0, y0, n0;
+  bool active;
 };
 
-// launch-wide tile id -> (level, image, patch origin, first output channel); N-tiles of one M-tile are adjacent so
-// that CTAs running concurrently share the same activation patch in L2.
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+__device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int unit, int rank) {
   TileCoord t;
-  const int nt = tile % p.n_tiles_n;
-  int mt = tile / p.n_tiles_n;
+  const int nt = unit % p.n_tiles_n;
+  int mt = (unit / p.n_tiles_n) * p.cluster + rank;
+  t.active = mt < p.tiles_m;
+  if (!t.active) mt = p.tiles_m - 1;
   int l = 0;
 #pragma unroll
   for (int i = 1; i < kMaxLevels; ++i)
@@ -208,17 +241,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
     tma_prefetch_desc(&p.bmap);
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();             // peers must see initialised barriers before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.tiles_m * p.n_tiles_n;
+  const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
+  const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
+  const int total_units = cdiv_dev(p.tiles_m, p.cluster) * p.n_tiles_n;
   const int kblocks = p.num_taps * p.kb_per_tap;
   const uint32_t stage_bytes = (uint32_t)(kABytes + b_bytes);
 
@@ -226,8 +263,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (lane == 0) {
       // ===================== TMA producer =====================
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      const int b_part = b_bytes / p.cluster, n_part = p.n_tile / p.cluster;
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+        const TileCoord tc = decode_tile(p, unit, crank);
         const int map0 = p.lv[tc.lvl].map0;
         for (int t = 0; t < p.num_taps; ++t) {
           const CUtensorMap* am = &p.amap[map0 + p.tap_map[t]];
@@ -235,10 +273,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int kc = 0; kc < p.kb_per_tap; ++kc, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_wait(&empty_bar[s], ph ^ 1);      // every CTA of the cluster has finished reading stage s
             mbar_expect_tx(&full_bar[s], stage_bytes);
             tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, tc.img);
-            tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], (t * p.kb_per_tap + kc) * 64, tc.n0);
+            const int kcoord = (t * p.kb_per_tap + kc) * 64;
+            if (p.cluster == 1) {
+              tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], kcoord, tc.n0);
+            } else {
+              // this CTA fetches 1/cluster of the weight tile and multicasts it into every CTA of the cluster
+              tma_load_2d_mc(sB + (size_t)s * b_bytes + (size_t)crank * b_part, &p.bmap, &full_bar[s], kcoord,
+                             tc.n0 + crank * n_part, cmask);
+            }
           }
         }
       }
@@ -248,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // ===================== MMA issuer =====================
       const uint32_t idesc = make_idesc(128, p.n_tile);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
         const int acc = lt % p.num_acc;
         const uint32_t acc_ph = (lt / p.num_acc) & 1;
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
@@ -266,49 +311,74 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in the >>4 start field
             umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);              // frees the smem stage when these MMAs retire
+          if (p.cluster == 1) umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+          else umma_commit_mc(&empty_bar[s], cmask);         // ... in every CTA of the cluster (peers write into it)
         }
         umma_commit(&tfull_bar[acc]);              // accumulator complete
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int lane_grp = warp & 3;                   // TMEM lanes 32*(warp%4) .. +31 are accessible to this warp
+    // ===================== epilogue warps (2..9) =====================
+    // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); the pair splits the tile's
+    // columns, which doubles the loads/stores in flight of this latency-bound phase.
+    const int lane_grp = warp & 3;
+    const int col_half = (warp - 2) >> 2;
     const int row = lane_grp * 32 + lane;
-    const int et = threadIdx.x - 64;                 // 0..127 within the epilogue group
+    const int et = threadIdx.x - 64;                 // 0..255 within the epilogue group
+    int split = ((p.n_tile / 2 + 31) / 32) * 32;
+    if (split > p.n_tile) split = p.n_tile;
+    const int c_begin = col_half ? split : 0, c_end = col_half ? p.n_tile : split;
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
+      const TileCoord tc = decode_tile(p, unit, crank);
       const LevelDesc& L = p.lv[tc.lvl];
       const int iy = row / L.BW, ix = row - iy * L.BW;
       const int x = tc.x0 + ix, y = tc.y0 + iy, n0 = tc.n0;
-      const bool valid = (x < L.W_out) && (y < L.H_out);
+      const bool valid = tc.active && (x < L.W_out) && (y < L.H_out);
       const size_t pix = ((size_t)tc.img * L.H_out + y) * L.W_out + x;
       const __half* res_row = nullptr;
-      if (p.res_mode == 1) {
-        res_row = L.residual + pix * p.res_pitch;
-      } else if (p.res_mode == 2) {
-        // F.interpolate(mode='nearest', size=...) : src = min(floor(dst * in/out), in-1)   (fpn.py:149-152)
-        const int sy = min((int)floorf((float)y * ((float)L.res_h / (float)L.H_out)), L.res_h - 1);
-        const int sx = min((int)floorf((float)x * ((float)L.res_w / (float)L.W_out)), L.res_w - 1);
-        res_row = L.residual + (((size_t)tc.img * L.res_h + sy) * L.res_w + sx) * p.res_pitch;
+      if (valid) {
+        if (p.res_mode == 1) {
+          res_row = L.residual + pix * p.res_pitch;
+        } else if (p.res_mode == 2) {
+          // F.interpolate(mode='nearest', size=...) : src = min(floor(dst * in/out), in-1)   (fpn.py:149-152)
+          const int sy = min((int)floorf((float)y * ((float)L.res_h / (float)L.H_out)), L.res_h - 1);
+          const int sx = min((int)floorf((float)x * ((float)L.res_w / (float)L.W_out)), L.res_w - 1);
+          res_row = L.residual + (((size_t)tc.img * L.res_h + sy) * L.res_w + sx) * p.res_pitch;
+        }
+      }
+      // residual prefetch (one 32-channel chunk ahead of the accumulator drain)
+      uint4 rcur[4], rnext[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { rcur[j] = make_uint4(0u, 0u, 0u, 0u); rnext[j] = make_uint4(0u, 0u, 0u, 0u); }
+      if (res_row && c_begin < c_end) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + c_begin + j * 8 + 8 <= p.Cout && c_begin + j * 8 < c_end)
+            rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c_begin + j * 8));
       }
       // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile)
       float* sb = s_bias + (lt & 1) * 256;
       if (p.bias) {
-        for (int c = et; c < p.n_tile; c += 128) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
+        for (int c = et; c < p.n_tile; c += kEpiThreads) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int acc = lt % p.num_acc;
       const uint32_t acc_ph = (lt / p.num_acc) & 1;
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        if (res_row && c0 + 32 < c_end) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n0 + c0 + 32 + j * 8 + 8 <= p.Cout && c0 + 32 + j * 8 < c_end)
+              rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c0 + 32 + j * 8));
+        }
         uint32_t v[32];
-        if (c0 + 32 <= p.n_tile) {
+        if (c0 + 32 <= c_end) {
           tmem_ld32(t_base + (uint32_t)c0, v);
-        } else {                                     // n_tile % 32 == 16: last half chunk
+        } else {                                     // 16-column tail
           tmem_ld16(t_base + (uint32_t)c0, v);
 #pragma unroll
           for (int j = 16; j < 32; ++j) v[j] = 0u;
@@ -317,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                // two 16-channel halves
           const int ch0 = n0 + c0 + h * 16;
-          if (c0 + h * 16 >= p.n_tile || ch0 >= p.Cout) continue;     // uniform across the CTA
+          if (c0 + h * 16 >= c_end || ch0 >= p.Cout) continue;     // warp-uniform
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
@@ -333,11 +403,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] *= p.alpha;
           }
-          if (res_row && valid) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(res_row + ch0);
-            const uint4 ra = __ldg(r4), rb = __ldg(r4 + 1);
-            const __half2* ha = reinterpret_cast<const __half2*>(&ra);
-            const __half2* hb = reinterpret_cast<const __half2*>(&rb);
+          if (res_row) {
+            const __half2* ha = reinterpret_cast<const __half2*>(&rcur[2 * h]);
+            const __half2* hb = reinterpret_cast<const __half2*>(&rcur[2 * h + 1]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 a = __half22float2(ha[j]), b = __half22float2(hb[j]);
@@ -403,8 +471,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
       }
-      // this warp has drained its quarter of the accumulator
+      // this warp has drained its share of the accumulator
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -412,7 +482,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();             // no CTA may exit while peers can still multicast to / arrive on it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -489,12 +560,17 @@ static void choose_patch(int H, int W, int* BH, int* BW) {
 
 static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weight) {
   ConvParams& p = pl->p;
-  // N tile: whole Cout when <= 256 (rounded to 16), else 256 / 128 divisors
-  int n_tile;
-  if (Cout <= 256) n_tile = (Cout + 15) / 16 * 16;
-  else if (Cout % 256 == 0) n_tile = 256;
-  else if (Cout % 128 == 0) n_tile = 128;
-  else { set_error("conv plan: unsupported Cout=%d", Cout); return SMB_EINVAL; }
+  // N tile: the largest of {Cout (<=256, rounded to 16) | 256, 128, 64} that still yields >= ~one wave of tiles.
+  // Small feature maps (few M tiles) are latency-bound per tile, so they are split along N to occupy more SMs.
+  int cand[3], nc = 0;
+  if (Cout <= 256) cand[nc++] = (Cout + 15) / 16 * 16;
+  else if (Cout % 256 == 0) cand[nc++] = 256;
+  if (Cout > 128 && Cout % 128 == 0) cand[nc++] = 128;
+  if (Cout > 64 && Cout % 64 == 0) cand[nc++] = 64;
+  if (nc == 0) { set_error("conv plan: unsupported Cout=%d", Cout); return SMB_EINVAL; }
+  int n_tile = cand[nc - 1];
+  for (int i = 0; i < nc; ++i)
+    if ((long)p.tiles_m * cdiv(Cout, cand[i]) >= 120) { n_tile = cand[i]; break; }
   p.n_tile = n_tile;
   p.n_tiles_n = cdiv(Cout, n_tile);
   p.num_acc = (2 * n_tile <= 512) ? 2 : 1;
@@ -511,11 +587,19 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   // weights: [Cout, Ktotal] K-major
   uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
   uint64_t strides[1] = {(uint64_t)Ktotal * 2};
-  uint32_t box[2] = {64, (uint32_t)n_tile};
+  // cluster size: share the weight tile between CTAs when there is at least one full wave of M-tiles
+  int cluster = 1;
+  const char* env = getenv("SMB_CONV_CLUSTER");
+  const int want = env ? atoi(env) : 2;
+  if ((want == 2 || want == 4) && p.tiles_m >= num_sms() && (n_tile / want) % 8 == 0) cluster = want;
+  p.cluster = cluster;
+  uint32_t box[2] = {64, (uint32_t)(n_tile / cluster)};
   int rc = encode_map(&p.bmap, const_cast<void*>(weight), 2, dims, strides, box);
   if (rc) return rc;
-  const int tiles = p.tiles_m * p.n_tiles_n;
-  pl->grid = tiles < num_sms() ? tiles : num_sms();
+  const int units = cdiv(p.tiles_m, cluster) * p.n_tiles_n;
+  const int max_clusters = (cluster == 4 ? 132 : num_sms()) / cluster;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  pl->grid = clusters * cluster;
   return SMB_OK;
 }
 
@@ -692,7 +776,20 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
     SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  conv_gemm_kernel<<<plan->grid, kThreads, plan->smem_bytes, (cudaStream_t)stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = plan->smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SMB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel, p));
   SMB_LAUNCH_OK("conv_gemm_kernel");
   return SMB_OK;
 }

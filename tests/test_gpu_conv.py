@@ -50,6 +50,9 @@ def _check(out, ref, tol=2e-3):
     (25, 42, 512, 128, 1, 1),
     (20, 20, 768, 512, 1, 1),       # sip_mask_lat0
     (9, 5, 2304, 256, 1, 1),        # DCN GEMM (K = 9*256)
+    (104, 208, 256, 256, 3, 1),     # 169 M-tiles (odd): 2-CTA clusters multicast the weight tile, last cluster has a dummy CTA
+    (200, 336, 64, 256, 1, 1),      # layer1 conv3 shape: 525 M-tiles, one k-block, cluster path
+    (120, 160, 128, 512, 3, 1),     # 2 N-tiles x 150 M-tiles
 ])
 def test_conv_matches_reference(H, W, cin, cout, k, stride):
     from sipmask_b200 import conv
