@@ -55,6 +55,7 @@ struct ConvParams {
   int n_img, tiles_m;
   int Cout, n_tile, n_tiles_n, stages, tmem_cols, num_acc;
   int cluster;                    // CTAs per cluster sharing (multicasting) the weight tile: 1, 2 or 4
+  int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
   int out_pitch; int out_f32;
   const float* bias; float alpha;
   int res_pitch; int res_mode;
@@ -113,6 +114,52 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                    smem_u32(bar)),
                "h"(mask)
                : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cta_group::2 TMA loads: data lands in the issuing CTA's shared memory, completion is signalled on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -228,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   // the 128-byte swizzle atoms (8 rows x 128 B) must start on 1024-byte boundaries
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b_bytes = p.n_tile * 128;
+  const int b_bytes = (p.pair ? p.n_tile / 2 : p.n_tile) * 128;      // per-CTA bytes of one B stage
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_bytes);
@@ -241,11 +288,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
     tma_prefetch_desc(&p.bmap);
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    if (p.pair) {
+      // full: leader's expect_tx arrive + peer's remote arrive; empty / tfull: one multicast tcgen05.commit;
+      // tempty (used in the leader): 8 local + 8 remote epilogue warps
+      for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+    } else {
+      for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 1) {
+    if (p.pair) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all();             // peers must see initialised barriers before any remote arrive
   else __syncthreads();
@@ -274,9 +331,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);      // every CTA of the cluster has finished reading stage s
+            const int kcoord = (t * p.kb_per_tap + kc) * 64;
+            if (p.pair) {
+              // each CTA loads its own 128 x 64 activation tile and its half of the weight tile; all bytes are
+              // accounted on the leader's barrier (the single MMA issuer waits there)
+              const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+              if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
+              else mbar_arrive_cluster(lbar);
+              tma_load_4d_2sm(sA + (size_t)s * kABytes, am, lbar, kc * 64, ax, ay, tc.img);
+              tma_load_2d_2sm(sB + (size_t)s * b_bytes, &p.bmap, lbar, kcoord, tc.n0 + crank * (p.n_tile / 2));
+              continue;
+            }
             mbar_expect_tx(&full_bar[s], stage_bytes);
             tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, tc.img);
-            const int kcoord = (t * p.kb_per_tap + kc) * 64;
             if (p.cluster == 1) {
               tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], kcoord, tc.n0);
             } else {
@@ -289,9 +356,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      const uint32_t idesc = make_idesc(128, p.n_tile);
+    if (lane == 0 && (!p.pair || crank == 0)) {
+      // ===================== MMA issuer (pair mode: the leader CTA issues for both SMs) =====================
+      const uint32_t idesc = make_idesc(p.pair ? 256 : 128, p.n_tile);
       uint32_t it = 0, lt = 0;
       for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
         const int acc = lt % p.num_acc;
@@ -309,12 +376,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in the >>4 start field
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            if (p.pair) umma2_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
-          if (p.cluster == 1) umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
-          else umma_commit_mc(&empty_bar[s], cmask);         // ... in every CTA of the cluster (peers write into it)
+          if (p.pair) umma_commit2_mc(&empty_bar[s], 3);       // frees stage s in both CTAs of the pair
+          else if (p.cluster == 1) umma_commit(&empty_bar[s]); // frees the smem stage when these MMAs retire
+          else umma_commit_mc(&empty_bar[s], cmask);          // ... in every CTA of the cluster (peers write into it)
         }
-        umma_commit(&tfull_bar[acc]);              // accumulator complete
+        if (p.pair) umma_commit2_mc(&tfull_bar[acc], 3);        // accumulator halves complete in both CTAs
+        else umma_commit(&tfull_bar[acc]);                     // accumulator complete
       }
     }
   } else {
@@ -477,7 +547,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       // this warp has drained its share of the accumulator
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (p.pair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
   }
 
@@ -486,7 +559,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (p.pair) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -577,7 +651,13 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   int tc = 32;
   while (tc < p.num_acc * n_tile) tc <<= 1;
   p.tmem_cols = tc;
-  const size_t stage = (size_t)kABytes + (size_t)n_tile * 128;
+  // pair mode (tcgen05 cta_group::2): two SMs compute one 256-row x n_tile tile and each ingests only half of the
+  // weight tile - the L2 -> SM ingress (the bound for these K-major 128-row tiles) drops from 16K+n*128 to 16K+n*64
+  // bytes per k-block per SM.
+  const char* envp = getenv("SMB_CONV_PAIR");
+  const int want_pair = envp ? atoi(envp) : 1;
+  p.pair = (want_pair && p.tiles_m >= 2 && n_tile % 32 == 0 && n_tile >= 32) ? 1 : 0;
+  const size_t stage = (size_t)kABytes + (size_t)(p.pair ? n_tile / 2 : n_tile) * 128;
   const size_t budget = 196 * 1024;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;
@@ -587,11 +667,15 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   // weights: [Cout, Ktotal] K-major
   uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
   uint64_t strides[1] = {(uint64_t)Ktotal * 2};
-  // cluster size: share the weight tile between CTAs when there is at least one full wave of M-tiles
+  // cluster size: pair mode is a 2-CTA cluster; otherwise optionally multicast the weight tile (SMB_CONV_CLUSTER)
   int cluster = 1;
-  const char* env = getenv("SMB_CONV_CLUSTER");
-  const int want = env ? atoi(env) : 2;
-  if ((want == 2 || want == 4) && p.tiles_m >= num_sms() && (n_tile / want) % 8 == 0) cluster = want;
+  if (p.pair) {
+    cluster = 2;
+  } else {
+    const char* env = getenv("SMB_CONV_CLUSTER");
+    const int want = env ? atoi(env) : 1;
+    if ((want == 2 || want == 4) && p.tiles_m >= num_sms() && (n_tile / want) % 8 == 0) cluster = want;
+  }
   p.cluster = cluster;
   uint32_t box[2] = {64, (uint32_t)(n_tile / cluster)};
   int rc = encode_map(&p.bmap, const_cast<void*>(weight), 2, dims, strides, box);
