@@ -55,6 +55,8 @@ struct ConvParams {
   int n_img, tiles_m;
   int Cout, n_tile, n_tiles_n, stages, tmem_cols, num_acc;
   int cluster;                    // CTAs per cluster sharing (multicasting) the weight tile: 1, 2 or 4
+  long long* dbg_ts;              // profiling only: clock64 stamps of CTA 0 (SMB_CONV_TS buffer), else null
+  int debug_mode;                 // profiling only (SMB_CONV_DEBUG): 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA only)
   int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
   int out_pitch; int out_f32;
   const float* bias; float alpha;
@@ -66,6 +68,20 @@ struct ConvParams {
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a fully converged warp.  Keeping the surrounding control flow warp-uniform (instead of an
+// `if (lane == 0)` region) lets the compiler keep TMA / UMMA operands in uniform registers; a divergent region makes
+// it wrap every UTMALDG / UTCHMMA in a per-lane "waterfall" loop (~200 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -270,12 +286,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int unit, 
   return t;
 }
 
+// kPair = true: tcgen05 cta_group::2 instantiation (must be launched with 2-CTA clusters); false: single-CTA MMA.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // the 128-byte swizzle atoms (8 rows x 128 B) must start on 1024-byte boundaries
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b_bytes = (p.pair ? p.n_tile / 2 : p.n_tile) * 128;      // per-CTA bytes of one B stage
+#define TS(slot) do { if (p.dbg_ts && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.dbg_ts[slot] = clock64(); } while (0)
+  if (threadIdx.x == 0) TS(0);
+  const int b_bytes = (kPair ? p.n_tile / 2 : p.n_tile) * 128;      // per-CTA bytes of one B stage
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_bytes);
@@ -288,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
     tma_prefetch_desc(&p.bmap);
-    if (p.pair) {
+    if (kPair) {
       // full: leader's expect_tx arrive + peer's remote arrive; empty / tfull: one multicast tcgen05.commit;
       // tempty (used in the leader): 8 local + 8 remote epilogue warps
       for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
@@ -300,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    if (p.pair) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
+    if constexpr (kPair) tmem_alloc2(tmem_slot, (uint32_t)p.tmem_cols);
     else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   }
   tc_fence_before();
@@ -308,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TS(1);
 
   const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
@@ -317,8 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t stage_bytes = (uint32_t)(kABytes + b_bytes);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    {
+      // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
       uint32_t it = 0;
       const int b_part = b_bytes / p.cluster, n_part = p.n_tile / p.cluster;
       for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
@@ -330,9 +351,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           for (int kc = 0; kc < p.kb_per_tap; ++kc, ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (it / p.stages) & 1;
+            if (p.debug_mode == 2) continue;
+            if (it == 0) TS(2);
             mbar_wait(&empty_bar[s], ph ^ 1);      // every CTA of the cluster has finished reading stage s
             const int kcoord = (t * p.kb_per_tap + kc) * 64;
-            if (p.pair) {
+            if (!elect_one()) continue;
+            if constexpr (kPair) {
               // each CTA loads its own 128 x 64 activation tile and its half of the weight tile; all bytes are
               // accounted on the leader's barrier (the single MMA issuer waits there)
               const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
@@ -356,12 +380,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && (!p.pair || crank == 0)) {
+    if (!kPair || crank == 0) {
       // ===================== MMA issuer (pair mode: the leader CTA issues for both SMs) =====================
-      const uint32_t idesc = make_idesc(p.pair ? 256 : 128, p.n_tile);
+      const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.n_tile);
       uint32_t it = 0, lt = 0;
       for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
         const int acc = lt % p.num_acc;
+        if (lt == 0) TS(3);
         const uint32_t acc_ph = (lt / p.num_acc) & 1;
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
@@ -369,22 +394,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (p.debug_mode != 2) mbar_wait(&full_bar[s], ph);
+          if (it == 0) TS(4);
+          if (it == 8) TS(5);
+          if (it == 16) TS(6);
+          if (it == 32) TS(7);
           tc_fence_after();
+          if (!elect_one()) continue;
+          if (p.debug_mode == 1) { mbar_arrive(&empty_bar[s]); continue; }
           const uint64_t adesc = make_sdesc(smem_u32(sA + (size_t)s * kABytes));
           const uint64_t bdesc = make_sdesc(smem_u32(sB + (size_t)s * b_bytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in the >>4 start field
-            if (p.pair) umma2_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            if constexpr (kPair) umma2_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
             else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
-          if (p.pair) umma_commit2_mc(&empty_bar[s], 3);       // frees stage s in both CTAs of the pair
+          if constexpr (kPair) umma_commit2_mc(&empty_bar[s], 3);       // frees stage s in both CTAs of the pair
           else if (p.cluster == 1) umma_commit(&empty_bar[s]); // frees the smem stage when these MMAs retire
           else umma_commit_mc(&empty_bar[s], cmask);          // ... in every CTA of the cluster (peers write into it)
         }
-        if (p.pair) umma_commit2_mc(&tfull_bar[acc], 3);        // accumulator halves complete in both CTAs
-        else umma_commit(&tfull_bar[acc]);                     // accumulator complete
+        if (lt == 0) TS(8);
+        if (elect_one()) {
+          if constexpr (kPair) umma_commit2_mc(&tfull_bar[acc], 3);      // accumulator halves complete in both CTAs
+          else umma_commit(&tfull_bar[acc]);                   // accumulator complete
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -436,6 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int acc = lt % p.num_acc;
       const uint32_t acc_ph = (lt / p.num_acc) & 1;
       mbar_wait(&tfull_bar[acc], acc_ph);
+      if (lt == 0 && warp == 2 && lane == 0) TS(9);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
@@ -544,22 +580,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
       }
+      if (lt == 0 && warp == 2 && lane == 0) TS(10);
       // this warp has drained its share of the accumulator
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
         else mbar_arrive(&tempty_bar[acc]);
       }
     }
   }
 
+  if (threadIdx.x == 0) TS(11);
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all();             // no CTA may exit while peers can still multicast to / arrive on it
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (p.pair) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+    if constexpr (kPair) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
     else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
@@ -657,6 +695,9 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   const char* envp = getenv("SMB_CONV_PAIR");
   const int want_pair = envp ? atoi(envp) : 1;
   p.pair = (want_pair && p.tiles_m >= 2 && n_tile % 32 == 0 && n_tile >= 32) ? 1 : 0;
+  const char* envd = getenv("SMB_CONV_DEBUG");
+  p.debug_mode = envd ? atoi(envd) : 0;
+  if (p.debug_mode) p.pair = 0;
   const size_t stage = (size_t)kABytes + (size_t)(p.pair ? n_tile / 2 : n_tile) * 128;
   const size_t budget = 196 * 1024;
   int stages = (int)(budget / stage);
@@ -855,9 +896,14 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
     }
   }
   p.alpha = alpha;
+  {
+    const char* ets = getenv("SMB_CONV_TS");      // hex device address of a 16 x int64 buffer (profiling only)
+    p.dbg_ts = ets ? (long long*)strtoull(ets, nullptr, 16) : nullptr;
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg;
@@ -873,7 +919,15 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SMB_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel, p));
+  {
+    cudaError_t e = p.pair ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p) : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, p);
+    if (e != cudaSuccess) {
+      set_error("conv_gemm_kernel launch failed: %s (grid=%d cluster=%d pair=%d smem=%zu n_tile=%d stages=%d tiles_m=%d n_tiles_n=%d)",
+                cudaGetErrorString(e), plan->grid, p.cluster, p.pair, plan->smem_bytes, p.n_tile, p.stages, p.tiles_m, p.n_tiles_n);
+      cudaGetLastError();
+      return SMB_ECUDA;
+    }
+  }
   SMB_LAUNCH_OK("conv_gemm_kernel");
   return SMB_OK;
 }
