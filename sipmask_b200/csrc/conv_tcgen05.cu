@@ -48,6 +48,7 @@ struct LevelDesc {
 struct ConvParams {
   CUtensorMap amap[kMaxMaps];
   CUtensorMap bmap;
+  CUtensorMap omap[kMaxLevels];   // per-level output maps for the TMA-store epilogue (fp16 outputs, n_tile % 64 == 0)
   LevelDesc lv[kMaxLevels];
   int num_levels;
   int tap_map[kMaxTaps], tap_dx[kMaxTaps], tap_dy[kMaxTaps];
@@ -58,7 +59,7 @@ struct ConvParams {
   long long* dbg_ts;              // profiling only: clock64 stamps of CTA 0 (SMB_CONV_TS buffer), else null
   int debug_mode;                 // profiling only (SMB_CONV_DEBUG): 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA only)
   int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
-  int out_pitch; int out_f32;
+  int out_pitch; int out_f32; int out_tma;
   const float* bias; float alpha;
   int res_pitch; int res_mode;
   int gn_group;                   // channels per GroupNorm group (8 or 16), 0 = no statistics
@@ -177,6 +178,15 @@ __device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -304,6 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [2][256] double-buffered per tile
+  // two 128 x 64 fp16 staging tiles (128-byte swizzle) for the TMA-store epilogue
+  uint8_t* s_stage = smem + (size_t)p.stages * (kABytes + b_bytes) + 4096;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -340,41 +352,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   if (warp == 0) {
     {
       // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      bool first = true;
       const int b_part = b_bytes / p.cluster, n_part = p.n_tile / p.cluster;
+      const uint32_t lbar0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;     // leader's full_bar[0] (pair mode)
+      const int nstages = p.stages, kb_per_tap = p.kb_per_tap, num_taps = p.num_taps;
       for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
         const TileCoord tc = decode_tile(p, unit, crank);
         const int map0 = p.lv[tc.lvl].map0;
-        for (int t = 0; t < p.num_taps; ++t) {
+        for (int t = 0; t < num_taps; ++t) {
           const CUtensorMap* am = &p.amap[map0 + p.tap_map[t]];
           const int ax = tc.x0 + p.tap_dx[t], ay = tc.y0 + p.tap_dy[t];
-          for (int kc = 0; kc < p.kb_per_tap; ++kc, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            if (p.debug_mode == 2) continue;
-            if (it == 0) TS(2);
-            mbar_wait(&empty_bar[s], ph ^ 1);      // every CTA of the cluster has finished reading stage s
-            const int kcoord = (t * p.kb_per_tap + kc) * 64;
-            if (!elect_one()) continue;
-            if constexpr (kPair) {
-              // each CTA loads its own 128 x 64 activation tile and its half of the weight tile; all bytes are
-              // accounted on the leader's barrier (the single MMA issuer waits there)
-              const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
-              if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
-              else mbar_arrive_cluster(lbar);
-              tma_load_4d_2sm(sA + (size_t)s * kABytes, am, lbar, kc * 64, ax, ay, tc.img);
-              tma_load_2d_2sm(sB + (size_t)s * b_bytes, &p.bmap, lbar, kcoord, tc.n0 + crank * (p.n_tile / 2));
-              continue;
+          int kcoord = t * kb_per_tap * 64;
+          for (int kc = 0; kc < kb_per_tap; ++kc, kcoord += 64) {
+            if ((p.debug_mode & 3) != 2) {
+              if (first) { TS(2); first = false; }
+              mbar_wait(&empty_bar[s], ph ^ 1);    // every CTA of the cluster has finished reading stage s
+              if (elect_one()) {
+                if constexpr (kPair) {
+                  // each CTA loads its own 128 x 64 activation tile and its half of the weight tile; all bytes are
+                  // accounted on the leader's barrier (the single MMA issuer waits there)
+                  const uint32_t lbar = lbar0 + (uint32_t)s * 8u;
+                  if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * stage_bytes);
+                  else mbar_arrive_cluster(lbar);
+                  tma_load_4d_2sm(sA + (size_t)s * kABytes, am, lbar, kc * 64, ax, ay, tc.img);
+                  tma_load_2d_2sm(sB + (size_t)s * b_bytes, &p.bmap, lbar, kcoord, tc.n0 + crank * (p.n_tile / 2));
+                } else {
+                  mbar_expect_tx(&full_bar[s], stage_bytes);
+                  tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, tc.img);
+                  if (p.cluster == 1) {
+                    tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], kcoord, tc.n0);
+                  } else {
+                    // this CTA fetches 1/cluster of the weight tile and multicasts it into every CTA of the cluster
+                    tma_load_2d_mc(sB + (size_t)s * b_bytes + (size_t)crank * b_part, &p.bmap, &full_bar[s], kcoord,
+                                   tc.n0 + crank * n_part, cmask);
+                  }
+                }
+              }
+              __syncwarp();
             }
-            mbar_expect_tx(&full_bar[s], stage_bytes);
-            tma_load_4d(sA + (size_t)s * kABytes, am, &full_bar[s], kc * 64, ax, ay, tc.img);
-            if (p.cluster == 1) {
-              tma_load_2d(sB + (size_t)s * b_bytes, &p.bmap, &full_bar[s], kcoord, tc.n0);
-            } else {
-              // this CTA fetches 1/cluster of the weight tile and multicasts it into every CTA of the cluster
-              tma_load_2d_mc(sB + (size_t)s * b_bytes + (size_t)crank * b_part, &p.bmap, &full_bar[s], kcoord,
-                             tc.n0 + crank * n_part, cmask);
-            }
+            if (++s == nstages) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -383,36 +401,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (!kPair || crank == 0) {
       // ===================== MMA issuer (pair mode: the leader CTA issues for both SMs) =====================
       const uint32_t idesc = make_idesc(kPair ? 256 : 128, p.n_tile);
-      uint32_t it = 0, lt = 0;
+      int s = 0;
+      uint32_t ph = 0, lt = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      const int nstages = p.stages, num_acc = p.num_acc;
+      const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
       for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
-        const int acc = lt % p.num_acc;
         if (lt == 0) TS(3);
-        const uint32_t acc_ph = (lt / p.num_acc) & 1;
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          if (p.debug_mode != 2) mbar_wait(&full_bar[s], ph);
-          if (it == 0) TS(4);
-          if (it == 8) TS(5);
-          if (it == 16) TS(6);
-          if (it == 32) TS(7);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          if ((p.debug_mode & 3) != 2) mbar_wait(&full_bar[s], ph);
+          if (lt == 0 && kb == 0) TS(4);
           tc_fence_after();
-          if (!elect_one()) continue;
-          if (p.debug_mode == 1) { mbar_arrive(&empty_bar[s]); continue; }
-          const uint64_t adesc = make_sdesc(smem_u32(sA + (size_t)s * kABytes));
-          const uint64_t bdesc = make_sdesc(smem_u32(sB + (size_t)s * b_bytes));
+          if (elect_one()) {
+            if ((p.debug_mode & 3) == 1) {
+              mbar_arrive(&empty_bar[s]);
+            } else {
+              const uint64_t adesc = make_sdesc(sA0 + (uint32_t)s * kABytes);
+              const uint64_t bdesc = make_sdesc(sB0 + (uint32_t)s * (uint32_t)b_bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in the >>4 start field
-            if constexpr (kPair) umma2_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-            else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in the >>4 start field
+                if constexpr (kPair) umma2_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+              }
+              if constexpr (kPair) umma_commit2_mc(&empty_bar[s], 3);       // frees stage s in both CTAs of the pair
+              else if (p.cluster == 1) umma_commit(&empty_bar[s]); // frees the smem stage when these MMAs retire
+              else umma_commit_mc(&empty_bar[s], cmask);          // ... in every CTA of the cluster (peers write into it)
+            }
           }
-          if constexpr (kPair) umma_commit2_mc(&empty_bar[s], 3);       // frees stage s in both CTAs of the pair
-          else if (p.cluster == 1) umma_commit(&empty_bar[s]); // frees the smem stage when these MMAs retire
-          else umma_commit_mc(&empty_bar[s], cmask);          // ... in every CTA of the cluster (peers write into it)
+          __syncwarp();
+          if (++s == nstages) { s = 0; ph ^= 1; }
         }
         if (lt == 0) TS(8);
         if (elect_one()) {
@@ -420,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           else umma_commit(&tfull_bar[acc]);                   // accumulator complete
         }
         __syncwarp();
+        if (++acc == num_acc) { acc = 0; acc_ph ^= 1; }
       }
     }
   } else {
@@ -433,7 +456,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int split = ((p.n_tile / 2 + 31) / 32) * 32;
     if (split > p.n_tile) split = p.n_tile;
     const int c_begin = col_half ? split : 0, c_end = col_half ? p.n_tile : split;
-    uint32_t lt = 0;
+    uint32_t lt = 0, stage_ctr = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
     for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
       const TileCoord tc = decode_tile(p, unit, crank);
       const LevelDesc& L = p.lv[tc.lvl];
@@ -456,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       uint4 rcur[4], rnext[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { rcur[j] = make_uint4(0u, 0u, 0u, 0u); rnext[j] = make_uint4(0u, 0u, 0u, 0u); }
-      if (res_row && c_begin < c_end) {
+      if (res_row && c_begin < c_end && !p.out_tma) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (n0 + c_begin + j * 8 + 8 <= p.Cout && c_begin + j * 8 < c_end)
@@ -468,12 +493,125 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int c = et; c < p.n_tile; c += kEpiThreads) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int acc = lt % p.num_acc;
-      const uint32_t acc_ph = (lt / p.num_acc) & 1;
       mbar_wait(&tfull_bar[acc], acc_ph);
       if (lt == 0 && warp == 2 && lane == 0) TS(9);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      if (p.out_tma) {
+        // ---------- staged epilogue: TMEM -> registers -> swizzled smem tile (128 px x 64 ch) -> TMA store ----------
+        // All 8 warps work on the same 64-channel chunk (warp pair = two 32-channel halves of a lane quadrant); the
+        // scattered per-thread 16-byte global stores of the direct path become one coalesced, bounds-clipped TMA store.
+        const int nch = p.n_tile >> 6;
+        float gv[32];                                  // GroupNorm partials: [chunk][group of 8 ch][sum, sumsq]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) gv[j] = 0.f;
+        uint4 rc[4], rn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { rc[j] = make_uint4(0u, 0u, 0u, 0u); rn[j] = make_uint4(0u, 0u, 0u, 0u); }
+        if (res_row) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + col_half * 32 + j * 8));
+        }
+#pragma unroll
+        for (int c64 = 0; c64 < 4; ++c64) {
+          if (c64 < nch) {
+            const int cc = c64 * 64 + col_half * 32;     // first of this thread's 32 columns inside the tile
+            if (res_row && c64 + 1 < nch) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
+            }
+            uint32_t v[32];
+            tmem_ld32(t_base + (uint32_t)cc, v);
+            // the staging buffer written two chunks ago must have been read by its TMA store
+            uint8_t* sbuf = s_stage + (size_t)(stage_ctr & 1) * 16384;
+            if (et == 0 && stage_ctr >= 2) bulk_wait_read<1>();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(sb + cc);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = b4[j];
+                f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+              }
+            }
+            if (p.alpha != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+            }
+            if (res_row) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __half2* hh = reinterpret_cast<const __half2*>(&rc[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 a = __half22float2(hh[e]);
+                  f[j * 8 + 2 * e] += a.x; f[j * 8 + 2 * e + 1] += a.y;
+                }
+              }
+            }
+            if (p.gn_group && valid && !(p.debug_mode & 4)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float sg = 0.f, qg = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { sg += f[g * 8 + e]; qg += f[g * 8 + e] * f[g * 8 + e]; }
+                gv[c64 * 8 + g * 2] = sg;
+                gv[c64 * 8 + g * 2 + 1] = qg;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
+              const int chunk = (col_half * 4 + j) ^ (row & 7);
+              *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = o;
+            }
+            fence_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0 && tc.active && !(p.debug_mode & 8)) {
+              tma_store_4d(&p.omap[tc.lvl], sbuf, n0 + c64 * 64, tc.x0, tc.y0, tc.img);
+              bulk_commit();
+            } else if (et == 0) {
+              bulk_commit();                           // keep the group count in step with stage_ctr
+            }
+            ++stage_ctr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rc[j] = rn[j];
+          }
+        }
+        if (p.gn_group && !(p.debug_mode & 4)) {
+          // 32 lanes x 32 partials -> lane j holds the warp total of partial j (recursive halving: 31 shuffles),
+          // then ONE 64-bit fixed-point atomic per lane (associative: bit-reproducible statistics).
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = up ? gv[i] : gv[i + off];
+              const float keep = up ? gv[i + off] : gv[i];
+              gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          const int c64 = lane >> 3, g = (lane >> 1) & 3, kind = lane & 1;
+          if (c64 < nch && tc.active) {
+            const int grp = ((n0 + c64 * 64 + col_half * 32) >> 3) + g;
+            const int ngroups = p.Cout / p.gn_group;
+            unsigned long long* st = reinterpret_cast<unsigned long long*>(L.gn_stats) + ((size_t)tc.img * ngroups + grp) * 2 + kind;
+            atomicAdd(st, (unsigned long long)__float2ll_rn(gv[0] * (kind ? kGnSqScale : kGnSumScale)));
+          }
+        }
+      } else
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         if (res_row && c0 + 32 < c_end) {
 #pragma unroll
@@ -519,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
             }
           }
-          if (p.gn_group) {
+          if (p.gn_group && !(p.debug_mode & 4)) {
             // per-(image, group) sum / sum of squares of the conv output (pre-activation), fp32 in-warp, then
             // 64-bit fixed-point integer atomics (associative -> bit-reproducible run to run).
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
@@ -557,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (valid) {
+          if (valid && !(p.debug_mode & 8)) {
             if (p.out_f32) {
               float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(L.out) + pix * p.out_pitch + ch0);
 #pragma unroll
@@ -588,9 +726,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
         else mbar_arrive(&tempty_bar[acc]);
       }
+      if (++acc == p.num_acc) { acc = 0; acc_ph ^= 1; }
     }
   }
 
+  if (threadIdx.x == 64 && p.out_tma) bulk_wait_read<0>();      // staging tiles must outlive their TMA stores
   if (threadIdx.x == 0) TS(11);
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all();             // no CTA may exit while peers can still multicast to / arrive on it
@@ -647,6 +787,7 @@ struct smb_conv_plan {
   int grid;
   size_t smem_bytes;
   int has_bias, has_residual, gn_stats;
+  int omap_ok;                    // output tensor maps encoded (fp16 output, Cout % 64 == 0)
 };
 
 static int g_num_sms = 0;
@@ -697,14 +838,15 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   p.pair = (want_pair && p.tiles_m >= 2 && n_tile % 32 == 0 && n_tile >= 32) ? 1 : 0;
   const char* envd = getenv("SMB_CONV_DEBUG");
   p.debug_mode = envd ? atoi(envd) : 0;
-  if (p.debug_mode) p.pair = 0;
+  if (p.debug_mode & 3) p.pair = 0;
   const size_t stage = (size_t)kABytes + (size_t)(p.pair ? n_tile / 2 : n_tile) * 128;
-  const size_t budget = 196 * 1024;
+  p.out_tma = (pl->omap_ok && !p.out_f32 && n_tile % 64 == 0 && !getenv("SMB_CONV_NO_TMA_STORE")) ? 1 : 0;
+  const size_t budget = (p.out_tma ? 160 : 194) * 1024;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv plan: tile too large for shared memory"); return SMB_EINVAL; }
   p.stages = stages;
-  pl->smem_bytes = stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16 + 2 * 256 * sizeof(float) + 1024;
+  pl->smem_bytes = stages * stage + 4096 + (p.out_tma ? 2 * 16384 : 0) + 1024;    // + barriers/bias (4 KB) + staging + align
   // weights: [Cout, Ktotal] K-major
   uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
   uint64_t strides[1] = {(uint64_t)Ktotal * 2};
@@ -744,6 +886,7 @@ extern "C" int smb_conv_plan_create_multi(const smb_conv_desc_t* d, int num_leve
   SMB_CHECK_ARG(((uintptr_t)weight % 16) == 0, "smb_conv_plan_create: weight must be 16-byte aligned");
   smb_conv_plan* pl = new smb_conv_plan();
   memset(&pl->p, 0, sizeof(ConvParams));
+  pl->omap_ok = 0;
   ConvParams& p = pl->p;
   const int k = d->kh, s = d->stride;
   p.n_img = d->N;
@@ -783,6 +926,14 @@ extern "C" int smb_conv_plan_create_multi(const smb_conv_desc_t* d, int num_leve
     L.out = lv.out; L.residual = (const __half*)lv.residual; L.gn_stats = (long long*)lv.gn_stats;
     L.res_h = lv.res_h; L.res_w = lv.res_w;
     const uint32_t box[4] = {64, (uint32_t)L.BW, (uint32_t)L.BH, 1};
+    if (rc == SMB_OK && d->out_dtype == SMB_F16 && d->Cout % 64 == 0 && out_pitch % 8 == 0) {
+      uint64_t odims[4] = {(uint64_t)d->Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->N};
+      const uint64_t opx = (uint64_t)out_pitch * 2;
+      uint64_t ostr[3] = {opx, opx * Wo, opx * Wo * Ho};
+      rc = encode_map(&p.omap[l], lv.out, 4, odims, ostr, box);
+      pl->omap_ok = (rc == SMB_OK);
+      if (rc != SMB_OK) break;
+    }
     if (s == 1) {
       L.map0 = l;
       uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)d->N};
@@ -845,6 +996,7 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
   SMB_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "smb_stem_plan_create: H, W must be even (images are padded to /32)");
   smb_conv_plan* pl = new smb_conv_plan();
   memset(&pl->p, 0, sizeof(ConvParams));
+  pl->omap_ok = 0;
   ConvParams& p = pl->p;
   LevelDesc& L = p.lv[0];
   const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
@@ -869,6 +1021,12 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
     rc = encode_map(&p.amap[par], (char*)const_cast<void*>(img_nhwc8) + par * rowb, 4, dims, strides, box);
   }
   for (int i = 2; i < kMaxMaps; ++i) p.amap[i] = p.amap[i & 1];
+  if (rc == SMB_OK) {
+    uint64_t odims[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+    uint64_t ostr[3] = {128, (uint64_t)128 * Wo, (uint64_t)128 * Wo * Ho};
+    rc = encode_map(&p.omap[0], out, 4, odims, ostr, box);
+    pl->omap_ok = (rc == SMB_OK);
+  }
   for (int r = 0; r < 7; ++r) { p.tap_map[r] = r & 1; p.tap_dy[r] = r >> 1; p.tap_dx[r] = 0; }
   if (rc == SMB_OK) rc = finish_plan(pl, 64, 448, weight448);
   if (rc != SMB_OK) { delete pl; return rc; }

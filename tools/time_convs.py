@@ -17,16 +17,23 @@ flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 tot_w = tot_c = 0.0
 print('%-44s %8s %5s %6s %3s %8s %8s %8s' % ('conv', 'M', 'N', 'K', 'k', 'warm_us', 'cold_us', 'TF/s(w)'))
+REPS = 20
 for plan, m in zip(eng.conv_plans, eng.conv_meta):
     for _ in range(3):
         plan.run()
     torch.cuda.synchronize()
+    # warm: REPS back-to-back launches replayed from a CUDA graph (no Python / driver launch cost in the number)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(REPS):
+            plan.run()
+    g.replay()
+    torch.cuda.synchronize()
     e0.record()
-    for _ in range(10):
-        plan.run()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
-    warm = e0.elapsed_time(e1) / 10 * 1e3
+    warm = e0.elapsed_time(e1) / REPS * 1e3
     cold = []
     for i in range(3):
         flush.fill_(i)
@@ -40,4 +47,4 @@ for plan, m in zip(eng.conv_plans, eng.conv_meta):
     tot_c += cold
     print('%-44s %8d %5d %6d %3d %8.1f %8.1f %8.1f %s%s' % (m['name'][-44:], m['M'], m['N'], m['K'], m['k'], warm, cold,
                                                          m['flops'] / warm / 1e6, 'R' if m['res'] else '', 'G' if m['gn'] else ''))
-print('sum warm %.1f us, sum cold %.1f us, %.1f GFLOP' % (tot_w, tot_c, eng.conv_flops / 1e9))
+print('sum warm(graph) %.1f us, sum cold %.1f us, %.1f GFLOP' % (tot_w, tot_c, eng.conv_flops / 1e9))
