@@ -163,6 +163,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from sipmask_b200 import dist as sdist
     from sipmask_b200 import ops, synth
     from sipmask_b200.engine import SipMaskEngine
 
@@ -187,9 +188,7 @@ def run_ours(args):
         out = eng.forward(None)
         if world > 1:
             # the single collective of the path: fixed-shape detection record
-            mine = torch.cat([out['det_bboxes'][0], out['det_labels'][0].float().unsqueeze(1),
-                              out['count'].float().expand(eng.max_num).unsqueeze(1)], 1)
-            dist.all_gather_into_tensor(rec, mine)
+            sdist.gather_records(sdist.pack_record(out['det_bboxes'][0], out['det_labels'][0], out['count']), out=rec)
         return out
 
     host_det = torch.empty((eng.max_num, 5), dtype=torch.float32).pin_memory()

@@ -24,12 +24,15 @@ ARCH = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
 class SipMaskEngine(object):
     def __init__(self, state_dict, img_hw, batch=1, depth=50, stacked_convs=4, gn=True, ssd_flag=False, num_classes=81,
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
-                 mask_thr=0.4, use_graph=True, pos_dtype=torch.float32):
+                 mask_thr=0.4, use_graph=True, pos_dtype=torch.float32, head_only=False, feat_sizes=None, in_channels=256,
+                 fcos=False, prefix_head='bbox_head.', build_postproc=True):
         L.check(L.lib().smb_check_device(), 'smb_check_device')
         self.dev = torch.device(device)
         self.N, (self.H, self.W) = batch, img_hw
+        self.head_only, self.feat_sizes, self.in_channels, self.fcos = head_only, feat_sizes, in_channels, fcos
+        self.hp, self.build_post = prefix_head, build_postproc
         assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
-        assert self.H % 32 == 0 and self.W % 32 == 0, 'images are padded to a multiple of 32 (Pad size_divisor=32)'
+        assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
         self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
         self.ncls = num_classes - 1
         self.strides = tuple(strides)
@@ -101,6 +104,14 @@ class SipMaskEngine(object):
     # -------------------------------------------------------------------------------------------- build
     def _build(self):
         N, H, W = self.N, self.H, self.W
+        if self.head_only:
+            # drop-in head: the five FPN levels come from the caller (reference backbone/neck), NHWC fp16 copies
+            self.fpn_outs = [self._t(N, h, w, self.in_channels) for (h, w) in self.feat_sizes]
+            if self.fcos:
+                self._build_fcos_head(self.fpn_outs)
+            else:
+                self._build_head(self.fpn_outs)
+            return
         self.img = self._t(N, 3, H, W, dtype=torch.float32)
         # ---- stem
         img8 = self._t(N, H + 6, W + 8, 8)
@@ -188,7 +199,7 @@ class SipMaskEngine(object):
 
     def _build_head(self, feats):
         N = self.N
-        hp = 'bbox_head.'
+        hp = self.hp
         sizes = [(f.shape[1], f.shape[2]) for f in feats]
         self.level_sizes = sizes
         tot = sum(h * w for h, w in sizes)
@@ -258,7 +269,52 @@ class SipMaskEngine(object):
         m1 = self._conv(m0, hp + 'sip_mask_lat.weight', 3, relu=True, bias_key=hp + 'sip_mask_lat.bias')
         self.protos = self._t(N, 4 * h3, 4 * w3, 32)
         self._add(lambda: C.upsample_bilinear(m1, 4, out=self.protos))
-        self._build_postproc()
+        if self.build_post:
+            self._build_postproc()
+
+    def _build_fcos_head(self, feats):
+        """Plain FCOS head (MM/mmdet/models/anchor_heads/fcos_head.py:118-135): 4+4 tower ConvModules, fcos_cls and
+        fcos_centerness on the cls tower, fcos_reg on the reg tower (exp(scale * x) is applied by the caller)."""
+        N, hp = self.N, self.hp
+        sizes = [(f.shape[1], f.shape[2]) for f in feats]
+        self.level_sizes = sizes
+        nl = len(feats)
+        tot = sum(h * w for h, w in sizes)
+        self.gn_arena = self._t(2 * self.stacked, nl, N, 32, 2, dtype=torch.int64, zero=True)
+        self._add(lambda: self.gn_arena.zero_(), 0)
+        ncls = self.ncls
+        CCp = (ncls + 1 + 15) // 16 * 16
+        w_cls = torch.cat([self._w(hp + 'fcos_cls.weight'), self._w(hp + 'fcos_centerness.weight')], 0)
+        b_cls = torch.cat([self._w(hp + 'fcos_cls.bias'), self._w(hp + 'fcos_centerness.bias')], 0)
+        wk_cls, _ = C.pack_weight(w_cls, cout_pad=CCp, device=self.dev)
+        b_cls = torch.cat([b_cls, b_cls.new_zeros(CCp - ncls - 1)]).to(self.dev)
+        wk_reg, _ = C.pack_weight(self._w(hp + 'fcos_reg.weight'), cout_pad=16, device=self.dev)
+        b_reg = torch.cat([self._w(hp + 'fcos_reg.bias'), torch.zeros(12)]).to(self.dev)
+        self._keep += [wk_cls, b_cls, wk_reg, b_reg]
+        self.scales = [float(self._w(hp + 'scales.%d.scale' % i)) for i in range(nl)]
+        self.clscof = self._t(N, tot, CCp, dtype=torch.float32)       # [cls(80) | centerness(1) | pad]
+        self.regctr = self._t(N, tot, 16, dtype=torch.float32)        # [reg(4) | pad]
+        offs0 = [sum(h * w for h, w in sizes[:l]) for l in range(nl)]
+        cls_l = [self.clscof[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], CCp) for l in range(nl)]
+        reg_l = [self.regctr[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], 16) for l in range(nl)]
+        self.level_views = list(zip(cls_l, reg_l))
+        si = 0
+        cls_feats, reg_feats = list(feats), list(feats)
+        for i in range(self.stacked):
+            cls_feats = self._tower_conv(cls_feats, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
+                                         hp + 'cls_convs.%d.conv.bias' % i, [self.gn_arena[si, l] for l in range(nl)])
+            si += 1
+        for i in range(self.stacked):
+            reg_feats = self._tower_conv(reg_feats, hp + 'reg_convs.%d.conv.weight' % i, hp + 'reg_convs.%d.gn' % i,
+                                         hp + 'reg_convs.%d.conv.bias' % i, [self.gn_arena[si, l] for l in range(nl)])
+            si += 1
+        self._conv_multi(cls_feats, wk_cls, 3, outs=cls_l, bias=b_cls, cout_real=ncls + 1)
+        self._conv_multi(reg_feats, wk_reg, 3, outs=reg_l, bias=b_reg, cout_real=4)
+
+    def load_features(self, feats):
+        """feats: five NCHW tensors (fp16/fp32, CUDA) from the caller's neck -> the engine's NHWC fp16 buffers."""
+        for buf, f in zip(self.fpn_outs, feats):
+            buf.copy_(f.permute(0, 2, 3, 1))
 
     # ------------------------------------------------------------------------------- post-processing
     def _build_postproc(self):

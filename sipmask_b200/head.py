@@ -1,0 +1,220 @@
+"""Drop-in heads with the reference's registry / module API, computed by the sm_100a kernels.
+
+    SipMaskHead  <- MM/mmdet/models/anchor_heads/sipmask_head.py:107-287,500-662
+    FCOSHead     <- MM/mmdet/models/anchor_heads/fcos_head.py:15-135,190-291
+
+Same constructor keywords, same parameter names (a reference checkpoint `load_state_dict`s unchanged:
+`cls_convs.{i}.conv.weight`, `cls_convs.{i}.gn.{weight,bias}`, `fcos_cls`, `scales.{i}.scale`,
+`feat_align.conv_offset/conv_adaption/norm`, `sip_cof`, `sip_mask_lat`, `sip_mask_lat0`), same
+`forward(feats)` / `get_bboxes(*outs, img_metas, cfg, rescale)` signatures and return structure as used by
+`SingleStageDetector.simple_test` (MM/mmdet/models/detectors/single_stage.py:75-93).
+
+The nn.Conv2d / nn.GroupNorm members only hold parameters; nothing here calls their forward.  Inference only:
+`loss()` raises (training stays with the reference implementation).  CUDA sm_100 required - no CPU path.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import postproc, rle
+from .engine import SipMaskEngine
+
+INF = 1e8
+
+
+class _ConvModule(nn.Module):
+    """Parameter container with the reference ConvModule's attribute names (`conv`, `gn`; ops/conv_module.py:68-100)."""
+
+    def __init__(self, cin, cout, k=3, stride=1, padding=1, gn=True):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=not gn)
+        if gn:
+            self.gn = nn.GroupNorm(32, cout)
+
+
+class _Scale(nn.Module):
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.tensor(scale, dtype=torch.float))
+
+
+class _DeformConvParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(cout, cin, 3, 3))
+
+
+class _FeatureAlign(nn.Module):
+    def __init__(self, c, dg=4):
+        super().__init__()
+        self.conv_offset = nn.Conv2d(4, dg * 18, 1, bias=False)
+        self.conv_adaption = _DeformConvParams(c, c)
+        self.norm = nn.GroupNorm(32, c)
+
+
+class _HeadBase(nn.Module):
+    fcos = False
+
+    def _engine(self, feats):
+        sizes = tuple((f.shape[2], f.shape[3]) for f in feats)
+        key = (sizes, feats[0].device, self._param_version())
+        if getattr(self, '_eng_key', None) != key:
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            self._eng = SipMaskEngine(sd, (0, 0), batch=feats[0].shape[0], stacked_convs=self.stacked_convs,
+                                      gn=self.norm_cfg is not None, ssd_flag=getattr(self, 'ssd_flag', False),
+                                      num_classes=self.num_classes, strides=self.strides, device=feats[0].device,
+                                      use_graph=False, head_only=True, feat_sizes=sizes, in_channels=self.in_channels,
+                                      fcos=self.fcos, prefix_head='', build_postproc=False)
+            self._eng_key = key
+        return self._eng
+
+    def _param_version(self):
+        return tuple(p._version for p in self.parameters())
+
+    def loss(self, *args, **kwargs):
+        raise NotImplementedError('sipmask_b200 heads are inference-only; train with the reference head '
+                                  '(same parameter names, so checkpoints move both ways)')
+
+
+class SipMaskHead(_HeadBase):
+    def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
+                 regress_ranges=((-1, 64), (64, 128), (128, 256), (256, 512), (512, INF)), center_sampling=False,
+                 center_sample_radius=1.5, ssd_flag=False, rescoring_flag=False, loss_cls=None, loss_bbox=None,
+                 loss_centerness=None, conv_cfg=None, norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
+        super().__init__()
+        if rescoring_flag:
+            raise NotImplementedError('rescoring_flag (SipMask++ mask rescoring) is a later row of the scope table')
+        if in_channels != 256 or feat_channels != 256:
+            raise NotImplementedError('the GroupNorm-statistics epilogue is specialised for 256 feature channels')
+        self.num_classes, self.cls_out_channels = num_classes, num_classes - 1
+        self.in_channels, self.feat_channels, self.stacked_convs = in_channels, feat_channels, stacked_convs
+        self.strides, self.regress_ranges = tuple(strides), regress_ranges
+        self.ssd_flag, self.rescoring_flag = ssd_flag, rescoring_flag
+        self.conv_cfg, self.norm_cfg = conv_cfg, norm_cfg
+        self.fp16_enabled = False
+        gn = norm_cfg is not None
+        self.cls_convs = nn.ModuleList([_ConvModule(in_channels if i == 0 else feat_channels, feat_channels, gn=gn)
+                                        for i in range(stacked_convs - 1)])
+        self.reg_convs = nn.ModuleList([_ConvModule(in_channels if i == 0 else feat_channels, feat_channels, gn=gn)
+                                        for i in range(stacked_convs)])
+        self.fcos_cls = nn.Conv2d(feat_channels, self.cls_out_channels, 3, padding=1)
+        self.fcos_reg = nn.Conv2d(feat_channels, 4, 3, padding=1)
+        self.fcos_centerness = nn.Conv2d(feat_channels, 1, 3, padding=1)
+        self.scales = nn.ModuleList([_Scale(1.0) for _ in self.strides])
+        self.nc = 32
+        self.feat_align = _FeatureAlign(feat_channels)
+        self.sip_cof = nn.Conv2d(feat_channels, self.nc * 4, 3, padding=1)
+        self.sip_mask_lat = nn.Conv2d(512, self.nc, 3, padding=1)
+        self.sip_mask_lat0 = nn.Conv2d(768, 512, 1, padding=0)
+        self.init_weights()
+
+    def init_weights(self):
+        """sipmask_head.py:226-239 (normal std 0.01, cls bias = -log(99), zero DCN offsets)."""
+        for m in list(self.cls_convs) + list(self.reg_convs):
+            nn.init.normal_(m.conv.weight, 0, 0.01)
+        for m, std in ((self.fcos_cls, 0.01), (self.fcos_reg, 0.01), (self.fcos_centerness, 0.01), (self.sip_cof, 0.001),
+                       (self.sip_mask_lat, 0.01), (self.sip_mask_lat0, 0.01)):
+            nn.init.normal_(m.weight, 0, std)
+            nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.fcos_cls.bias, float(-np.log((1 - 0.01) / 0.01)))
+        nn.init.constant_(self.feat_align.conv_offset.weight, 0.0)
+        nn.init.normal_(self.feat_align.conv_adaption.weight, 0, 0.01)
+
+    @torch.no_grad()
+    def forward(self, feats):
+        """feats: tuple of 5 NCHW CUDA tensors -> (cls_scores, bbox_preds, centernesses, cof_preds: lists of 5 NCHW
+        fp32 views; feat_masks [N,32,4*h3,4*w3] fp16 view) - sipmask_head.py:241-287."""
+        eng = self._engine(feats)
+        eng.load_features(feats)
+        eng._run_ops()
+        o = eng.head_outputs()
+        return o['cls'], o['bbox'], o['ctr'], o['cof'], o['feat_masks']
+
+    @torch.no_grad()
+    def get_bboxes(self, cls_scores, bbox_preds, centernesses, cof_preds, feat_masks, img_metas, cfg, rescale=None):
+        """-> list over images of (det_bboxes [k,5], det_labels [k], cls_segms: list[num_classes-1] of RLE dicts),
+        sipmask_head.py:500-541,645-662."""
+        results = []
+        for i in range(len(img_metas)):
+            meta = img_metas[i]
+            res = postproc.get_bboxes_single(
+                [t[i] for t in cls_scores], [t[i] for t in bbox_preds], [t[i] for t in centernesses],
+                [t[i] for t in cof_preds], feat_masks[i], self.strides, meta['img_shape'], meta['ori_shape'],
+                meta['scale_factor'], cfg, rescale=rescale, ssd_flag=self.ssd_flag)
+            k = int(res['count'])
+            det_bboxes, det_labels = res['det_bboxes'][:k], res['det_labels'][:k]
+            masks = res['masks'][:k].cpu().numpy()                 # ONE device->host copy (the reference does k)
+            labels = det_labels.cpu().numpy()
+            cls_segms = [[] for _ in range(self.num_classes - 1)]
+            for j in range(k):
+                cls_segms[int(labels[j])].append(rle.encode(masks[j]))
+            results.append((det_bboxes, det_labels, cls_segms))
+        return results
+
+
+class FCOSHead(_HeadBase):
+    fcos = True
+
+    def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
+                 regress_ranges=((-1, 64), (64, 128), (128, 256), (256, 512), (512, INF)), center_sampling=False,
+                 center_sample_radius=1.5, loss_cls=None, loss_bbox=None, loss_centerness=None, conv_cfg=None,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
+        super().__init__()
+        if in_channels != 256 or feat_channels != 256:
+            raise NotImplementedError('the GroupNorm-statistics epilogue is specialised for 256 feature channels')
+        self.num_classes, self.cls_out_channels = num_classes, num_classes - 1
+        self.in_channels, self.feat_channels, self.stacked_convs = in_channels, feat_channels, stacked_convs
+        self.strides, self.regress_ranges = tuple(strides), regress_ranges
+        self.conv_cfg, self.norm_cfg = conv_cfg, norm_cfg
+        self.fp16_enabled = False
+        gn = norm_cfg is not None
+        self.cls_convs = nn.ModuleList([_ConvModule(in_channels if i == 0 else feat_channels, feat_channels, gn=gn)
+                                        for i in range(stacked_convs)])
+        self.reg_convs = nn.ModuleList([_ConvModule(in_channels if i == 0 else feat_channels, feat_channels, gn=gn)
+                                        for i in range(stacked_convs)])
+        self.fcos_cls = nn.Conv2d(feat_channels, self.cls_out_channels, 3, padding=1)
+        self.fcos_reg = nn.Conv2d(feat_channels, 4, 3, padding=1)
+        self.fcos_centerness = nn.Conv2d(feat_channels, 1, 3, padding=1)
+        self.scales = nn.ModuleList([_Scale(1.0) for _ in self.strides])
+        self.init_weights()
+
+    def init_weights(self):
+        for m in list(self.cls_convs) + list(self.reg_convs):
+            nn.init.normal_(m.conv.weight, 0, 0.01)
+        for m in (self.fcos_cls, self.fcos_reg, self.fcos_centerness):
+            nn.init.normal_(m.weight, 0, 0.01)
+            nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.fcos_cls.bias, float(-np.log((1 - 0.01) / 0.01)))
+
+    @torch.no_grad()
+    def forward(self, feats):
+        """-> (cls_scores, bbox_preds, centernesses), lists of 5 NCHW fp32 tensors (fcos_head.py:118-135)."""
+        eng = self._engine(feats)
+        eng.load_features(feats)
+        eng._run_ops()
+        ncls = self.cls_out_channels
+        cls, box, ctr = [], [], []
+        for l, (cc, rc) in enumerate(eng.level_views):
+            cls.append(cc[..., :ncls].permute(0, 3, 1, 2))
+            ctr.append(cc[..., ncls:ncls + 1].permute(0, 3, 1, 2))
+            box.append((rc[..., :4] * eng.scales[l]).exp().permute(0, 3, 1, 2))     # scale(x).float().exp() (:134)
+        return cls, box, ctr
+
+    @torch.no_grad()
+    def get_bboxes(self, cls_scores, bbox_preds, centernesses, img_metas, cfg, rescale=None):
+        """-> list over images of (det_bboxes [k,5], det_labels [k]) - fcos_head.py:190-291."""
+        from . import ops
+        results = []
+        for i in range(len(img_metas)):
+            meta = img_metas[i]
+            cl = [t[i].float().permute(1, 2, 0).contiguous() for t in cls_scores]
+            bl = [t[i].float().permute(1, 2, 0).contiguous() for t in bbox_preds]
+            tl = [t[i].float().permute(1, 2, 0).contiguous() for t in centernesses]
+            sf = np.atleast_1d(np.asarray(meta['scale_factor'], dtype=np.float32))
+            boxes, scores, ctr, _ = ops.decode_topk(cl, bl, tl, self.strides, meta['img_shape'], cfg.get('nms_pre', -1),
+                                                    scale_factor=(sf if rescale else None))
+            iou_thr = cfg['nms']['iou_thr'] if isinstance(cfg['nms'], dict) else cfg['nms'].iou_thr
+            det, lab, _ = ops.multiclass_nms_idx(boxes, scores, cfg['score_thr'], dict(iou_thr=iou_thr),
+                                                 int(cfg.get('max_per_img', 100)), score_factors=ctr, has_bg_column=False)
+            results.append((det, lab))
+        return results
