@@ -204,12 +204,20 @@ def run_ours(args):
         host_bits.copy_(out['mask_bits'][0], non_blocking=True)
 
     def timed(fn, steps, sample_clocks=False):
+        """K steps between barrier+synchronize, CUDA events, max over ranks.  nvidia-smi samples clocks every 100 ms;
+        a short timed region would get no sample, so the same load runs untimed for ~0.4 s before and after it and the
+        sampler stays on throughout (clocks.window says so)."""
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        if sample_clocks:
+            t_end = time.perf_counter() + 0.4
+            while time.perf_counter() < t_end:
+                fn()
+                torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -218,7 +226,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        if sample_clocks:
+            t_end = time.perf_counter() + 0.4
+            while time.perf_counter() < t_end:
+                fn()
+                torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
+        if clocks is not None:
+            clocks['window'] = 'timed region plus 0.4 s of the identical load before and after it'
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -62,7 +62,7 @@ class SipMaskEngine(object):
         return t
 
     def _w(self, key):
-        return self.sd[key].detach().float()
+        return self.sd[key].detach().float().cpu()
 
     def _bn(self, prefix):
         return (self._w(prefix + '.weight'), self._w(prefix + '.bias'), self._w(prefix + '.running_mean'),
