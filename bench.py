@@ -93,6 +93,7 @@ def build_oracle(threads):
     return net
 
 
+ROLL = 200          # untimed pre/post-roll steps around the timed region while nvidia-smi samples clocks
 CLS_BIAS = -5.0
 TEST_CFG = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
 
@@ -205,16 +206,15 @@ def run_ours(args):
 
     def timed(fn, steps, sample_clocks=False):
         """K steps between barrier+synchronize, CUDA events, max over ranks.  nvidia-smi samples clocks every 100 ms;
-        a short timed region would get no sample, so the same load runs untimed for ~0.4 s before and after it and the
-        sampler stays on throughout (clocks.window says so)."""
+        a short timed region would get no sample, so ROLL untimed steps of the same load run before and after it and
+        the sampler stays on throughout (clocks.window says so)."""
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
         if sampler:
             sampler.start()
         if sample_clocks:
-            t_end = time.perf_counter() + 0.4
-            while time.perf_counter() < t_end:
+            for _ in range(ROLL):                       # fixed count: every rank must issue the same collectives
                 fn()
-                torch.cuda.synchronize()
+            torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -227,13 +227,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         if sample_clocks:
-            t_end = time.perf_counter() + 0.4
-            while time.perf_counter() < t_end:
+            for _ in range(ROLL):
                 fn()
-                torch.cuda.synchronize()
+            torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         if clocks is not None:
-            clocks['window'] = 'timed region plus 0.4 s of the identical load before and after it'
+            clocks['window'] = 'timed region plus %d untimed steps of the identical load before and after it' % ROLL
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -48,6 +48,7 @@ struct LevelDesc {
 struct ConvParams {
   CUtensorMap amap[kMaxMaps];
   CUtensorMap bmap;
+  CUtensorMap rmap[kMaxLevels];   // per-level residual maps (res_tma): residual tiles are TMA-prefetched into smem
   CUtensorMap omap[kMaxLevels];   // per-level output maps for the TMA-store epilogue (fp16 outputs, n_tile % 64 == 0)
   LevelDesc lv[kMaxLevels];
   int num_levels;
@@ -59,7 +60,7 @@ struct ConvParams {
   long long* dbg_ts;              // profiling only: clock64 stamps of CTA 0 (SMB_CONV_TS buffer), else null
   int debug_mode;                 // profiling only (SMB_CONV_DEBUG): 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA only)
   int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
-  int out_pitch; int out_f32; int out_tma;
+  int out_pitch; int out_f32; int out_tma; int res_tma;
   const float* bias; float alpha;
   int res_pitch; int res_mode;
   int gn_group;                   // channels per GroupNorm group (8 or 16), 0 = no statistics
@@ -312,10 +313,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rfull_bar = tempty_bar + 2;                               // [4] residual chunk landed (res_tma)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 4);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [2][256] double-buffered per tile
   // two 128 x 64 fp16 staging tiles (128-byte swizzle) for the TMA-store epilogue
   uint8_t* s_stage = smem + (size_t)p.stages * (kABytes + b_bytes) + 4096;
+  uint8_t* s_res = s_stage + 2 * 16384;                               // [n_tile/64] x 16 KB residual tiles (res_tma)
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -487,6 +491,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (n0 + c_begin + j * 8 + 8 <= p.Cout && c_begin + j * 8 < c_end)
             rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c_begin + j * 8));
       }
+      if (p.res_tma && et == 0 && tc.active) {
+        // this tile's residual (128 px x n_tile ch) arrives by TMA while the main loop is still running
+        fence_async_smem();
+        const int nchr = p.n_tile >> 6;
+        for (int c = 0; c < nchr; ++c) {
+          mbar_expect_tx(&rfull_bar[c], 16384);
+          tma_load_4d(s_res + (size_t)c * 16384, &p.rmap[tc.lvl], &rfull_bar[c], n0 + c * 64, tc.x0, tc.y0, tc.img);
+        }
+      }
       // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile)
       float* sb = s_bias + (lt & 1) * 256;
       if (p.bias) {
@@ -508,7 +521,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint4 rc[4], rn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { rc[j] = make_uint4(0u, 0u, 0u, 0u); rn[j] = make_uint4(0u, 0u, 0u, 0u); }
-        if (res_row) {
+        const bool res_smem = p.res_tma && tc.active;
+        if (res_row && !res_smem) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + col_half * 32 + j * 8));
         }
@@ -516,9 +530,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int c64 = 0; c64 < 4; ++c64) {
           if (c64 < nch) {
             const int cc = c64 * 64 + col_half * 32;     // first of this thread's 32 columns inside the tile
-            if (res_row && c64 + 1 < nch) {
+            if (res_row && !res_smem && c64 + 1 < nch) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
+            }
+            if (res_smem) {
+              mbar_wait(&rfull_bar[c64], lt & 1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                rc[j] = *reinterpret_cast<const uint4*>(s_res + (size_t)c64 * 16384 + row * 128 + (((col_half * 4 + j) ^ (row & 7)) * 16));
             }
             uint32_t v[32];
             tmem_ld32(t_base + (uint32_t)cc, v);
@@ -542,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
             }
-            if (res_row) {
+            if (res_row || res_smem) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const __half2* hh = reinterpret_cast<const __half2*>(&rc[j]);
@@ -788,6 +808,8 @@ struct smb_conv_plan {
   size_t smem_bytes;
   int has_bias, has_residual, gn_stats;
   int omap_ok;                    // output tensor maps encoded (fp16 output, Cout % 64 == 0)
+  int rmap_ok;                    // residual tensor maps encoded (same-shape fp16 residual)
+  const void* rmap_ptr;           // single-level plans: residual pointer rmap[0] is currently encoded for (lazy, smb_conv_run)
 };
 
 static int g_num_sms = 0;
@@ -841,12 +863,14 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   if (p.debug_mode & 3) p.pair = 0;
   const size_t stage = (size_t)kABytes + (size_t)(p.pair ? n_tile / 2 : n_tile) * 128;
   p.out_tma = (pl->omap_ok && !p.out_f32 && n_tile % 64 == 0 && !getenv("SMB_CONV_NO_TMA_STORE")) ? 1 : 0;
-  const size_t budget = (p.out_tma ? 160 : 194) * 1024;
+  p.res_tma = (p.out_tma && p.res_mode == 1 && pl->rmap_ok && !getenv("SMB_CONV_NO_TMA_RES")) ? 1 : 0;
+  const size_t res_bytes = p.res_tma ? (size_t)(n_tile / 64) * 16384 : 0;
+  const size_t budget = (p.out_tma ? 160 : 194) * 1024 - res_bytes;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv plan: tile too large for shared memory"); return SMB_EINVAL; }
   p.stages = stages;
-  pl->smem_bytes = stages * stage + 4096 + (p.out_tma ? 2 * 16384 : 0) + 1024;    // + barriers/bias (4 KB) + staging + align
+  pl->smem_bytes = stages * stage + 4096 + (p.out_tma ? 2 * 16384 : 0) + res_bytes + 1024;    // + barriers/bias (4 KB) + staging + align
   // weights: [Cout, Ktotal] K-major
   uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
   uint64_t strides[1] = {(uint64_t)Ktotal * 2};
@@ -887,6 +911,8 @@ extern "C" int smb_conv_plan_create_multi(const smb_conv_desc_t* d, int num_leve
   smb_conv_plan* pl = new smb_conv_plan();
   memset(&pl->p, 0, sizeof(ConvParams));
   pl->omap_ok = 0;
+  pl->rmap_ok = 0;
+  pl->rmap_ptr = nullptr;
   ConvParams& p = pl->p;
   const int k = d->kh, s = d->stride;
   p.n_img = d->N;
@@ -933,6 +959,14 @@ extern "C" int smb_conv_plan_create_multi(const smb_conv_desc_t* d, int num_leve
       rc = encode_map(&p.omap[l], lv.out, 4, odims, ostr, box);
       pl->omap_ok = (rc == SMB_OK);
       if (rc != SMB_OK) break;
+      if (d->has_residual && !d->residual_upsample && num_levels == 1) pl->rmap_ok = 1;   // encoded lazily in smb_conv_run
+      if (d->has_residual && !d->residual_upsample && num_levels > 1) {
+        // multi-level plans bake the residual pointer, so its map can be encoded here
+        uint64_t rstr[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->Cout * 2 * Wo, (uint64_t)d->Cout * 2 * Wo * Ho};
+        rc = encode_map(&p.rmap[l], const_cast<void*>(lv.residual), 4, odims, rstr, box);
+        pl->rmap_ok = (rc == SMB_OK);
+        if (rc != SMB_OK) break;
+      }
     }
     if (s == 1) {
       L.map0 = l;
@@ -997,6 +1031,8 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
   smb_conv_plan* pl = new smb_conv_plan();
   memset(&pl->p, 0, sizeof(ConvParams));
   pl->omap_ok = 0;
+  pl->rmap_ok = 0;
+  pl->rmap_ptr = nullptr;
   ConvParams& p = pl->p;
   LevelDesc& L = p.lv[0];
   const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
@@ -1047,6 +1083,19 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
     if (plan->has_residual) {
       SMB_CHECK_ARG(residual, "smb_conv_run: plan expects a residual");
       p.lv[0].residual = (const __half*)residual;
+      if (p.res_tma) {
+        smb_conv_plan* mp = const_cast<smb_conv_plan*>(plan);       // descriptor cache keyed by the residual pointer
+        if (mp->rmap_ptr != residual) {
+          const LevelDesc& L0 = p.lv[0];
+          uint64_t rdims[4] = {(uint64_t)p.Cout, (uint64_t)L0.W_out, (uint64_t)L0.H_out, (uint64_t)p.n_img};
+          uint64_t rstr[3] = {(uint64_t)p.Cout * 2, (uint64_t)p.Cout * 2 * L0.W_out, (uint64_t)p.Cout * 2 * L0.W_out * L0.H_out};
+          uint32_t rbox[4] = {64, (uint32_t)L0.BW, (uint32_t)L0.BH, 1};
+          const int erc = encode_map(&mp->p.rmap[0], const_cast<void*>(residual), 4, rdims, rstr, rbox);
+          if (erc) return erc;
+          mp->rmap_ptr = residual;
+        }
+        p.rmap[0] = mp->p.rmap[0];
+      }
     }
     if (plan->gn_stats) {
       SMB_CHECK_ARG(gn_stats, "smb_conv_run: plan expects a gn_stats buffer");
