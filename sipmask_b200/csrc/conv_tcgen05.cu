@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* rfull_bar = tempty_bar + 2;                               // [4] residual chunk landed (res_tma)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 4);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [2][256] double-buffered per tile
-  // two 128 x 64 fp16 staging tiles (128-byte swizzle) for the TMA-store epilogue
+  // n_tile/64 staging tiles of 128 px x 64 ch fp16 (128-byte swizzle).  The residual tile is TMA-loaded INTO them and each
+  // thread overwrites exactly the 64 bytes it read with its result, which is then TMA-stored: one buffer, no extra barrier.
   uint8_t* s_stage = smem + (size_t)p.stages * (kABytes + b_bytes) + 4096;
-  uint8_t* s_res = s_stage + 2 * 16384;                               // [n_tile/64] x 16 KB residual tiles (res_tma)
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int split = ((p.n_tile / 2 + 31) / 32) * 32;
     if (split > p.n_tile) split = p.n_tile;
     const int c_begin = col_half ? split : 0, c_end = col_half ? p.n_tile : split;
-    uint32_t lt = 0, stage_ctr = 0;
+    uint32_t lt = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
@@ -491,13 +491,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (n0 + c_begin + j * 8 + 8 <= p.Cout && c_begin + j * 8 < c_end)
             rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c_begin + j * 8));
       }
-      if (p.res_tma && et == 0 && tc.active) {
-        // this tile's residual (128 px x n_tile ch) arrives by TMA while the main loop is still running
-        fence_async_smem();
-        const int nchr = p.n_tile >> 6;
-        for (int c = 0; c < nchr; ++c) {
-          mbar_expect_tx(&rfull_bar[c], 16384);
-          tma_load_4d(s_res + (size_t)c * 16384, &p.rmap[tc.lvl], &rfull_bar[c], n0 + c * 64, tc.x0, tc.y0, tc.img);
+      if (p.out_tma && et == 0) {
+        bulk_wait_read<0>();                         // the previous tile's TMA stores have finished reading the staging tiles
+        if (p.res_tma && tc.active) {
+          // this tile's residual (128 px x n_tile ch) arrives by TMA while the main loop is still running
+          fence_async_smem();
+          const int nchr = p.n_tile >> 6;
+          for (int c = 0; c < nchr; ++c) {
+            mbar_expect_tx(&rfull_bar[c], 16384);
+            tma_load_4d(s_stage + (size_t)c * 16384, &p.rmap[tc.lvl], &rfull_bar[c], n0 + c * 64, tc.x0, tc.y0, tc.img);
+          }
         }
       }
       // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile)
@@ -535,17 +538,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
             }
             if (res_smem) {
+              const uint8_t* sbuf_c = s_stage + (size_t)c64 * 16384;
               mbar_wait(&rfull_bar[c64], lt & 1);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                rc[j] = *reinterpret_cast<const uint4*>(s_res + (size_t)c64 * 16384 + row * 128 + (((col_half * 4 + j) ^ (row & 7)) * 16));
+                rc[j] = *reinterpret_cast<const uint4*>(sbuf_c + row * 128 + (((col_half * 4 + j) ^ (row & 7)) * 16));
             }
             uint32_t v[32];
             tmem_ld32(t_base + (uint32_t)cc, v);
-            // the staging buffer written two chunks ago must have been read by its TMA store
-            uint8_t* sbuf = s_stage + (size_t)(stage_ctr & 1) * 16384;
-            if (et == 0 && stage_ctr >= 2) bulk_wait_read<1>();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint8_t* sbuf = s_stage + (size_t)c64 * 16384;
             tmem_ld_wait();
             float f[32];
 #pragma unroll
@@ -602,10 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (et == 0 && tc.active && !(p.debug_mode & 8)) {
               tma_store_4d(&p.omap[tc.lvl], sbuf, n0 + c64 * 64, tc.x0, tc.y0, tc.img);
               bulk_commit();
-            } else if (et == 0) {
-              bulk_commit();                           // keep the group count in step with stage_ctr
             }
-            ++stage_ctr;
 #pragma unroll
             for (int j = 0; j < 4; ++j) rc[j] = rn[j];
           }
@@ -864,13 +862,13 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   const size_t stage = (size_t)kABytes + (size_t)(p.pair ? n_tile / 2 : n_tile) * 128;
   p.out_tma = (pl->omap_ok && !p.out_f32 && n_tile % 64 == 0 && !getenv("SMB_CONV_NO_TMA_STORE")) ? 1 : 0;
   p.res_tma = (p.out_tma && p.res_mode == 1 && pl->rmap_ok && !getenv("SMB_CONV_NO_TMA_RES")) ? 1 : 0;
-  const size_t res_bytes = p.res_tma ? (size_t)(n_tile / 64) * 16384 : 0;
-  const size_t budget = (p.out_tma ? 160 : 194) * 1024 - res_bytes;
+  const size_t stage_out = p.out_tma ? (size_t)(n_tile / 64) * 16384 : 0;      // result / residual staging tiles
+  const size_t budget = 194 * 1024 - stage_out;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) { set_error("conv plan: tile too large for shared memory"); return SMB_EINVAL; }
   p.stages = stages;
-  pl->smem_bytes = stages * stage + 4096 + (p.out_tma ? 2 * 16384 : 0) + res_bytes + 1024;    // + barriers/bias (4 KB) + staging + align
+  pl->smem_bytes = stages * stage + 4096 + stage_out + 1024;    // + barriers/bias (4 KB) + staging + align
   // weights: [Cout, Ktotal] K-major
   uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
   uint64_t strides[1] = {(uint64_t)Ktotal * 2};
