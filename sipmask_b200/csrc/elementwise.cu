@@ -355,64 +355,59 @@ __global__ void offset_conv_multi_kernel(MultiDesc d, int bbox_pitch, const floa
 }
 
 // deformable im2col for all levels: a[l] = x fp16 [n,H,W,C], b[l] = offsets fp32 [n,H,W,dg*18], c[l] = col fp16 [n,H,W,9C]
-// work item = (pixel, tap) handled by one warp.
-__global__ void deform_im2col_multi_kernel(MultiDesc d, int off_pitch, int C, int dg) {
+// work item = one pixel handled by one warp: all 9 taps x 4 bilinear corners are independent 16-byte loads (36 in
+// flight per lane), the offsets of a pixel are read once, index math is 32-bit.
+__global__ void __launch_bounds__(256) deform_im2col_multi_kernel(MultiDesc d, int off_pitch, int C, int dg) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const long long total = d.start[d.num];
+  const int total = (int)d.start[d.num];          // pixels over all levels (items_per_pixel == 1)
   const int vecs = C >> 3;
   const int cpg = C / dg;
-  for (long long wq0 = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); wq0 < total;
-       wq0 += (long long)gridDim.x * warps_per_block) {
-    const int l = find_level(d, wq0);
-    const long long wq = wq0 - d.start[l];
+  for (int wq0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5); wq0 < total; wq0 += gridDim.x * warps_per_block) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLv; ++i)
+      if (i < d.num && wq0 >= (int)d.start[i]) l = i;
+    const int pix = wq0 - (int)d.start[l];
     const int H = d.H[l], W = d.W[l];
-    const int tap = (int)(wq % 9);
-    const long long pix = wq / 9;
-    const int w_ = (int)(pix % W);
-    const int h_ = (int)((pix / W) % H);
-    const int img = (int)(pix / ((long long)W * H));
-    const int i = tap / 3, j = tap - i * 3;
+    const int w_ = pix % W;
+    const int hq = pix / W;
+    const int h_ = hq % H;
+    const int img = hq / H;
     const __half* xim = reinterpret_cast<const __half*>(d.a[l]) + (size_t)img * H * W * C;
-    const float* off = reinterpret_cast<const float*>(d.b[l]);
-    __half* col = reinterpret_cast<__half*>(d.c[l]);
+    const float* off = reinterpret_cast<const float*>(d.b[l]) + (size_t)pix * off_pitch;
+    __half* col = reinterpret_cast<__half*>(d.c[l]) + (size_t)pix * 9 * C;
     for (int v = lane; v < vecs; v += 32) {
       const int g = (v * 8) / cpg;
-      const float* o = off + pix * off_pitch + g * 18 + 2 * tap;
-      const float h_im = (float)(h_ - 1 + i) + o[0];
-      const float w_im = (float)(w_ - 1 + j) + o[1];
-      float r[8];
+      const float* og = off + g * 18;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] = 0.f;
-      if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
-        const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-        const int h_high = h_low + 1, w_high = w_low + 1;
-        const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
-        const float hh = 1.f - lh, hw = 1.f - lw;
-        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-        float f[8];
-        if (h_low >= 0 && w_low >= 0) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_low * W + w_low) * C + v * 8)), f);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int i = tap / 3, j = tap - i * 3;
+        const float h_im = (float)(h_ - 1 + i) + og[2 * tap];
+        const float w_im = (float)(w_ - 1 + j) + og[2 * tap + 1];
+        float r[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] = w1 * f[e];
+        for (int e = 0; e < 8; ++e) r[e] = 0.f;
+        if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+          const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+          const int h_high = h_low + 1, w_high = w_low + 1;
+          const float lh = h_im - (float)h_low, lw = w_im - (float)w_low;
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+          const bool ok1 = h_low >= 0 && w_low >= 0, ok2 = h_low >= 0 && w_high <= W - 1;
+          const bool ok3 = h_high <= H - 1 && w_low >= 0, ok4 = h_high <= H - 1 && w_high <= W - 1;
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          const uint4 u1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(xim + (h_low * W + w_low) * C + v * 8)) : z;
+          const uint4 u2 = ok2 ? __ldg(reinterpret_cast<const uint4*>(xim + (h_low * W + w_high) * C + v * 8)) : z;
+          const uint4 u3 = ok3 ? __ldg(reinterpret_cast<const uint4*>(xim + (h_high * W + w_low) * C + v * 8)) : z;
+          const uint4 u4 = ok4 ? __ldg(reinterpret_cast<const uint4*>(xim + (h_high * W + w_high) * C + v * 8)) : z;
+          float f1[8], f2[8], f3[8], f4[8];
+          unpack8(u1, f1); unpack8(u2, f2); unpack8(u3, f3); unpack8(u4, f4);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] = (w1 * f1[e] + w2 * f2[e] + w3 * f3[e] + w4 * f4[e]);
         }
-        if (h_low >= 0 && w_high <= W - 1) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_low * W + w_high) * C + v * 8)), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] += w2 * f[e];
-        }
-        if (h_high <= H - 1 && w_low >= 0) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_high * W + w_low) * C + v * 8)), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] += w3 * f[e];
-        }
-        if (h_high <= H - 1 && w_high <= W - 1) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(xim + ((size_t)h_high * W + w_high) * C + v * 8)), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] += w4 * f[e];
-        }
+        *reinterpret_cast<uint4*>(col + tap * C + v * 8) = pack8(r);
       }
-      *reinterpret_cast<uint4*>(col + (size_t)pix * 9 * C + (size_t)tap * C + v * 8) = pack8(r);
     }
   }
 }
@@ -553,7 +548,7 @@ extern "C" int smb_deform_im2col_multi(int num_levels, const void* const* xs, co
   SMB_CHECK_ARG(C % 8 == 0 && deformable_groups > 0 && C % deformable_groups == 0 && (C / deformable_groups) % 8 == 0,
                 "smb_deform_im2col_multi: C=%d dg=%d unsupported", C, deformable_groups);
   MultiDesc d;
-  SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, 9, n_img) == 0, "smb_deform_im2col_multi: bad levels");
+  SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, 1, n_img) == 0, "smb_deform_im2col_multi: bad levels");
   for (int l = 0; l < num_levels; ++l) { d.a[l] = xs[l]; d.b[l] = offs[l]; d.c[l] = cols[l]; d.scale[l] = 1.f; }
   deform_im2col_multi_kernel<<<grid_for(d.start[num_levels] * 32, 256), 256, 0, (cudaStream_t)stream>>>(d, off_pitch, C,
                                                                                                     deformable_groups);

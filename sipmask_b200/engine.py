@@ -45,6 +45,7 @@ class SipMaskEngine(object):
         self.pos_dtype = pos_dtype
         self.sd = {k: v for k, v in state_dict.items()}
         self.ops = []            # list of zero-argument callables = the launch sequence
+        self.op_names = []
         self.n_launch = 0
         self._keep = []
         self._wcache = {}
@@ -68,8 +69,9 @@ class SipMaskEngine(object):
         return (self._w(prefix + '.weight'), self._w(prefix + '.bias'), self._w(prefix + '.running_mean'),
                 self._w(prefix + '.running_var'))
 
-    def _add(self, fn, launches=1):
+    def _add(self, fn, launches=1, name=None):
         self.ops.append(fn)
+        self.op_names.append(name or getattr(fn, '__name__', 'op'))
         self.n_launch += launches
 
     def _conv(self, x, wkey, k, stride=1, relu=False, bn=None, bias_key=None, residual=None, residual_upsample=False,
@@ -98,7 +100,7 @@ class SipMaskEngine(object):
         self.conv_flops += fl
         self.conv_meta.append(dict(name=wkey or 'shared', M=N * Ho * Wo, N=weight.shape[0], K=weight.shape[1], k=k, stride=stride,
                                    flops=fl, res=residual is not None, gn=gn_stats is not None))
-        self._add(plan.run)
+        self._add(plan.run, name='conv')
         return out
 
     # -------------------------------------------------------------------------------------------- build
@@ -115,7 +117,7 @@ class SipMaskEngine(object):
         self.img = self._t(N, 3, H, W, dtype=torch.float32)
         # ---- stem
         img8 = self._t(N, H + 6, W + 8, 8)
-        self._add(lambda: C.image_to_nhwc8(self.img, img8))
+        self._add(lambda: C.image_to_nhwc8(self.img, img8), name='image_to_nhwc8')
         wk, b = C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'), device=self.dev)
         s1 = self._t(N, H // 2, W // 2, 64)
         stem = C.StemPlan(img8, wk, b, s1, N, H, W)
@@ -124,9 +126,9 @@ class SipMaskEngine(object):
         fl = 2.0 * N * (H // 2) * (W // 2) * 64 * 147                                 # algorithmic 7x7x3 (executed K is 448)
         self.conv_flops += fl
         self.conv_meta.append(dict(name='stem', M=N * (H // 2) * (W // 2), N=64, K=448, k=7, stride=2, flops=fl, res=False, gn=False))
-        self._add(stem.run)
+        self._add(stem.run, name='conv')
         x = self._t(N, H // 4, W // 4, 64)
-        self._add(lambda s1=s1, x=x: C.maxpool3x3s2(s1, x))
+        self._add(lambda s1=s1, x=x: C.maxpool3x3s2(s1, x), name='maxpool')
         # ---- residual stages (caffe style: stride on conv1, resnet.py:125-130)
         feats = []
         for i, nb in enumerate(ARCH[self.depth]):
@@ -153,7 +155,7 @@ class SipMaskEngine(object):
         p5 = self._conv(lat5, 'neck.fpn_convs.2.conv.weight', 3, bias_key='neck.fpn_convs.2.conv.bias')
         p6 = self._conv(p5, 'neck.fpn_convs.3.conv.weight', 3, 2, bias_key='neck.fpn_convs.3.conv.bias')
         p6r = self._t(*p6.shape)
-        self._add(lambda: C.upsample_bilinear(p6, 1, out=p6r, relu=True))          # F.relu(outs[-1]) (fpn.py:175)
+        self._add(lambda: C.upsample_bilinear(p6, 1, out=p6r, relu=True), name='relu_copy')   # F.relu(outs[-1]) (fpn.py:175)
         p7 = self._conv(p6r, 'neck.fpn_convs.4.conv.weight', 3, 2, bias_key='neck.fpn_convs.4.conv.bias')
         self.fpn_outs = [p3, p4, p5, p6, p7]
         self._build_head(self.fpn_outs)
@@ -180,7 +182,7 @@ class SipMaskEngine(object):
         self.conv_flops += fl
         self.conv_meta.append(dict(name='multi-level x%d' % len(xs), M=N * npix, N=weight.shape[0], K=weight.shape[1], k=k, stride=1,
                                    flops=fl, res=False, gn=gn_stats is not None))
-        self._add(plan.run)
+        self._add(plan.run, name='conv')
         return outs
 
     def _tower_conv(self, xs, wkey, gn_prefix, bias_key, stats):
@@ -192,7 +194,7 @@ class SipMaskEngine(object):
             gamma = self._w(gn_prefix + '.weight').to(self.dev)
             beta = self._w(gn_prefix + '.bias').to(self.dev)
             self._keep += [gamma, beta]
-            self._add(lambda: C.groupnorm_relu_apply_multi(ys, stats, gamma, beta, 1e-5, True))
+            self._add(lambda: C.groupnorm_relu_apply_multi(ys, stats, gamma, beta, 1e-5, True), name='gn_apply')
             return ys
         w, b = self._packed(wkey, bias_key)
         return self._conv_multi(xs, w, 3, relu=True, bias=b)
@@ -207,7 +209,7 @@ class SipMaskEngine(object):
         n_tower = (self.stacked - 1) + self.stacked + 1
         # one int64 fixed-point statistics arena for every (conv, level) GroupNorm, zeroed once per forward
         self.gn_arena = self._t(n_tower, nl, N, 32, 2, dtype=torch.int64, zero=True)
-        self._add(lambda: self.gn_arena.zero_(), 0)
+        self._add(lambda: self.gn_arena.zero_(), 0, name='memset')
         ncls, CC = self.ncls, self.ncls + 128
         CCp = (CC + 15) // 16 * 16
         w_cls = torch.cat([self._w(hp + 'fcos_cls.weight'), self._w(hp + 'sip_cof.weight')], 0)
@@ -245,16 +247,16 @@ class SipMaskEngine(object):
         self._conv_multi(reg_feats, wk_reg, 3, outs=regctr_l, bias=b_reg, cout_real=5)
         # FeatureAlign: offsets from scale*fcos_reg, DCN 3x3 dg=4, GN, ReLU (sipmask_head.py:49-55)
         offs = [self._t(N, h, w, 72, dtype=torch.float32) for h, w in sizes]
-        self._add(lambda: C.offset_conv1x1_multi(regctr_l, self.scales, w_off, offs))
+        self._add(lambda: C.offset_conv1x1_multi(regctr_l, self.scales, w_off, offs), name='offset_conv')
         cols = [self._t(N, h, w, 2304) for h, w in sizes]
-        self._add(lambda: C.deform_im2col_multi(cls_feats, offs, 4, cols))
+        self._add(lambda: C.deform_im2col_multi(cls_feats, offs, 4, cols), name='deform_im2col')
         if self.gn:
             stats = [self.gn_arena[si, l] for l in range(nl)]
             aligned = self._conv_multi(cols, wk_dcn, 1, gn_stats=stats)
             gamma = self._w(hp + 'feat_align.norm.weight').to(self.dev)
             beta = self._w(hp + 'feat_align.norm.bias').to(self.dev)
             self._keep += [gamma, beta]
-            self._add(lambda: C.groupnorm_relu_apply_multi(aligned, stats, gamma, beta, 1e-5, True))
+            self._add(lambda: C.groupnorm_relu_apply_multi(aligned, stats, gamma, beta, 1e-5, True), name='gn_apply')
         else:
             aligned = self._conv_multi(cols, wk_dcn, 1, relu=True)
         # fcos_cls | sip_cof on the aligned feature (sipmask_head.py:264,271)
@@ -263,12 +265,12 @@ class SipMaskEngine(object):
         h3, w3 = sizes[0]
         cat = self._t(N, h3, w3, 768)
         for l in range(3):
-            self._add(lambda l=l: C.upsample_bilinear(reg_feats[l], 2 ** l, out=cat, out_choff=256 * l))
+            self._add(lambda l=l: C.upsample_bilinear(reg_feats[l], 2 ** l, out=cat, out_choff=256 * l), name='upsample')
         # prototype branch (sipmask_head.py:283-285)
         m0 = self._conv(cat, hp + 'sip_mask_lat0.weight', 1, relu=True, bias_key=hp + 'sip_mask_lat0.bias')
         m1 = self._conv(m0, hp + 'sip_mask_lat.weight', 3, relu=True, bias_key=hp + 'sip_mask_lat.bias')
         self.protos = self._t(N, 4 * h3, 4 * w3, 32)
-        self._add(lambda: C.upsample_bilinear(m1, 4, out=self.protos))
+        self._add(lambda: C.upsample_bilinear(m1, 4, out=self.protos), name='upsample')
         if self.build_post:
             self._build_postproc()
 
@@ -281,7 +283,7 @@ class SipMaskEngine(object):
         nl = len(feats)
         tot = sum(h * w for h, w in sizes)
         self.gn_arena = self._t(2 * self.stacked, nl, N, 32, 2, dtype=torch.int64, zero=True)
-        self._add(lambda: self.gn_arena.zero_(), 0)
+        self._add(lambda: self.gn_arena.zero_(), 0, name='memset')
         ncls = self.ncls
         CCp = (ncls + 1 + 15) // 16 * 16
         w_cls = torch.cat([self._w(hp + 'fcos_cls.weight'), self._w(hp + 'fcos_centerness.weight')], 0)
@@ -368,7 +370,7 @@ class SipMaskEngine(object):
                                             L.ptr(self.cand_boxes[n]), L.ptr(self.cand_scores[n]), L.ptr(self.cand_ctr[n]),
                                             L.ptr(self.cand_loc[n]), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream_ptr()),
                         'smb_decode_topk')
-            self._add(decode, 3)
+            self._add(decode, 3, name='decode_topk')
             iou_thr = float(cfg['nms']['iou_thr'])
             if not self.ssd:
                 nws_bytes = lib.smb_multiclass_nms_workspace_bytes(ncand, ncls)
@@ -390,7 +392,7 @@ class SipMaskEngine(object):
                                              L.ptr(self.det[n]), L.ptr(self.labels[n]), L.ptr(self.idx[n]),
                                              L.ptr(self.count[n:n + 1]), L.ptr(nws), ctypes.c_size_t(nws_bytes), L.stream_ptr()),
                             'smb_fast_nms')
-            self._add(nms, 2)
+            self._add(nms, 4 if not self.ssd else 2, name='nms')
             cof_src = self.clscof[n][:, ncls:ncls + 128]                       # [tot,128] view, pitch CCp
 
             def gather(n=n, cof_src=cof_src):
@@ -399,14 +401,14 @@ class SipMaskEngine(object):
                 L.check(lib.smb_gather_rows_f32(L.ptr(cof_src), CCp, L.ptr(self.loc_kept[n]), L.ptr(self.count[n:n + 1]),
                                                 self.max_num, 128, L.ptr(self.det_cofs[n]), L.stream_ptr()), 'smb_gather_rows_f32')
                 self.det_boxes4[n].copy_(self.det[n][:, :4])
-            self._add(gather, 1)
+            self._add(gather, 1, name='gather_cofs')
 
             def masks(n=n):
                 # fused: prototypes -> sub-region dot/sigmoid/crop -> x2 bilinear -> threshold -> bit-pack (no pos_masks tensor)
                 L.check(lib.smb_mask_assemble_pack(L.ptr(self.protos[n]), L.F16, 1, L.ptr(self.det_cofs[n]), L.ptr(self.det_boxes4[n]),
                                                    self._box_scale4, L.ptr(self.mask_bits[n]), Hm, Wm, self.max_num, oh, ow,
                                                    ctypes.c_float(self.mask_thr), L.stream_ptr()), 'smb_mask_assemble_pack')
-            self._add(masks, 1)
+            self._add(masks, 1, name='mask_fused')
 
     # ---------------------------------------------------------------------------------------------- run
     def _run_ops(self):
