@@ -257,4 +257,6 @@ def test_multi_level_conv_and_helpers_match_single_level():
         o1 = conv.offset_conv1x1(bbs[i], scales[i], w_off)
         c1 = conv.deform_im2col(xs[i], o1, 4)
         torch.cuda.synchronize()
-        assert torch.equal(o1, offs[i]) and torch.equal(c1, cols[i]), i
+        assert torch.equal(o1, offs[i]), i
+        # the batched kernel evaluates the four bilinear terms in one expression (different FMA contraction): fp16-ulp level
+        assert (c1.float() - cols[i].float()).abs().max().item() <= 2e-3 * (c1.float().abs().max().item() + 1), i
