@@ -186,6 +186,9 @@ typedef struct {
 int smb_conv_plan_create_multi(const smb_conv_desc_t* desc, int num_levels, const smb_conv_level_t* levels,
                                const void* weight, smb_conv_plan_t** plan_out);
 void smb_conv_plan_destroy(smb_conv_plan_t* plan);
+/* Cap the persistent grid of a plan (multiple of its cluster size), so that independent convolutions launched on
+ * different streams share the GPU instead of running one after the other with half-empty last waves. */
+int smb_conv_plan_set_max_ctas(smb_conv_plan_t* plan, int max_ctas);
 /* out = relu?( (acc + bias) * alpha + residual ); alpha carries the per-level `Scale` of fcos_reg
  * (sipmask_head.py:261, ops/scale.py:12-15). */
 int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, void* gn_stats,

@@ -89,6 +89,10 @@ class ConvPlan(object):
                                              ctypes.byref(self.handle)), 'smb_conv_plan_create')
         self.out = out
 
+    def set_max_ctas(self, n):
+        L.check(L.lib().smb_conv_plan_set_max_ctas(self.handle, int(n)), 'smb_conv_plan_set_max_ctas')
+        return self
+
     def run(self, stream=None):
         L.check(L.lib().smb_conv_run(self.handle, L.ptr(self.bias), L.ptr(self.residual), L.ptr(self.gn_stats),
                                      ctypes.c_float(self.alpha), stream if stream is not None else L.stream_ptr()),

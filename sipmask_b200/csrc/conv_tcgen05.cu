@@ -1070,6 +1070,17 @@ extern "C" int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, 
 
 extern "C" void smb_conv_plan_destroy(smb_conv_plan_t* plan) { delete plan; }
 
+// Cap the persistent grid (e.g. to half the SMs) so that two independent convolutions captured on different streams
+// can run side by side and fill each other's partial waves.
+extern "C" int smb_conv_plan_set_max_ctas(smb_conv_plan_t* plan, int max_ctas) {
+  SMB_CHECK_ARG(plan && max_ctas >= 1, "smb_conv_plan_set_max_ctas: bad argument");
+  const int c = plan->p.cluster;
+  int g = (max_ctas / c) * c;
+  if (g < c) g = c;
+  if (g < plan->grid) plan->grid = g;
+  return SMB_OK;
+}
+
 extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, void* gn_stats,
                             float alpha, smb_stream_t stream) {
   SMB_CHECK_ARG(plan, "smb_conv_run: null plan");

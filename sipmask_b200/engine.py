@@ -25,12 +25,13 @@ class SipMaskEngine(object):
     def __init__(self, state_dict, img_hw, batch=1, depth=50, stacked_convs=4, gn=True, ssd_flag=False, num_classes=81,
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
                  mask_thr=0.4, use_graph=True, pos_dtype=torch.float32, head_only=False, feat_sizes=None, in_channels=256,
-                 fcos=False, prefix_head='bbox_head.', build_postproc=True):
+                 fcos=False, prefix_head='bbox_head.', build_postproc=True, two_streams=True):
         L.check(L.lib().smb_check_device(), 'smb_check_device')
         self.dev = torch.device(device)
         self.N, (self.H, self.W) = batch, img_hw
         self.head_only, self.feat_sizes, self.in_channels, self.fcos = head_only, feat_sizes, in_channels, fcos
         self.hp, self.build_post = prefix_head, build_postproc
+        self.two_streams = two_streams
         assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
         assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
         self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
@@ -46,6 +47,10 @@ class SipMaskEngine(object):
         self.sd = {k: v for k, v in state_dict.items()}
         self.ops = []            # list of zero-argument callables = the launch sequence
         self.op_names = []
+        self.op_tags = []        # 0 = main stream, 1 = side stream, 'fork' / 'join' = stream dependencies
+        self._tag = 0
+        self._max_ctas = None
+        self.side_stream = None
         self.n_launch = 0
         self._keep = []
         self._wcache = {}
@@ -72,7 +77,13 @@ class SipMaskEngine(object):
     def _add(self, fn, launches=1, name=None):
         self.ops.append(fn)
         self.op_names.append(name or getattr(fn, '__name__', 'op'))
+        self.op_tags.append(self._tag)
         self.n_launch += launches
+
+    def _marker(self, kind):
+        self.ops.append(None)
+        self.op_names.append(kind)
+        self.op_tags.append(kind)
 
     def _conv(self, x, wkey, k, stride=1, relu=False, bn=None, bias_key=None, residual=None, residual_upsample=False,
               gn_stats=None, out=None, out_dtype=torch.float16, cout_pad=None, weight=None, bias=None, cin=None,
@@ -94,6 +105,8 @@ class SipMaskEngine(object):
             out = self._t(N, Ho, Wo, weight.shape[0], dtype=out_dtype)
         plan = C.ConvPlan(x, weight, out, k, stride, relu=relu, bias=bias, residual=residual,
                           residual_upsample=residual_upsample, gn_stats=gn_stats, cin=cin)
+        if self._max_ctas:
+            plan.set_max_ctas(self._max_ctas)
         self._keep.append(plan)
         self.conv_plans.append(plan)
         fl = 2.0 * N * Ho * Wo * (cout_real or weight.shape[0]) * weight.shape[1]                 # algorithmic FLOPs
@@ -175,6 +188,8 @@ class SipMaskEngine(object):
         if outs is None:
             outs = [self._t(N, x.shape[1], x.shape[2], weight.shape[0], dtype=out_dtype) for x in xs]
         plan = C.ConvPlanMulti(xs, weight, outs, k, relu=relu, bias=bias, gn_stats=gn_stats)
+        if self._max_ctas:
+            plan.set_max_ctas(self._max_ctas)
         self._keep.append(plan)
         self.conv_plans.append(plan)
         npix = sum(x.shape[1] * x.shape[2] for x in xs)
@@ -235,16 +250,29 @@ class SipMaskEngine(object):
         self.level_views = list(zip(clscof_l, regctr_l))
         si = 0
         cls_feats, reg_feats = list(feats), list(feats)
+        # The cls and reg towers are independent chains of 202-tile GEMMs (1.36 waves each on 148 SMs).  They are
+        # captured on two streams with their persistent grids capped at half the GPU, so together they keep every SM
+        # busy (2.73 waves for a pair instead of 2 + 2).
+        two = self.two_streams
+        if two:
+            self._marker('fork')
+            self._max_ctas = 74
+        self._tag = 0
         for i in range(self.stacked - 1):
             cls_feats = self._tower_conv(cls_feats, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
                                          hp + 'cls_convs.%d.conv.bias' % i, [self.gn_arena[si, l] for l in range(nl)])
             si += 1
+        self._tag = 1 if two else 0
         for i in range(self.stacked):
             reg_feats = self._tower_conv(reg_feats, hp + 'reg_convs.%d.conv.weight' % i, hp + 'reg_convs.%d.gn' % i,
                                          hp + 'reg_convs.%d.conv.bias' % i, [self.gn_arena[si, l] for l in range(nl)])
             si += 1
         # fcos_reg | fcos_centerness on the reg tower (sipmask_head.py:261,265), raw fp32 (Scale applied by consumers)
         self._conv_multi(reg_feats, wk_reg, 3, outs=regctr_l, bias=b_reg, cout_real=5)
+        if two:
+            self._marker('join')
+            self._marker('fork')
+        self._tag = 0
         # FeatureAlign: offsets from scale*fcos_reg, DCN 3x3 dg=4, GN, ReLU (sipmask_head.py:49-55)
         offs = [self._t(N, h, w, 72, dtype=torch.float32) for h, w in sizes]
         self._add(lambda: C.offset_conv1x1_multi(regctr_l, self.scales, w_off, offs), name='offset_conv')
@@ -261,6 +289,8 @@ class SipMaskEngine(object):
             aligned = self._conv_multi(cols, wk_dcn, 1, relu=True)
         # fcos_cls | sip_cof on the aligned feature (sipmask_head.py:264,271)
         self._conv_multi(aligned, wk_cls, 3, outs=clscof_l, bias=b_cls)
+        # prototype branch on the side stream, next to FeatureAlign / the cls heads
+        self._tag = 1 if two else 0
         # prototype input: reg feature of levels 0..2 at P3 resolution (sipmask_head.py:275-281)
         h3, w3 = sizes[0]
         cat = self._t(N, h3, w3, 768)
@@ -271,6 +301,10 @@ class SipMaskEngine(object):
         m1 = self._conv(m0, hp + 'sip_mask_lat.weight', 3, relu=True, bias_key=hp + 'sip_mask_lat.bias')
         self.protos = self._t(N, 4 * h3, 4 * w3, 32)
         self._add(lambda: C.upsample_bilinear(m1, 4, out=self.protos), name='upsample')
+        if two:
+            self._marker('join')
+        self._tag = 0
+        self._max_ctas = None
         if self.build_post:
             self._build_postproc()
 
@@ -412,8 +446,20 @@ class SipMaskEngine(object):
 
     # ---------------------------------------------------------------------------------------------- run
     def _run_ops(self):
-        for f in self.ops:
-            f()
+        s0 = torch.cuda.current_stream(self.dev)
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.dev)
+        s1 = self.side_stream
+        for f, tag in zip(self.ops, self.op_tags):
+            if tag == 'fork':
+                s1.wait_stream(s0)
+            elif tag == 'join':
+                s0.wait_stream(s1)
+            elif tag == 1:
+                with torch.cuda.stream(s1):
+                    f()
+            else:
+                f()
 
     def forward(self, img=None):
         """img: NCHW fp32 CUDA tensor (or None to reuse the resident input).  Returns the device result record."""

@@ -19,6 +19,8 @@ names = getattr(eng, 'op_names', None) or ['op%d' % i for i in range(len(eng.ops
 tot = 0.0
 rows = []
 for i, op in enumerate(eng.ops):
+    if op is None:
+        continue
     op()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
