@@ -273,13 +273,11 @@ def run_ours(args):
     if rank == 0:
         pk, pk_kind = peaks()
         # ---- roofline of the dominant kernel (conv_gemm_kernel): all conv launches of one step replayed as one graph
-        for p in eng.conv_plans:
-            p.run()
+        eng._run_ops(only={'conv'})
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for p in eng.conv_plans:
-                p.run()
+            eng._run_ops(only={'conv'})          # same launches, same two-stream schedule as in the step
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()

@@ -345,6 +345,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) TS(1);
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+  // tail of the previous kernel in the stream; from here on we touch global memory, so wait for it to complete, and let
+  // the next kernel begin its own prologue as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int crank = (p.cluster > 1) ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / p.cluster, num_clusters = gridDim.x / p.cluster;
@@ -1128,13 +1133,20 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = plan->smem_bytes;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("SMB_CONV_PDL"); use_pdl = e ? atoi(e) : 1; }
+  if (use_pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   {
     cudaError_t e = p.pair ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p) : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, p);
     if (e != cudaSuccess) {

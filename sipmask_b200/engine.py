@@ -10,6 +10,7 @@ Weights come from a reference-keyed state_dict; all buffers are
 are baked into per-layer plans, and the launch sequence can be replayed as one CUDA graph.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -256,7 +257,7 @@ class SipMaskEngine(object):
         two = self.two_streams
         if two:
             self._marker('fork')
-            self._max_ctas = 74
+            self._max_ctas = int(os.environ.get('SMB_HEAD_MAX_CTAS', '100')) or None
         self._tag = 0
         for i in range(self.stacked - 1):
             cls_feats = self._tower_conv(cls_feats, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
@@ -445,12 +446,16 @@ class SipMaskEngine(object):
             self._add(masks, 1, name='mask_fused')
 
     # ---------------------------------------------------------------------------------------------- run
-    def _run_ops(self):
+    def _run_ops(self, only=None):
+        """Issue the launch sequence on the current stream (+ the side stream between fork / join markers).
+        `only`: optional set of op names to issue (markers are always honoured), e.g. {'conv'} for the roofline graph."""
         s0 = torch.cuda.current_stream(self.dev)
         if self.side_stream is None:
             self.side_stream = torch.cuda.Stream(device=self.dev)
         s1 = self.side_stream
-        for f, tag in zip(self.ops, self.op_tags):
+        for f, tag, name in zip(self.ops, self.op_tags, self.op_names):
+            if only is not None and f is not None and name not in only:
+                continue
             if tag == 'fork':
                 s1.wait_stream(s0)
             elif tag == 'join':
