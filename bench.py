@@ -93,7 +93,7 @@ def build_oracle(threads):
     return net
 
 
-ROLL = 200          # untimed pre/post-roll steps around the timed region while nvidia-smi samples clocks
+ROLL = 500          # untimed pre/post-roll steps around the timed region while nvidia-smi samples clocks
 CLS_BIAS = -5.0
 TEST_CFG = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
 
@@ -178,32 +178,40 @@ def run_ours(args):
     dev = torch.device('cuda', local)
 
     sd = synth.detector_state_dict(50, seed=1, cls_bias=CLS_BIAS)
-    eng = SipMaskEngine(sd, (H, W), test_cfg=TEST_CFG, img_shape=(H, IMG_W, 3), use_graph=True, device=dev)
+    from sipmask_b200.serving import PipelinedRunner, EnginePool, make_engines
+    nfl = max(1, args.in_flight)
+    # nfl images in flight per GPU: nfl engines (shared weights, private activations + CUDA graph), one image per forward
+    engs = make_engines(sd, (H, W), in_flight=nfl, test_cfg=TEST_CFG, img_shape=(H, IMG_W, 3), use_graph=True, device=dev)
+    eng = engs[0]
     img_host = synth.synthetic_image(H, W, seed=rank).pin_memory()        # one image per GPU (weak scaling)
-    eng.img.copy_(img_host, non_blocking=True)
+    for e in engs:
+        e.img.copy_(img_host, non_blocking=True)
+    torch.cuda.synchronize()
+    pool = EnginePool(engs)
     rec = torch.zeros((world, eng.max_num, 7), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def step(resident=True):
-        if not resident:
-            eng.img.copy_(img_host, non_blocking=True)
-        out = eng.forward(None)
-        if world > 1:
-            # the single collective of the path: fixed-shape detection record
-            sdist.gather_records(sdist.pack_record(out['det_bboxes'][0], out['det_labels'][0], out['count']), out=rec)
-        return out
+    def gather(out):
+        # the single collective of the path: fixed-shape detection record, on the main stream
+        sdist.gather_records(sdist.pack_record(out['det_bboxes'][0], out['det_labels'][0], out['count']), out=rec)
+
+    gather_fn = gather if world > 1 else None
+
+    def step():
+        pool.step(gather_fn)
+
+    def step_finish():
+        pool.flush(gather_fn)
 
     # end-to-end through the public serving API: pinned-host image in, pinned-host record + bit-packed masks out, the
-    # upload / replay / download of consecutive images overlapped on three streams (sipmask_b200/serving.py)
-    from sipmask_b200.serving import PipelinedRunner
-    runner = PipelinedRunner(eng)
+    # upload / replay / download of consecutive images overlapped on their own streams (sipmask_b200/serving.py)
+    runner = PipelinedRunner(engs)
     copy_done = []
 
     def step_e2e():
-        slot = runner.submit(img_host)
-        if world > 1:
-            out = dict(det_bboxes=eng.det, det_labels=eng.labels, count=eng.count)
-            sdist.gather_records(sdist.pack_record(out['det_bboxes'][0], out['det_labels'][0], out['count']), out=rec)
-        copy_done.append(slot)
+        copy_done.append(runner.step(img_host, gather_fn))
+
+    def e2e_finish():
+        runner.flush(gather_fn)       # the timed region ends when the last result is on the host
 
     def timed(fn, steps, sample_clocks=False, finish=None):
         """K steps between barrier+synchronize, CUDA events, max over ranks.  nvidia-smi samples clocks every 100 ms;
@@ -215,6 +223,8 @@ def run_ours(args):
         if sample_clocks:
             for _ in range(ROLL):                       # fixed count: every rank must issue the same collectives
                 fn()
+            if finish is not None:
+                finish()
             torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -232,6 +242,8 @@ def run_ours(args):
         if sample_clocks:
             for _ in range(ROLL):
                 fn()
+            if finish is not None:
+                finish()
             torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         if clocks is not None:
@@ -243,15 +255,14 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    step_finish()
     torch.cuda.synchronize()
-    total_ms, clocks = timed(step, args.steps, sample_clocks=True)
+    total_ms, clocks = timed(step, args.steps, sample_clocks=True, finish=step_finish)
     ms_per_step = total_ms / args.steps
     value = world * 1000.0 / ms_per_step
     for _ in range(3):
         step_e2e()
-    def e2e_finish():
-        torch.cuda.current_stream().wait_stream(runner.s_d2h)      # the timed region ends when the last result is on the host
-
+    e2e_finish()
     e2e_ms, _ = timed(step_e2e, args.steps, finish=e2e_finish)
     e2e_value = world * 1000.0 / (e2e_ms / args.steps)
     last = runner.result(copy_done[-1])
@@ -263,38 +274,72 @@ def run_ours(args):
                 ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16',
                 data='synthetic',
                 config=dict(workload=WORKLOAD, parallelism='dp%d (one image per GPU, one all-gather of the detection record)' % world,
-                            detections_per_image=ndet, cuda_graph=True,
+                            detections_per_image=ndet, cuda_graph=True, images_in_flight=nfl, batch_per_forward=1,
                             l2='no flush: one step streams ~1.3 GB of activations/masks through a 126 MB L2, so nothing but '
                                'weights (51 MB) can survive from the previous step'),
                 clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                         ms_per_step=e2e_ms / args.steps),
                 gpu_launches=eng.n_launch * args.steps)
+    torch.cuda.synchronize()
 
     if rank == 0:
         pk, pk_kind = peaks()
-        # ---- roofline of the dominant kernel (conv_gemm_kernel): all conv launches of one step replayed as one graph
-        eng._run_ops(only={'conv'})
+        # ---- roofline of the dominant kernel (conv_gemm_kernel): the conv launches of one step of EVERY engine in flight,
+        # captured per engine (same stream schedule as in the step) and replayed concurrently on the pool's streams
+        graphs = []
+        for e, st in zip(engs, pool.streams):
+            with torch.cuda.stream(st):
+                e._run_ops(only={'conv'})
+                st.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    e._run_ops(only={'conv'})
+            graphs.append(g)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            eng._run_ops(only={'conv'})          # same launches, same two-stream schedule as in the step
+
+        def conv_round():
+            for g, st in zip(graphs, pool.streams):
+                with torch.cuda.stream(st):
+                    g.replay()
+
         for _ in range(3):
-            g.replay()
+            conv_round()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(3, min(args.steps, 20))
         e0.record()
+        for st in pool.streams:
+            st.wait_event(e0)
         for _ in range(reps):
-            g.replay()
+            conv_round()
+        pool.join()
         e1.record()
         torch.cuda.synchronize()
-        conv_ms = e0.elapsed_time(e1) / reps
+        conv_ms = e0.elapsed_time(e1) / (reps * nfl)                      # per image
         tf = eng.conv_flops / (conv_ms * 1e-3) / 1e12
         peak_tf = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops', 1400.0)))
         line['roofline'] = dict(bound='tensor', kernel='conv_gemm_kernel (%d launches/step)' % len(eng.conv_plans),
                                 achieved=tf, peak=peak_tf, unit='TFLOP/s', frac=tf / peak_tf, traffic=None,
                                 peak_source=pk_kind + ' bf16_tflops_sustained', algorithmic_gflop_per_step=eng.conv_flops / 1e9,
-                                ms_per_step=conv_ms, share_of_step=conv_ms / ms_per_step)
+                                ms_per_step=conv_ms, share_of_step=conv_ms / ms_per_step,
+                                note='conv launches of %d images in flight replayed concurrently; time per image' % nfl)
+        del graphs
+        # ---- strictly serial reference point: ONE engine tuned for a single stream, one image at a time
+        if nfl > 1:
+            e1s = make_engines(sd, (H, W), in_flight=1, test_cfg=TEST_CFG, img_shape=(H, IMG_W, 3), use_graph=True, device=dev)[0]
+            e1s.img.copy_(img_host, non_blocking=True)
+            for _ in range(5):
+                e1s.forward(None)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(max(args.steps, 20)):
+                e1s.forward(None)
+            e1.record()
+            torch.cuda.synchronize()
+            sms = e0.elapsed_time(e1) / max(args.steps, 20)
+            line['serial'] = dict(ms_per_step=sms, value=1000.0 / sms, unit='images/s',
+                                  note='one image in flight (latency-optimal planner settings), same GPU, N=1 rank only')
+            del e1s
         # ---- mask assembly (BASELINE metric part 2): HBM GB/s of the fused kernel, N = max_per_img detections
         N = eng.max_num
         Hm, Wm = eng.protos.shape[1], eng.protos.shape[2]
@@ -356,6 +401,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--in-flight', type=int, default=int(os.environ.get('SMB_IN_FLIGHT', '4')),
+                    help='images in flight per GPU (independent batch-1 forwards on separate streams); 1 = strictly serial')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

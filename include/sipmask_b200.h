@@ -189,6 +189,10 @@ void smb_conv_plan_destroy(smb_conv_plan_t* plan);
 /* Cap the persistent grid of a plan (multiple of its cluster size), so that independent convolutions launched on
  * different streams share the GPU instead of running one after the other with half-empty last waves. */
 int smb_conv_plan_set_max_ctas(smb_conv_plan_t* plan, int max_ctas);
+/* Planner knob for plans created AFTER the call: the N tile is the largest of {256,128,64} that still yields at least
+ * `min_tiles` output tiles (default 48; <= 0 restores the default).  Small values favour fat tiles (fewer bytes through
+ * L2 -> SM per FLOP), large values favour occupancy of a single stream.  Returns the previous value. */
+int smb_conv_set_min_tiles(int min_tiles);
 /* out = relu?( (acc + bias) * alpha + residual ); alpha carries the per-level `Scale` of fcos_reg
  * (sipmask_head.py:261, ops/scale.py:12-15). */
 int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, const void* residual, void* gn_stats,

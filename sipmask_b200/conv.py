@@ -52,6 +52,11 @@ def pack_stem_weight(w, bn, eps=1e-5, device=None):
     return wk, bias
 
 
+def set_min_tiles(n):
+    """Planner knob for plans created afterwards (smb_conv_set_min_tiles); returns the previous value."""
+    return int(L.lib().smb_conv_set_min_tiles(int(n)))
+
+
 class ConvPlan(object):
     """One convolution bound to fixed input / weight / output buffers (TMA descriptors are baked at creation)."""
 

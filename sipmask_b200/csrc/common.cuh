@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
 
 #include "../../include/sipmask_b200.h"
 
@@ -39,6 +41,36 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while the previous kernel in the
+// stream is still draining; it must call pdl_wait() before its first global-memory access (the wait returns once the
+// previous grid has completed and its writes are visible).  Chains of short kernels lose the ~1-2 us launch gap each.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  static int enabled = -1;                                  // SMB_PDL_AUX=1 turns the attribute on; measured SLOWER for the
+                                                            // elementwise / NMS kernels (r01: 639 vs 656 img/s), so off by default
+  if (enabled < 0) {
+    const char* e = getenv("SMB_PDL_AUX");
+    enabled = e ? atoi(e) : 0;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // GroupNorm statistics are accumulated as 64-bit fixed point (deterministic integer atomics)

@@ -815,6 +815,13 @@ struct smb_conv_plan {
   const void* rmap_ptr;           // single-level plans: residual pointer rmap[0] is currently encoded for (lazy, smb_conv_run)
 };
 
+static int g_min_tiles = 48;
+extern "C" int smb_conv_set_min_tiles(int min_tiles) {
+  const int prev = g_min_tiles;
+  g_min_tiles = min_tiles > 0 ? min_tiles : 48;
+  return prev;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -847,8 +854,10 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   if (Cout > 64 && Cout % 64 == 0) cand[nc++] = 64;
   if (nc == 0) { set_error("conv plan: unsupported Cout=%d", Cout); return SMB_EINVAL; }
   int n_tile = cand[nc - 1];
+  const char* envt = getenv("SMB_CONV_MIN_TILES");
+  const long min_tiles = envt ? atol(envt) : g_min_tiles;
   for (int i = 0; i < nc; ++i)
-    if ((long)p.tiles_m * cdiv(Cout, cand[i]) >= 120) { n_tile = cand[i]; break; }
+    if ((long)p.tiles_m * cdiv(Cout, cand[i]) >= min_tiles) { n_tile = cand[i]; break; }
   p.n_tile = n_tile;
   p.n_tiles_n = cdiv(Cout, n_tile);
   p.num_acc = (2 * n_tile <= 512) ? 2 : 1;
@@ -891,7 +900,10 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   int rc = encode_map(&p.bmap, const_cast<void*>(weight), 2, dims, strides, box);
   if (rc) return rc;
   const int units = cdiv(p.tiles_m, cluster) * p.n_tiles_n;
-  const int max_clusters = (cluster == 4 ? 132 : num_sms()) / cluster;
+  const char* envc = getenv("SMB_CONV_MAX_CTAS");            // experiments: leave SMs free for a concurrent stream
+  int sm_cap = num_sms();
+  if (envc && atoi(envc) > 0 && atoi(envc) < sm_cap) sm_cap = atoi(envc);
+  const int max_clusters = (cluster == 4 && sm_cap > 132 ? 132 : sm_cap) / cluster;
   const int clusters = units < max_clusters ? units : max_clusters;
   pl->grid = clusters * cluster;
   return SMB_OK;

@@ -179,6 +179,7 @@ __global__ void deform_im2col_kernel(const __half* __restrict__ x, const float* 
 // -------------------------------------------------------------------------------------------- max pool
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ x, __half* __restrict__ y, int N, int H, int W, int C, int Ho,
                                     int Wo) {
+  pdl_wait();
   const int vecs = C >> 3;
   const long long total = (long long)N * Ho * Wo * vecs;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
@@ -213,6 +214,7 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ x, __half* __rest
 //   src = max((dst + 0.5) / factor - 0.5, 0); i0 = (int)src; i1 = i0 + (i0 < in-1); l1 = src - i0
 __global__ void upsample_bilinear_kernel(const __half* __restrict__ x, int in_pitch, __half* __restrict__ y, int out_pitch,
                                          int out_choff, int N, int H, int W, int C, int factor, int relu) {
+  pdl_wait();
   const int vecs = C >> 3;
   const int Ho = H * factor, Wo = W * factor;
   const float rs = 1.0f / (float)factor;
@@ -246,6 +248,7 @@ __global__ void upsample_bilinear_kernel(const __half* __restrict__ x, int in_pi
 // plain strided copy of a channel block (level 0 of the prototype concat: torch.cat is a copy in the reference)
 __global__ void copy_channels_kernel(const __half* __restrict__ x, int in_pitch, __half* __restrict__ y, int out_pitch,
                                      int out_choff, long long npix, int C, int relu) {
+  pdl_wait();
   const int vecs = C >> 3;
   const long long total = npix * vecs;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
@@ -265,6 +268,7 @@ __global__ void copy_channels_kernel(const __half* __restrict__ x, int in_pitch,
 // --------------------------------------------------------------------------------------- image -> NHWC8
 // img [N,3,H,W] fp32 -> out [N, H+6, W+8, 8] fp16, pixel (y,x) at (y+3, x+3), zeros elsewhere / in ch 3..7.
 __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, __half* __restrict__ out, int N, int H, int W) {
+  pdl_wait();
   const int Hp = H + 6, Wp = W + 8;
   const long long total = (long long)N * Hp * Wp;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
@@ -306,6 +310,7 @@ __device__ __forceinline__ int find_level(const MultiDesc& d, long long t) {
 // GroupNorm(32) + ReLU in place; a[l] = x (fp16 [n_img*hw, C]), b[l] = stats (int64 fixed point).  C/32 % 8 == 0.
 __global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, int relu) {
+  pdl_wait();
   const int vecs = C >> 3;
   const int cpg = C / 32;
   const long long total = d.start[d.num];
@@ -340,6 +345,7 @@ __global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, 
 
 // offsets for all levels: a[l] = raw fcos_reg (fp32, pitch bbox_pitch), c[l] = offsets fp32 [hw, n_off], scale[l] = Scale_l
 __global__ void offset_conv_multi_kernel(MultiDesc d, int bbox_pitch, const float* __restrict__ w, int n_off) {
+  pdl_wait();
   const long long total = d.start[d.num];
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
     const int l = find_level(d, t);
@@ -358,6 +364,7 @@ __global__ void offset_conv_multi_kernel(MultiDesc d, int bbox_pitch, const floa
 // work item = one pixel handled by one warp: all 9 taps x 4 bilinear corners are independent 16-byte loads (36 in
 // flight per lane), the offsets of a pixel are read once, index math is 32-bit.
 __global__ void __launch_bounds__(256) deform_im2col_multi_kernel(MultiDesc d, int off_pitch, int C, int dg) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int total = (int)d.start[d.num];          // pixels over all levels (items_per_pixel == 1)
@@ -470,7 +477,8 @@ extern "C" int smb_maxpool3x3s2(const void* x, void* y, int N, int H, int W, int
   SMB_CHECK_ARG(x && y && C % 8 == 0, "smb_maxpool3x3s2: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, N, H, W, C, Ho, Wo);
+  SMB_CUDA_OK(launch_pdl(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x,
+                         (__half*)y, N, H, W, C, Ho, Wo));
   SMB_LAUNCH_OK("maxpool3x3s2_kernel");
   return SMB_OK;
 }
@@ -481,14 +489,14 @@ extern "C" int smb_upsample_bilinear(const void* x, int in_pitch, void* y, int o
                 "smb_upsample_bilinear: bad argument");
   if (factor == 1) {
     const long long npix = (long long)N * H * W;
-    copy_channels_kernel<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, in_pitch, (__half*)y,
-                                                                                          out_pitch, out_choff, npix, C, relu);
+    SMB_CUDA_OK(launch_pdl(copy_channels_kernel, dim3(grid_for(npix * (C / 8), 256)), dim3(256), 0, (cudaStream_t)stream,
+                           (const __half*)x, in_pitch, (__half*)y, out_pitch, out_choff, npix, C, relu));
     SMB_LAUNCH_OK("copy_channels_kernel");
     return SMB_OK;
   }
   const long long total = (long long)N * H * factor * W * factor * (C / 8);
-  upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, in_pitch, (__half*)y,
-                                                                                   out_pitch, out_choff, N, H, W, C, factor, relu);
+  SMB_CUDA_OK(launch_pdl(upsample_bilinear_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x,
+                         in_pitch, (__half*)y, out_pitch, out_choff, N, H, W, C, factor, relu));
   SMB_LAUNCH_OK("upsample_bilinear_kernel");
   return SMB_OK;
 }
@@ -496,7 +504,8 @@ extern "C" int smb_upsample_bilinear(const void* x, int in_pitch, void* y, int o
 extern "C" int smb_image_to_nhwc8(const float* img, void* out, int N, int H, int W, smb_stream_t stream) {
   SMB_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0, "smb_image_to_nhwc8: bad argument");
   const long long total = (long long)N * (H + 6) * (W + 8);
-  image_to_nhwc8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__half*)out, N, H, W);
+  SMB_CUDA_OK(launch_pdl(image_to_nhwc8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, img, (__half*)out, N,
+                         H, W));
   SMB_LAUNCH_OK("image_to_nhwc8_kernel");
   return SMB_OK;
 }
@@ -523,8 +532,8 @@ extern "C" int smb_groupnorm_relu_apply_multi(int num_levels, void* const* xs, c
   MultiDesc d;
   SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, C / 8, n_img) == 0, "smb_groupnorm_relu_apply_multi: bad levels");
   for (int l = 0; l < num_levels; ++l) { d.c[l] = xs[l]; d.b[l] = stats[l]; d.a[l] = nullptr; d.scale[l] = 1.f; }
-  gn_apply_multi_kernel<<<grid_for(d.start[num_levels], 256), 256, 0, (cudaStream_t)stream>>>(d, n_img, C, pitch, gamma, beta, eps,
-                                                                                           relu);
+  SMB_CUDA_OK(launch_pdl(gn_apply_multi_kernel, dim3(grid_for(d.start[num_levels], 256)), dim3(256), 0, (cudaStream_t)stream, d, n_img, C,
+                         pitch, gamma, beta, eps, relu));
   SMB_LAUNCH_OK("gn_apply_multi_kernel");
   return SMB_OK;
 }
@@ -536,7 +545,8 @@ extern "C" int smb_offset_conv1x1_multi(int num_levels, const float* const* bbox
   MultiDesc d;
   SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, n_off, n_img) == 0, "smb_offset_conv1x1_multi: bad levels");
   for (int l = 0; l < num_levels; ++l) { d.a[l] = bboxes[l]; d.c[l] = offs[l]; d.b[l] = nullptr; d.scale[l] = scales[l]; }
-  offset_conv_multi_kernel<<<grid_for(d.start[num_levels], 256), 256, 0, (cudaStream_t)stream>>>(d, bbox_pitch, weight, n_off);
+  SMB_CUDA_OK(launch_pdl(offset_conv_multi_kernel, dim3(grid_for(d.start[num_levels], 256)), dim3(256), 0, (cudaStream_t)stream, d,
+                         bbox_pitch, weight, n_off));
   SMB_LAUNCH_OK("offset_conv_multi_kernel");
   return SMB_OK;
 }
@@ -550,8 +560,8 @@ extern "C" int smb_deform_im2col_multi(int num_levels, const void* const* xs, co
   MultiDesc d;
   SMB_CHECK_ARG(fill_multi(&d, num_levels, Hs, Ws, 1, n_img) == 0, "smb_deform_im2col_multi: bad levels");
   for (int l = 0; l < num_levels; ++l) { d.a[l] = xs[l]; d.b[l] = offs[l]; d.c[l] = cols[l]; d.scale[l] = 1.f; }
-  deform_im2col_multi_kernel<<<grid_for(d.start[num_levels] * 32, 256), 256, 0, (cudaStream_t)stream>>>(d, off_pitch, C,
-                                                                                                    deformable_groups);
+  SMB_CUDA_OK(launch_pdl(deform_im2col_multi_kernel, dim3(grid_for(d.start[num_levels] * 32, 256)), dim3(256), 0, (cudaStream_t)stream,
+                         d, off_pitch, C, deformable_groups));
   SMB_LAUNCH_OK("deform_im2col_multi_kernel");
   return SMB_OK;
 }

@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(NT) mc_prepare_kernel(const float* __restrict_
                                                         int* __restrict__ w_cidx, float* __restrict__ w_cscore,
                                                         unsigned long long* __restrict__ w_keys, float4* __restrict__ w_sbox,
                                                         int* __restrict__ w_m) {
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   McPrepSmem& S = *reinterpret_cast<McPrepSmem*>(smem_raw);
   const int c = blockIdx.x;
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(NT) mc_prepare_kernel(const float* __restrict_
 __global__ void __launch_bounds__(64) mc_mask_kernel(const float4* __restrict__ w_sbox, const int* __restrict__ w_m, int n, int C,
                                                      int nbmax, float iou_thr, int cmp_ge,
                                                      unsigned long long* __restrict__ mask) {
+  pdl_wait();
   __shared__ int s_pref[1025];
   __shared__ float4 s_col[64];
   __shared__ int s_tile[3];
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(NT) mc_sweep_kernel(const unsigned long long* 
                                                       const int* __restrict__ w_cidx, const float* __restrict__ w_cscore,
                                                       const int* __restrict__ w_m, int n, int nbmax, int* __restrict__ ws_idx,
                                                       float* __restrict__ ws_score, int* __restrict__ ws_count) {
+  pdl_wait();
   __shared__ McSweepSmem S;
   const int c = blockIdx.x;
   const int m = w_m[c];
@@ -437,6 +440,7 @@ __global__ void __launch_bounds__(NT) finalize_kernel(const float* __restrict__ 
                                                       int* __restrict__ gval, float* __restrict__ det_out,
                                                       long long* __restrict__ label_out,
                                                       long long* __restrict__ idx_out, int* __restrict__ count_out) {
+  pdl_wait();
   __shared__ int s_off[1025];
   __shared__ int s_warp[33];
   __shared__ unsigned s_hist[256];
@@ -607,6 +611,7 @@ struct Levels {
 
 // s[loc] = max_c(sigmoid(cls)*sigmoid(ctr)) = sigmoid(max_c cls) * sigmoid(ctr)   (sipmask_head.py:572)
 __global__ void level_score_kernel(Levels L, int C, float* __restrict__ s) {
+  pdl_wait();
   const int total = L.loc_off[L.num];
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -629,6 +634,7 @@ __global__ void level_score_kernel(Levels L, int C, float* __restrict__ s) {
 // one CTA per level: selected location indices (descending score, ties -> lower index)
 __global__ void __launch_bounds__(NT) level_topk_kernel(Levels L, int nms_pre, const float* __restrict__ s,
                                                         int* __restrict__ sel) {
+  pdl_wait();
   __shared__ unsigned s_hist[256];
   __shared__ unsigned long long s_sel[1024];
   __shared__ int s_nsel;
@@ -675,6 +681,7 @@ __global__ void gather_decode_kernel(Levels L, int C, int img_h, int img_w, floa
                                      int has_scale, const int* __restrict__ sel, float* __restrict__ cand_boxes,
                                      float* __restrict__ cand_scores, float* __restrict__ cand_ctr,
                                      int* __restrict__ cand_loc) {
+  pdl_wait();
   const int total = L.cand_off[L.num];
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -708,6 +715,7 @@ __global__ void gather_decode_kernel(Levels L, int C, int img_h, int img_w, floa
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, int src_pitch, const long long* __restrict__ idx,
                                    const int* __restrict__ count, int max_rows, int row_elems, float* __restrict__ dst) {
+  pdl_wait();
   const int total = max_rows * row_elems;
   const int cnt = *count;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -811,21 +819,21 @@ extern "C" int smb_multiclass_nms(const float* boxes, const float* scores, const
     SMB_CUDA_OK(cudaMemsetAsync(ws_count, 0, sizeof(int) * (num_classes + 1), st));
   } else {
     const int nbmax = (n + 63) / 64;
-    mc_prepare_kernel<<<num_classes, NT, sizeof(McPrepSmem), st>>>(boxes, scores, ctr, n, num_classes, score_thr, (int*)(ws + w.cidx),
+    SMB_CUDA_OK(launch_pdl(mc_prepare_kernel, dim3(num_classes), dim3(NT), sizeof(McPrepSmem), st, boxes, scores, ctr, n, num_classes, score_thr, (int*)(ws + w.cidx),
                                                                    (float*)(ws + w.cscore), (unsigned long long*)(ws + w.keys),
-                                                                   (float4*)(ws + w.sbox), (int*)(ws + w.m));
+                                                                   (float4*)(ws + w.sbox), (int*)(ws + w.m)));
     SMB_LAUNCH_OK("mc_prepare_kernel");
-    mc_mask_kernel<<<148 * 16, 64, 0, st>>>((const float4*)(ws + w.sbox), (const int*)(ws + w.m), n, num_classes, nbmax, iou_thr,
-                                            cmp_ge, (unsigned long long*)(ws + w.mask));
+    SMB_CUDA_OK(launch_pdl(mc_mask_kernel, dim3(148 * 16), dim3(64), 0, st, (const float4*)(ws + w.sbox), (const int*)(ws + w.m), n, num_classes, nbmax, iou_thr,
+                                            cmp_ge, (unsigned long long*)(ws + w.mask)));
     SMB_LAUNCH_OK("mc_mask_kernel");
-    mc_sweep_kernel<<<num_classes, NT, 0, st>>>((const unsigned long long*)(ws + w.mask), (const unsigned long long*)(ws + w.keys),
+    SMB_CUDA_OK(launch_pdl(mc_sweep_kernel, dim3(num_classes), dim3(NT), 0, st, (const unsigned long long*)(ws + w.mask), (const unsigned long long*)(ws + w.keys),
                                                 (const int*)(ws + w.cidx), (const float*)(ws + w.cscore), (const int*)(ws + w.m), n,
-                                                nbmax, (int*)(ws + w.idx), (float*)(ws + w.score), ws_count);
+                                                nbmax, (int*)(ws + w.idx), (float*)(ws + w.score), ws_count));
     SMB_LAUNCH_OK("mc_sweep_kernel");
   }
-  finalize_kernel<<<1, NT, 0, st>>>(boxes, n, num_classes, max_num, 0, (const int*)(ws + w.idx), (const float*)(ws + w.score),
+  SMB_CUDA_OK(launch_pdl(finalize_kernel, dim3(1), dim3(NT), 0, st, boxes, n, num_classes, max_num, 0, (const int*)(ws + w.idx), (const float*)(ws + w.score),
                                     ws_count, nn, (unsigned long long*)(ws + w.gkey), (int*)(ws + w.gval), det_out,
-                                    (long long*)label_out, (long long*)idx_out, count_out);
+                                    (long long*)label_out, (long long*)idx_out, count_out));
   SMB_LAUNCH_OK("finalize_kernel");
   return SMB_OK;
 }
@@ -858,9 +866,9 @@ extern "C" int smb_fast_nms(const float* boxes, const float* scores, const float
   fast_nms_class_kernel<<<num_classes, NT, sizeof(FastSmem), st>>>(boxes, scores, ctr, n, num_classes, score_thr, iou_thr, top_k,
                                                                    (int*)(ws + o_idx), (float*)(ws + o_score), (int*)(ws + o_count));
   SMB_LAUNCH_OK("fast_nms_class_kernel");
-  finalize_kernel<<<1, NT, 0, st>>>(boxes, n, num_classes, max_num, 1, (const int*)(ws + o_idx), (const float*)(ws + o_score),
+  SMB_CUDA_OK(launch_pdl(finalize_kernel, dim3(1), dim3(NT), 0, st, boxes, n, num_classes, max_num, 1, (const int*)(ws + o_idx), (const float*)(ws + o_score),
                                     (const int*)(ws + o_count), top_k, (unsigned long long*)(ws + o_gkey), (int*)(ws + o_gval),
-                                    det_out, (long long*)label_out, (long long*)idx_out, count_out);
+                                    det_out, (long long*)label_out, (long long*)idx_out, count_out));
   SMB_LAUNCH_OK("finalize_kernel");
   return SMB_OK;
 }
@@ -889,16 +897,16 @@ extern "C" int smb_decode_topk(int num_levels, const smb_level_t* host_levels, i
   float* s = (float*)workspace;
   int* sel = (int*)((char*)workspace + s_bytes);
   const int total = L.loc_off[L.num];
-  level_score_kernel<<<min(cdiv(total, 8), 148 * 8), 256, 0, st>>>(L, num_classes, s);
+  SMB_CUDA_OK(launch_pdl(level_score_kernel, dim3(min(cdiv(total, 8), 148 * 8)), dim3(256), 0, st, L, num_classes, s));
   SMB_LAUNCH_OK("level_score_kernel");
-  level_topk_kernel<<<num_levels, NT, 0, st>>>(L, nms_pre, s, sel);
+  SMB_CUDA_OK(launch_pdl(level_topk_kernel, dim3(num_levels), dim3(NT), 0, st, L, nms_pre, s, sel));
   SMB_LAUNCH_OK("level_topk_kernel");
   const int ncand = L.cand_off[L.num];
   const float i0 = host_scale4 ? host_scale4[0] : 1.f, i1 = host_scale4 ? host_scale4[1] : 1.f;
   const float i2 = host_scale4 ? host_scale4[2] : 1.f, i3 = host_scale4 ? host_scale4[3] : 1.f;
-  gather_decode_kernel<<<min(cdiv(ncand, 8), 148 * 8), 256, 0, st>>>(L, num_classes, img_h, img_w, i0, i1, i2, i3,
+  SMB_CUDA_OK(launch_pdl(gather_decode_kernel, dim3(min(cdiv(ncand, 8), 148 * 8)), dim3(256), 0, st, L, num_classes, img_h, img_w, i0, i1, i2, i3,
                                                                     host_scale4 ? 1 : 0, sel, cand_boxes, cand_scores,
-                                                                    cand_ctr, cand_loc);
+                                                                    cand_ctr, cand_loc));
   SMB_LAUNCH_OK("gather_decode_kernel");
   return SMB_OK;
 }
@@ -906,8 +914,8 @@ extern "C" int smb_decode_topk(int num_levels, const smb_level_t* host_levels, i
 extern "C" int smb_gather_rows_f32(const float* src, int src_pitch, const int64_t* idx, const int* count_dev, int max_rows,
                                    int row_elems, float* dst, smb_stream_t stream) {
   SMB_CHECK_ARG(src && idx && count_dev && dst && max_rows > 0 && row_elems > 0, "smb_gather_rows_f32: bad argument");
-  gather_rows_kernel<<<cdiv(max_rows * row_elems, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, (const long long*)idx,
-                                                                                         count_dev, max_rows, row_elems, dst);
+  SMB_CUDA_OK(launch_pdl(gather_rows_kernel, dim3(cdiv(max_rows * row_elems, 256)), dim3(256), 0, (cudaStream_t)stream, src, src_pitch, (const long long*)idx,
+                                                                                         count_dev, max_rows, row_elems, dst));
   SMB_LAUNCH_OK("gather_rows_kernel");
   return SMB_OK;
 }

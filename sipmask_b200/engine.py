@@ -26,13 +26,16 @@ class SipMaskEngine(object):
     def __init__(self, state_dict, img_hw, batch=1, depth=50, stacked_convs=4, gn=True, ssd_flag=False, num_classes=81,
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
                  mask_thr=0.4, use_graph=True, pos_dtype=torch.float32, head_only=False, feat_sizes=None, in_channels=256,
-                 fcos=False, prefix_head='bbox_head.', build_postproc=True, two_streams=True):
+                 fcos=False, prefix_head='bbox_head.', build_postproc=True, two_streams=True, share_weights=None,
+                 max_ctas=None, head_max_ctas=None):
         L.check(L.lib().smb_check_device(), 'smb_check_device')
         self.dev = torch.device(device)
         self.N, (self.H, self.W) = batch, img_hw
         self.head_only, self.feat_sizes, self.in_channels, self.fcos = head_only, feat_sizes, in_channels, fcos
         self.hp, self.build_post = prefix_head, build_postproc
         self.two_streams = two_streams
+        self.fork_branches = two_streams and os.environ.get('SMB_FORK_BRANCHES', '1') != '0'
+        self.fork_from_layer = int(os.environ.get('SMB_FORK_FROM_LAYER', '1'))      # 0-based residual stage index
         assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
         assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
         self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
@@ -50,11 +53,15 @@ class SipMaskEngine(object):
         self.op_names = []
         self.op_tags = []        # 0 = main stream, 1 = side stream, 'fork' / 'join' = stream dependencies
         self._tag = 0
-        self._max_ctas = None
+        self._max_ctas = max_ctas
         self.side_stream = None
         self.n_launch = 0
         self._keep = []
-        self._wcache = {}
+        # packed weights; `share_weights=<engine>` makes several engines (images in flight) read ONE copy, so the weights'
+        # L2 footprint does not grow with the number of images in flight
+        self._wcache = share_weights._wcache if share_weights is not None else {}
+        self.max_ctas = max_ctas                   # persistent-grid cap of every conv (None: all SMs)
+        self.head_max_ctas = head_max_ctas         # cap inside the two-stream head section (None: env / 100)
         self.conv_plans = []
         self.conv_meta = []
         self.conv_flops = 0.0
@@ -132,7 +139,8 @@ class SipMaskEngine(object):
         # ---- stem
         img8 = self._t(N, H + 6, W + 8, 8)
         self._add(lambda: C.image_to_nhwc8(self.img, img8), name='image_to_nhwc8')
-        wk, b = C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'), device=self.dev)
+        wk, b = self._once('stem', lambda: C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'),
+                                                              device=self.dev))
         s1 = self._t(N, H // 2, W // 2, 64)
         stem = C.StemPlan(img8, wk, b, s1, N, H, W)
         self._keep += [stem, wk, b]
@@ -149,9 +157,19 @@ class SipMaskEngine(object):
             for j in range(nb):
                 p = 'backbone.layer%d.%d.' % (i + 1, j)
                 stride = 2 if (j == 0 and i > 0) else 1
+                # the projection shortcut only depends on the block input: it runs on the side stream next to conv1/conv2
+                # (layers 2-4 are short latency-bound launches that leave most SMs idle)
+                side = self.fork_branches and j == 0 and i >= self.fork_from_layer
+                if side:
+                    self._marker('fork')
+                    self._tag = 1
+                    idn = self._conv(x, p + 'downsample.0.weight', 1, stride, relu=False, bn=p + 'downsample.1')
+                    self._tag = 0
                 t1 = self._conv(x, p + 'conv1.weight', 1, stride, relu=True, bn=p + 'bn1')
                 t2 = self._conv(t1, p + 'conv2.weight', 3, 1, relu=True, bn=p + 'bn2')
-                if j == 0:
+                if side:
+                    self._marker('join')
+                elif j == 0:
                     idn = self._conv(x, p + 'downsample.0.weight', 1, stride, relu=False, bn=p + 'downsample.1')
                 else:
                     idn = x
@@ -160,19 +178,37 @@ class SipMaskEngine(object):
         c3, c4, c5 = feats[1], feats[2], feats[3]
         # ---- FPN (fpn.py:138-178): laterals top-down with the nearest-upsample add fused into the epilogue
         lat5 = self._conv(c5, 'neck.lateral_convs.2.conv.weight', 1, bias_key='neck.lateral_convs.2.conv.bias')
+        if self.fork_branches:
+            # P5 -> P6 -> P7 is a chain of tiny convolutions (9 / 3 / 1 M-tiles): side stream, next to the P4 / P3 laterals
+            self._marker('fork')
+            self._tag = 1
+            p5, p6, p7 = self._fpn_top(lat5)
+            self._tag = 0
         lat4 = self._conv(c4, 'neck.lateral_convs.1.conv.weight', 1, bias_key='neck.lateral_convs.1.conv.bias',
                           residual=lat5, residual_upsample=True)
         lat3 = self._conv(c3, 'neck.lateral_convs.0.conv.weight', 1, bias_key='neck.lateral_convs.0.conv.bias',
                           residual=lat4, residual_upsample=True)
         p3 = self._conv(lat3, 'neck.fpn_convs.0.conv.weight', 3, bias_key='neck.fpn_convs.0.conv.bias')
         p4 = self._conv(lat4, 'neck.fpn_convs.1.conv.weight', 3, bias_key='neck.fpn_convs.1.conv.bias')
+        if self.fork_branches:
+            self._marker('join')
+        else:
+            p5, p6, p7 = self._fpn_top(lat5)
+        self.fpn_outs = [p3, p4, p5, p6, p7]
+        self._build_head(self.fpn_outs)
+
+    def _fpn_top(self, lat5):
         p5 = self._conv(lat5, 'neck.fpn_convs.2.conv.weight', 3, bias_key='neck.fpn_convs.2.conv.bias')
         p6 = self._conv(p5, 'neck.fpn_convs.3.conv.weight', 3, 2, bias_key='neck.fpn_convs.3.conv.bias')
         p6r = self._t(*p6.shape)
         self._add(lambda: C.upsample_bilinear(p6, 1, out=p6r, relu=True), name='relu_copy')   # F.relu(outs[-1]) (fpn.py:175)
         p7 = self._conv(p6r, 'neck.fpn_convs.4.conv.weight', 3, 2, bias_key='neck.fpn_convs.4.conv.bias')
-        self.fpn_outs = [p3, p4, p5, p6, p7]
-        self._build_head(self.fpn_outs)
+        return p5, p6, p7
+
+    def _once(self, key, fn):
+        if key not in self._wcache:
+            self._wcache[key] = fn()
+        return self._wcache[key]
 
     def _packed(self, wkey, bias_key=None, cout_pad=None):
         ck = (wkey, None, bias_key, cout_pad)
@@ -230,14 +266,16 @@ class SipMaskEngine(object):
         CCp = (CC + 15) // 16 * 16
         w_cls = torch.cat([self._w(hp + 'fcos_cls.weight'), self._w(hp + 'sip_cof.weight')], 0)
         b_cls = torch.cat([self._w(hp + 'fcos_cls.bias'), self._w(hp + 'sip_cof.bias')], 0)
-        wk_cls, _ = C.pack_weight(w_cls, cout_pad=CCp, device=self.dev)
-        b_cls = torch.cat([b_cls, b_cls.new_zeros(CCp - CC)]).to(self.dev)
+        wk_cls = self._once('head.wk_cls', lambda: C.pack_weight(w_cls, cout_pad=CCp, device=self.dev)[0])
+        b_cls = self._once('head.b_cls', lambda: torch.cat([b_cls, b_cls.new_zeros(CCp - CC)]).to(self.dev))
         w_reg = torch.cat([self._w(hp + 'fcos_reg.weight'), self._w(hp + 'fcos_centerness.weight')], 0)
         b_reg = torch.cat([self._w(hp + 'fcos_reg.bias'), self._w(hp + 'fcos_centerness.bias')], 0)
-        wk_reg, _ = C.pack_weight(w_reg, cout_pad=16, device=self.dev)
-        b_reg = torch.cat([b_reg, b_reg.new_zeros(16 - 5)]).to(self.dev)
-        wk_dcn, _ = C.pack_weight(self._w(hp + 'feat_align.conv_adaption.weight'), device=self.dev)
-        w_off = self._w(hp + 'feat_align.conv_offset.weight').view(72, 4).contiguous().to(self.dev)
+        wk_reg = self._once('head.wk_reg', lambda: C.pack_weight(w_reg, cout_pad=16, device=self.dev)[0])
+        b_reg = self._once('head.b_reg', lambda: torch.cat([b_reg, b_reg.new_zeros(16 - 5)]).to(self.dev))
+        wk_dcn = self._once('head.wk_dcn', lambda: C.pack_weight(self._w(hp + 'feat_align.conv_adaption.weight'),
+                                                                   device=self.dev)[0])
+        w_off = self._once('head.w_off',
+                           lambda: self._w(hp + 'feat_align.conv_offset.weight').view(72, 4).contiguous().to(self.dev))
         self._keep += [wk_cls, b_cls, wk_reg, b_reg, wk_dcn, w_off]
         self.scales = [float(self._w(hp + 'scales.%d.scale' % i)) for i in range(nl)]
         # level-concatenated fp32 head outputs (channel-last): [tot, 80+128] and [tot, 16 = 4 reg | 1 ctr | pad]
@@ -257,7 +295,10 @@ class SipMaskEngine(object):
         two = self.two_streams
         if two:
             self._marker('fork')
-            self._max_ctas = int(os.environ.get('SMB_HEAD_MAX_CTAS', '100')) or None
+            cap = self.head_max_ctas if self.head_max_ctas is not None else int(os.environ.get('SMB_HEAD_MAX_CTAS', '100'))
+            if self.max_ctas:
+                cap = min(cap, self.max_ctas) if cap else self.max_ctas
+            self._max_ctas = cap or None
         self._tag = 0
         for i in range(self.stacked - 1):
             cls_feats = self._tower_conv(cls_feats, hp + 'cls_convs.%d.conv.weight' % i, hp + 'cls_convs.%d.gn' % i,
@@ -305,7 +346,7 @@ class SipMaskEngine(object):
         if two:
             self._marker('join')
         self._tag = 0
-        self._max_ctas = None
+        self._max_ctas = self.max_ctas
         if self.build_post:
             self._build_postproc()
 
