@@ -401,7 +401,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--in-flight', type=int, default=int(os.environ.get('SMB_IN_FLIGHT', '4')),
+    ap.add_argument('--in-flight', type=int, default=int(os.environ.get('SMB_IN_FLIGHT', '6')),
                     help='images in flight per GPU (independent batch-1 forwards on separate streams); 1 = strictly serial')
     args = ap.parse_args()
     if args.impl == 'reference':

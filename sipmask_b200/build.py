@@ -10,6 +10,7 @@ LIB = os.path.join(HERE, 'lib', 'libsipmask_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+FLAGS += os.environ.get('SMB_NVCC_EXTRA', '').split()       # e.g. -DSMB_TS_FINE for tools/conv_timeline.py (then build -f)
 
 
 def sources():

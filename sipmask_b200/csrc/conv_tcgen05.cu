@@ -28,7 +28,9 @@ namespace smb {
 constexpr int kMaxTaps = 9;
 constexpr int kMaxMaps = 8;
 constexpr int kMaxLevels = 5;
-constexpr int kThreads = 320;          // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue (2 per TMEM lane quadrant)
+constexpr int kThreads = 352;          // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue (2 per TMEM lane quadrant),
+                                       // warp 10 = staging ring: TMA stores of finished chunks + residual prefetch
+constexpr int kStoreWarp = 10;
 constexpr int kEpiThreads = 256;
 constexpr int kABytes = 128 * 64 * 2;   // one A stage: 128 pixels x 64 channels fp16
 
@@ -61,6 +63,7 @@ struct ConvParams {
   int debug_mode;                 // profiling only (SMB_CONV_DEBUG): 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA only)
   int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
   int out_pitch; int out_f32; int out_tma; int res_tma;
+  int stage_slots;                // staging ring: n_tile/64 (one tile) or 2*n_tile/64 (two tiles) chunk buffers of 128 px x 64 ch
   const float* bias; float alpha;
   int res_pitch; int res_mode;
   int gn_group;                   // channels per GroupNorm group (8 or 16), 0 = no statistics
@@ -313,11 +316,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* rfull_bar = tempty_bar + 2;                               // [4] residual chunk landed (res_tma)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 4);
+  // staging ring (TMA-store epilogue): slot = chunk counter % stage_slots
+  uint64_t* rfull_bar = tempty_bar + 2;                               // [8] residual chunk landed in the slot (res_tma)
+  uint64_t* sfull_bar = rfull_bar + 8;                                // [8] the 8 epilogue warps have written the slot
+  uint64_t* sfree_bar = sfull_bar + 8;                                // [8] the slot's TMA store has been read out (no residual)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree_bar + 8);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);          // [2][256] double-buffered per tile
-  // n_tile/64 staging tiles of 128 px x 64 ch fp16 (128-byte swizzle).  The residual tile is TMA-loaded INTO them and each
-  // thread overwrites exactly the 64 bytes it read with its result, which is then TMA-stored: one buffer, no extra barrier.
+  // Ring of staging chunks, each 128 px x 64 ch fp16 (128-byte swizzle).  The residual chunk is TMA-loaded INTO a slot, each
+  // epilogue thread overwrites exactly the 64 bytes it read with its result, the store warp TMA-stores the slot and, once the
+  // store has been read out, requests the residual of the chunk that will use the slot next.
   uint8_t* s_stage = smem + (size_t)p.stages * (kABytes + b_bytes) + 4096;
 
   if (warp == 0 && lane == 0) {
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&rfull_bar[i], 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&sfull_bar[i], 8); mbar_init(&sfree_bar[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -454,6 +461,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (++acc == num_acc) { acc = 0; acc_ph ^= 1; }
       }
     }
+  } else if (warp == kStoreWarp) {
+    // ===================== staging-ring warp: TMA stores + residual prefetch =====================
+    if (p.out_tma) {
+      const int nch = p.n_tile >> 6, nslots = p.stage_slots;
+      const int my_tiles = cluster_id < total_units ? (total_units - cluster_id + num_clusters - 1) / num_clusters : 0;
+      const int total_chunks = my_tiles * nch;
+      // residual request for chunk g (tile g / nch of this CTA, 64-channel chunk g % nch) into slot g % nslots
+      auto request_residual = [&](int g) {
+        const int t = g / nch, c = g - t * nch;
+        const TileCoord tr = decode_tile(p, cluster_id + t * num_clusters, crank);
+        const int sl = g % nslots;
+        if (tr.active) {
+          mbar_expect_tx(&rfull_bar[sl], 16384);
+          tma_load_4d(s_stage + (size_t)sl * 16384, &p.rmap[tr.lvl], &rfull_bar[sl], tr.n0 + c * 64, tr.x0, tr.y0, tr.img);
+        } else {
+          mbar_arrive(&rfull_bar[sl]);
+        }
+      };
+      if (p.res_tma && elect_one()) {
+        for (int g = 0; g < nslots && g < total_chunks; ++g) request_residual(g);
+      }
+      __syncwarp();
+      int slot = 0, c = 0, t = 0;
+      uint32_t slot_ph = 0;
+      TileCoord tc = decode_tile(p, cluster_id, crank);
+      for (int g = 0; g < total_chunks; ++g) {
+        mbar_wait(&sfull_bar[slot], slot_ph);
+        if (elect_one()) {
+          if (tc.active && !(p.debug_mode & 8))
+            tma_store_4d(&p.omap[tc.lvl], s_stage + (size_t)slot * 16384, tc.n0 + c * 64, tc.x0, tc.y0, tc.img);
+          bulk_commit();
+          // release a slot once its store has been read out: the previous chunk's (this chunk's own store keeps running),
+          // or this chunk's at once when the ring has a single slot
+          int h = -1;
+          if (nslots == 1) { bulk_wait_read<0>(); h = g; }
+          else if (g >= 1) { bulk_wait_read<1>(); h = g - 1; }
+          if (h >= 0) {
+            if (p.res_tma) {
+              if (h + nslots < total_chunks) { fence_async_smem(); request_residual(h + nslots); }
+            } else {
+              mbar_arrive(&sfree_bar[h % nslots]);
+            }
+          }
+        }
+        __syncwarp();
+        if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
+        if (++c == nch) {
+          c = 0;
+          ++t;
+          if (g + 1 < total_chunks) tc = decode_tile(p, cluster_id + t * num_clusters, crank);
+        }
+      }
+      if (elect_one()) bulk_wait_read<0>();          // staging slots must outlive their TMA stores
+      __syncwarp();
+    }
   } else {
     // ===================== epilogue warps (2..9) =====================
     // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); the pair splits the tile's
@@ -468,9 +530,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t lt = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
+    int slot = 0;                                    // staging ring position of the next chunk, and its use parity
+    uint32_t slot_ph = 0;
+    const int nslots = p.stage_slots;
     for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
       const TileCoord tc = decode_tile(p, unit, crank);
       const LevelDesc& L = p.lv[tc.lvl];
+#define TS2(slot) do { if (lt == 1 && warp == 2) TS(slot); } while (0)
+#ifdef SMB_TS_FINE                                   // per-chunk stamps (tools/conv_timeline.py; build with -DSMB_TS_FINE)
+#define TS3(slot) TS2(slot)
+#else
+#define TS3(slot) do { } while (0)
+#endif
+      TS2(16);
       const int iy = row / L.BW, ix = row - iy * L.BW;
       const int x = tc.x0 + ix, y = tc.y0 + iy, n0 = tc.n0;
       const bool valid = tc.active && (x < L.W_out) && (y < L.H_out);
@@ -496,25 +568,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (n0 + c_begin + j * 8 + 8 <= p.Cout && c_begin + j * 8 < c_end)
             rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c_begin + j * 8));
       }
-      if (p.out_tma && et == 0) {
-        bulk_wait_read<0>();                         // the previous tile's TMA stores have finished reading the staging tiles
-        if (p.res_tma && tc.active) {
-          // this tile's residual (128 px x n_tile ch) arrives by TMA while the main loop is still running
-          fence_async_smem();
-          const int nchr = p.n_tile >> 6;
-          for (int c = 0; c < nchr; ++c) {
-            mbar_expect_tx(&rfull_bar[c], 16384);
-            tma_load_4d(s_stage + (size_t)c * 16384, &p.rmap[tc.lvl], &rfull_bar[c], n0 + c * 64, tc.x0, tc.y0, tc.img);
-          }
-        }
-      }
+      TS2(17);
       // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile)
       float* sb = s_bias + (lt & 1) * 256;
       if (p.bias) {
         for (int c = et; c < p.n_tile; c += kEpiThreads) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      TS2(18);
       mbar_wait(&tfull_bar[acc], acc_ph);
+      TS2(19);
       if (lt == 0 && warp == 2 && lane == 0) TS(9);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
@@ -542,17 +605,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
             }
-            if (res_smem) {
-              const uint8_t* sbuf_c = s_stage + (size_t)c64 * 16384;
-              mbar_wait(&rfull_bar[c64], lt & 1);
+            uint8_t* sbuf = s_stage + (size_t)slot * 16384;
+            if (p.res_tma) {
+              // the slot's previous store has been read out AND this chunk's residual has landed in it (inactive tiles:
+              // the store warp arrives without a load)
+              mbar_wait(&rfull_bar[slot], slot_ph);
+              if (res_smem) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                rc[j] = *reinterpret_cast<const uint4*>(sbuf_c + row * 128 + (((col_half * 4 + j) ^ (row & 7)) * 16));
+                for (int j = 0; j < 4; ++j)
+                  rc[j] = *reinterpret_cast<const uint4*>(sbuf + row * 128 + (((col_half * 4 + j) ^ (row & 7)) * 16));
+              }
+            } else {
+              mbar_wait(&sfree_bar[slot], slot_ph ^ 1);       // the slot's previous TMA store has been read out
             }
+            TS3(20 + 4 * c64);
             uint32_t v[32];
             tmem_ld32(t_base + (uint32_t)cc, v);
-            uint8_t* sbuf = s_stage + (size_t)c64 * 16384;
             tmem_ld_wait();
+            TS3(21 + 4 * c64);
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -593,6 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
+            if (c64 == 1) TS3(40);
             // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -603,12 +674,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               const int chunk = (col_half * 4 + j) ^ (row & 7);
               *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = o;
             }
-            fence_async_smem();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0 && tc.active && !(p.debug_mode & 8)) {
-              tma_store_4d(&p.omap[tc.lvl], sbuf, n0 + c64 * 64, tc.x0, tc.y0, tc.img);
-              bulk_commit();
-            }
+            if (c64 == 1) TS3(41);
+            fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
+            if (c64 == 1) TS3(42);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sfull_bar[slot]);  // 8 warps -> the store warp ships the slot
+            TS3(22 + 4 * c64);
+            if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) rc[j] = rn[j];
           }
@@ -742,6 +814,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
       }
       if (lt == 0 && warp == 2 && lane == 0) TS(10);
+      TS2(36);
       // this warp has drained its share of the accumulator
       tc_fence_before();
       __syncwarp();
@@ -753,7 +826,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   }
 
-  if (threadIdx.x == 64 && p.out_tma) bulk_wait_read<0>();      // staging tiles must outlive their TMA stores
   if (threadIdx.x == 0) TS(11);
   tc_fence_before();
   if (p.cluster > 1) cluster_sync_all();             // no CTA may exit while peers can still multicast to / arrive on it
@@ -876,7 +948,21 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   const size_t stage = (size_t)kABytes + (size_t)(p.pair ? n_tile / 2 : n_tile) * 128;
   p.out_tma = (pl->omap_ok && !p.out_f32 && n_tile % 64 == 0 && !getenv("SMB_CONV_NO_TMA_STORE")) ? 1 : 0;
   p.res_tma = (p.out_tma && p.res_mode == 1 && pl->rmap_ok && !getenv("SMB_CONV_NO_TMA_RES")) ? 1 : 0;
-  const size_t stage_out = p.out_tma ? (size_t)(n_tile / 64) * 16384 : 0;      // result / residual staging tiles
+  size_t stage_out = p.out_tma ? (size_t)(n_tile / 64) * 16384 : 0;      // result / residual staging tiles
+  // Staging ring of the TMA-store epilogue: one tile's worth of 64-channel chunks, or two when shared memory allows it
+  // without starving the operand pipeline (short-K tiles - the bottleneck output / shortcut 1x1 convs - are epilogue-bound:
+  // with two tiles of slots the residual of the next tile lands and the stores of the previous tile drain meanwhile).
+  p.stage_slots = n_tile / 64;
+  {
+    const int kblocks = Ktotal / 64;
+    const char* envs = getenv("SMB_CONV_STAGE_SETS");
+    const int want2 = envs ? atoi(envs) == 2 : 1;
+    const int st2 = (int)((194 * 1024 - 2 * (long)stage_out) / (long)stage);
+    if (p.out_tma && want2 && 2 * stage_out <= 128 * 1024 && st2 >= (kblocks < 3 ? kblocks : 3)) {
+      p.stage_slots *= 2;
+      stage_out *= 2;
+    }
+  }
   const size_t budget = 194 * 1024 - stage_out;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;

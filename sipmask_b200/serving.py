@@ -19,12 +19,18 @@ from .engine import SipMaskEngine
 
 # tuning measured on B200 (profiles/r01_inflight_sweep.txt): grid cap / planner min_tiles per number of images in flight
 _TUNING = {1: dict(max_ctas=None, head_max_ctas=None, min_tiles=48)}
-_TUNING_N = dict(max_ctas=64, head_max_ctas=64, min_tiles=40)
+
+
+def _tuning(n):
+    if n in _TUNING:
+        return dict(_TUNING[n])
+    cap = 48 if n >= 6 else 64
+    return dict(max_ctas=cap, head_max_ctas=cap, min_tiles=16)
 
 
 def make_engines(state_dict, img_hw, in_flight=1, **kw):
     """n engines for n images in flight (weights shared, activations private)."""
-    tune = dict(_TUNING.get(in_flight, _TUNING_N))
+    tune = _tuning(in_flight)
     prev = C.set_min_tiles(kw.pop('min_tiles', tune.pop('min_tiles')))
     for k, v in tune.items():
         kw.setdefault(k, v)

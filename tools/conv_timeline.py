@@ -4,7 +4,7 @@ import sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-ts = torch.zeros(16, dtype=torch.int64, device='cuda')
+ts = torch.zeros(64, dtype=torch.int64, device='cuda')
 os.environ['SMB_CONV_TS'] = hex(ts.data_ptr())
 import bench  # noqa: E402
 from sipmask_b200 import synth  # noqa: E402
@@ -25,3 +25,11 @@ for i in [int(a) for a in sys.argv[1:]]:
     m = eng.conv_meta[i]
     print('plan %d %s M=%d N=%d K=%d' % (i, m['name'], m['M'], m['N'], m['K']))
     print('   ' + '  '.join('%s=%d' % (n, (t[j] - t[0]) if t[j] else -1) for j, n in enumerate(names)))
+    if t[16]:
+        e = lambda j: (t[j] - t[16]) if t[j] else -1
+        print('   tile#1 epilogue (warp 2, cycles from its loop top): prefetch/wait_read=%d bias-bar=%d tfull=%d' % (e(17), e(18), e(19)))
+        for c in range(4):
+            if t[20 + 4 * c]:
+                print('      chunk %d: slot+residual=%d tmem-ld=%d staged+arrived=%d' % (c, e(20 + 4 * c), e(21 + 4 * c),
+                                                                          e(22 + 4 * c)))
+        print('      tile end=%d   chunk 1 detail: math done=%d sts done=%d fence done=%d' % (e(36), e(40), e(41), e(42)))
