@@ -234,6 +234,46 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Explicit shared-window accesses.  In a cluster launch every generic->shared conversion costs an S2R SR_CgaCtaId (the
+// compiler re-derives the CTA's window each time); the epilogue keeps 32-bit shared addresses instead.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_A:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE_A;\n"
+      "bra WAIT_LOOP_A;\n"
+      "WAIT_DONE_A:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+// value the compiler must keep in a register (kernel parameters are otherwise re-read from the constant bank inside loops)
+__device__ __forceinline__ int opaque(int x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+// wait that carries a data dependency on the 16 destination registers of an earlier (prefetched) tcgen05.ld, so that no
+// consumer of v[] can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024>>4 |
@@ -494,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           bulk_commit();
           // release a slot once its store has been read out: the previous chunk's (this chunk's own store keeps running),
           // or this chunk's at once when the ring has a single slot
+          // (a deeper lag - more stores in flight - was measured slower: it delays the residual requests, r01 run 42)
           int h = -1;
           if (nslots == 1) { bulk_wait_read<0>(); h = g; }
           else if (g >= 1) { bulk_wait_read<1>(); h = g - 1; }
@@ -533,6 +574,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     int slot = 0;                                    // staging ring position of the next chunk, and its use parity
     uint32_t slot_ph = 0;
     const int nslots = p.stage_slots;
+    const bool single_n = p.n_tiles_n == 1;
+    // loop-invariant parameters and shared addresses of the chunk loop, pinned in registers
+    const int o_flags = opaque((p.bias ? 1 : 0) | (p.relu ? 2 : 0) | (p.res_tma ? 4 : 0) | (p.gn_group ? 8 : 0) |
+                               (p.alpha != 1.0f ? 16 : 0));
+    const int o_dbg = opaque(p.debug_mode);
+    const float o_alpha = __int_as_float(opaque(__float_as_int(p.alpha)));
+    const uint32_t stage_a = smem_u32(s_stage), bias_a = smem_u32(s_bias);
+    const uint32_t rfull_a = smem_u32(rfull_bar), sfull_a = smem_u32(sfull_bar), sfree_a = smem_u32(sfree_bar);
     for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
       const TileCoord tc = decode_tile(p, unit, crank);
       const LevelDesc& L = p.lv[tc.lvl];
@@ -569,12 +618,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c_begin + j * 8));
       }
       TS2(17);
-      // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile)
-      float* sb = s_bias + (lt & 1) * 256;
-      if (p.bias) {
-        for (int c = et; c < p.n_tile; c += kEpiThreads) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
+      // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile).  With a single N
+      // tile the slice never changes: staged once, before the first tile.
+      float* sb = s_bias + (single_n ? 0 : (lt & 1) * 256);
+      if (!single_n || lt == 0) {
+        if (p.bias) {
+          for (int c = et; c < p.n_tile; c += kEpiThreads) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       TS2(18);
       mbar_wait(&tfull_bar[acc], acc_ph);
       TS2(19);
@@ -586,9 +638,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         // All 8 warps work on the same 64-channel chunk (warp pair = two 32-channel halves of a lane quadrant); the
         // scattered per-thread 16-byte global stores of the direct path become one coalesced, bounds-clipped TMA store.
         const int nch = p.n_tile >> 6;
-        float gv[32];                                  // GroupNorm partials: [chunk][group of 8 ch][sum, sumsq]
-#pragma unroll
-        for (int j = 0; j < 32; ++j) gv[j] = 0.f;
         uint4 rc[4], rn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { rc[j] = make_uint4(0u, 0u, 0u, 0u); rn[j] = make_uint4(0u, 0u, 0u, 0u); }
@@ -597,113 +646,130 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 4; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + col_half * 32 + j * 8));
         }
-#pragma unroll
-        for (int c64 = 0; c64 < 4; ++c64) {
-          if (c64 < nch) {
+        // Half-chunk software pipeline: while 16 accumulator columns are being turned into fp16, the tcgen05.ld of the next
+        // 16 is in flight (same register budget as one 32-column load).
+        uint32_t va[16], vb[16];
+        tmem_ld16(t_base + (uint32_t)(col_half * 32), va);
+        // The chunk loop is deliberately NOT unrolled: unrolled it was ~3000 straight-line instructions per tile with no
+        // reuse, and the epilogue ran at instruction-fetch speed (~700 cycles per chunk even with all work disabled).
+#pragma unroll 1
+        for (int c64 = 0; c64 < nch; ++c64) {
+          {
             const int cc = c64 * 64 + col_half * 32;     // first of this thread's 32 columns inside the tile
+            float gv[8];                                   // GroupNorm partials of this chunk: [group of 8 ch][sum, sumsq]
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = 0.f;
             if (res_row && !res_smem && c64 + 1 < nch) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
             }
-            uint8_t* sbuf = s_stage + (size_t)slot * 16384;
-            if (p.res_tma) {
+            const uint32_t srow = stage_a + (uint32_t)slot * 16384u + (uint32_t)row * 128u;   // this thread's staging row
+            if (o_flags & 4) {
               // the slot's previous store has been read out AND this chunk's residual has landed in it (inactive tiles:
               // the store warp arrives without a load)
-              mbar_wait(&rfull_bar[slot], slot_ph);
+              mbar_wait_a(rfull_a + (uint32_t)slot * 8u, slot_ph);
               if (res_smem) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  rc[j] = *reinterpret_cast<const uint4*>(sbuf + row * 128 + (((col_half * 4 + j) ^ (row & 7)) * 16));
+                for (int j = 0; j < 4; ++j) rc[j] = lds128(srow + (uint32_t)(((col_half * 4 + j) ^ (row & 7)) * 16));
               }
             } else {
-              mbar_wait(&sfree_bar[slot], slot_ph ^ 1);       // the slot's previous TMA store has been read out
+              mbar_wait_a(sfree_a + (uint32_t)slot * 8u, slot_ph ^ 1);       // the slot's previous TMA store has been read out
             }
             TS3(20 + 4 * c64);
-            uint32_t v[32];
-            tmem_ld32(t_base + (uint32_t)cc, v);
-            tmem_ld_wait();
-            TS3(21 + 4 * c64);
-            float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(sb + cc);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b = b4[j];
-                f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            for (int h = 0; h < 2; ++h) {
+              uint32_t* v = h ? vb : va;
+              if (!(o_dbg & 128)) {
+                tmem_ld_wait16(v);
+                if (h == 0) tmem_ld16(t_base + (uint32_t)(cc + 16), vb);
+                else if (c64 + 1 < nch) tmem_ld16(t_base + (uint32_t)(cc + 64), va);
               }
-            }
-            if (p.alpha != 1.0f) {
+              if (h == 0) TS3(21 + 4 * c64);
+              float f[16];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
-            }
-            if (res_row || res_smem) {
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+              if ((o_flags & 1) && !(o_dbg & 64)) {
+                const uint32_t ba = bias_a + (uint32_t)((single_n ? 0 : (int)(lt & 1) * 256) + cc + h * 16) * 4u;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __half2* hh = reinterpret_cast<const __half2*>(&rc[j]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 a = __half22float2(hh[e]);
-                  f[j * 8 + 2 * e] += a.x; f[j * 8 + 2 * e + 1] += a.y;
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 b = lds128(ba + (uint32_t)j * 16u);
+                  f[4 * j] += __uint_as_float(b.x); f[4 * j + 1] += __uint_as_float(b.y);
+                  f[4 * j + 2] += __uint_as_float(b.z); f[4 * j + 3] += __uint_as_float(b.w);
                 }
               }
-            }
-            if (p.gn_group && valid && !(p.debug_mode & 4)) {
+              if (o_flags & 16) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float sg = 0.f, qg = 0.f;
+                for (int j = 0; j < 16; ++j) f[j] *= o_alpha;
+              }
+              if ((res_row || res_smem) && !(o_dbg & 64)) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { sg += f[g * 8 + e]; qg += f[g * 8 + e] * f[g * 8 + e]; }
-                gv[c64 * 8 + g * 2] = sg;
-                gv[c64 * 8 + g * 2 + 1] = qg;
+                for (int j = 0; j < 2; ++j) {
+                  const __half2* hh = reinterpret_cast<const __half2*>(&rc[h * 2 + j]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 a = __half22float2(hh[e]);
+                    f[j * 8 + 2 * e] += a.x; f[j * 8 + 2 * e + 1] += a.y;
+                  }
+                }
+              }
+              if ((o_flags & 8) && valid && !(o_dbg & 4)) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                  float sg = 0.f, qg = 0.f;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) { sg += f[g * 8 + e]; qg += f[g * 8 + e] * f[g * 8 + e]; }
+                  gv[(h * 2 + g) * 2] = sg;
+                  gv[(h * 2 + g) * 2 + 1] = qg;
+                }
+              }
+              // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7); ReLU on the packed halves
+              // (max(round(x), 0) == round(max(x, 0)): rounding is monotonic and 0 is exact)
+              const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 o;
+                __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 hv = __floats2half2_rn(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
+                  ho[e] = (o_flags & 2) ? __hmax2(hv, zero2) : hv;
+                }
+                const int chunk = (col_half * 4 + h * 2 + j) ^ (row & 7);
+                if (!(o_dbg & 32)) sts128(srow + (uint32_t)(chunk * 16), o);
               }
             }
-            if (p.relu) {
+            if ((o_flags & 8) && !(o_dbg & 4)) {
+              // 32 lanes x 8 partials -> lane j (j < 8) ends up with the warp total of partial j (recursive halving over
+              // lane bits 2..0, then two full exchanges over bits 3, 4: 9 shuffles), then ONE 64-bit fixed-point atomic
+              // per partial (integer adds are associative: bit-reproducible statistics).
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              for (int off = 4; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                  const float send = up ? gv[i] : gv[i + off];
+                  const float keep = up ? gv[i + off] : gv[i];
+                  gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 8);
+              gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 16);
+              if (lane < 8 && tc.active) {
+                const int g = lane >> 1, kind = lane & 1;
+                const int grp = ((n0 + cc) >> 3) + g;
+                const int ngroups = p.Cout / p.gn_group;
+                unsigned long long* st = reinterpret_cast<unsigned long long*>(L.gn_stats) + ((size_t)tc.img * ngroups + grp) * 2 + kind;
+                atomicAdd(st, (unsigned long long)__float2ll_rn(gv[0] * (kind ? kGnSqScale : kGnSumScale)));
+              }
             }
-            if (c64 == 1) TS3(40);
-            // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __half2* ho = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ho[e] = __floats2half2_rn(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
-              const int chunk = (col_half * 4 + j) ^ (row & 7);
-              *reinterpret_cast<uint4*>(sbuf + row * 128 + chunk * 16) = o;
-            }
-            if (c64 == 1) TS3(41);
-            fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
-            if (c64 == 1) TS3(42);
+            TS3(41);
+            if (!(o_dbg & 16)) fence_async_smem();         // generic-proxy writes -> visible to the TMA store
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sfull_bar[slot]);  // 8 warps -> the store warp ships the slot
+            if (lane == 0) mbar_arrive_a(sfull_a + (uint32_t)slot * 8u);  // 8 warps -> the store warp ships the slot
             TS3(22 + 4 * c64);
             if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) rc[j] = rn[j];
-          }
-        }
-        if (p.gn_group && !(p.debug_mode & 4)) {
-          // 32 lanes x 32 partials -> lane j holds the warp total of partial j (recursive halving: 31 shuffles),
-          // then ONE 64-bit fixed-point atomic per lane (associative: bit-reproducible statistics).
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send = up ? gv[i] : gv[i + off];
-              const float keep = up ? gv[i + off] : gv[i];
-              gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          const int c64 = lane >> 3, g = (lane >> 1) & 3, kind = lane & 1;
-          if (c64 < nch && tc.active) {
-            const int grp = ((n0 + c64 * 64 + col_half * 32) >> 3) + g;
-            const int ngroups = p.Cout / p.gn_group;
-            unsigned long long* st = reinterpret_cast<unsigned long long*>(L.gn_stats) + ((size_t)tc.img * ngroups + grp) * 2 + kind;
-            atomicAdd(st, (unsigned long long)__float2ll_rn(gv[0] * (kind ? kGnSqScale : kGnSumScale)));
           }
         }
       } else

@@ -30,6 +30,6 @@ for i in [int(a) for a in sys.argv[1:]]:
         print('   tile#1 epilogue (warp 2, cycles from its loop top): prefetch/wait_read=%d bias-bar=%d tfull=%d' % (e(17), e(18), e(19)))
         for c in range(4):
             if t[20 + 4 * c]:
-                print('      chunk %d: slot+residual=%d tmem-ld=%d staged+arrived=%d' % (c, e(20 + 4 * c), e(21 + 4 * c),
+                print('      chunk %d: slot+residual=%d tmem-ld(h0)=%d fenced+arrived=%d' % (c, e(20 + 4 * c), e(21 + 4 * c),
                                                                           e(22 + 4 * c)))
-        print('      tile end=%d   chunk 1 detail: math done=%d sts done=%d fence done=%d' % (e(36), e(40), e(41), e(42)))
+        print('      tile end=%d   last chunk both halves staged=%d' % (e(36), e(41)))
