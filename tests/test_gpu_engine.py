@@ -136,3 +136,54 @@ def test_images_in_flight_match_serial(small_case):
         assert torch.equal(host['det'], w['det_bboxes'].cpu())
         assert torch.equal(host['bits'], w['mask_bits'].cpu())
         assert seen[i] == int(w['count'][0])
+
+
+def _engine_vs_oracle(depth, stacked, gn, ssd, H, W, cfg, cls_bias, scale_factor=1.0, tol=2e-2):
+    from oracle import model as M
+    from oracle import postproc as P
+    from sipmask_b200 import ops, synth
+    from sipmask_b200.engine import SipMaskEngine
+    sd = synth.detector_state_dict(depth=depth, stacked_convs=stacked, gn=gn, seed=1, cls_bias=cls_bias)
+    img = synth.synthetic_image(H, W, seed=0)
+    net = M.SipMaskDetector(depth, stacked_convs=stacked, gn=gn, ssd_flag=ssd)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        ref = net(img)
+    img_shape = (H, W, 3)
+    eng = SipMaskEngine(sd, (H, W), depth=depth, stacked_convs=stacked, gn=gn, ssd_flag=ssd, test_cfg=cfg, img_shape=img_shape,
+                        scale_factor=scale_factor, use_graph=True)
+    out = eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    ho = eng.head_outputs()
+    cls, bbox, ctr, cof, fm = ref
+    for l in range(5):
+        assert _rel(ho['cls'][l].cpu(), cls[l]) < tol, l
+        assert _rel(ho['bbox'][l].cpu(), bbox[l]) < tol, l
+        assert _rel(ho['cof'][l].cpu(), cof[l]) < tol, l
+    assert _rel(ho['feat_masks'].float().cpu(), fm) < tol
+    res = P.get_bboxes_single([t[0].cpu() for t in ho['cls']], [t[0].cpu() for t in ho['bbox']],
+                              [t[0].cpu() for t in ho['ctr']], [t[0].cpu() for t in ho['cof']],
+                              ho['feat_masks'][0].float().cpu(), eng.strides, img_shape, img_shape, scale_factor, cfg,
+                              rescale=True, ssd_flag=ssd)
+    k = int(out['count'][0])
+    assert k == res['det_bboxes'].shape[0] and k > 0
+    assert out['det_labels'][0, :k].cpu().tolist() == res['det_labels'].tolist()
+    np.testing.assert_allclose(out['det_bboxes'][0, :k].cpu().numpy(), res['det_bboxes'].numpy(), rtol=1e-5, atol=1e-5)
+    masks = ops.unpack_mask_bits(out['mask_bits'][0, :k].cpu(), img_shape[1]).numpy().astype(bool)
+    want = res['masks'].astype(bool)
+    iou = (np.logical_and(masks, want).sum((1, 2)) + 1e-9) / (np.logical_or(masks, want).sum((1, 2)) + 1e-9)
+    assert iou.min() >= 0.999, iou
+
+
+def test_config_b_ssd_two_convs_no_gn_fast_nms():
+    """SURVEY §8 config B at reduced size: stacked_convs=2, norm_cfg=None, ssd_flag (fast_nms, per-axis scale_factor),
+    sipmask_r50_caffe_fpn_ssd_6x.py.  Head outputs within 2e-2 of the fp32 oracle; detections equal to the oracle's on the
+    engine's own head outputs; masks IoU >= 0.999."""
+    cfg = dict(nms_pre=200, score_thr=0.1, nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
+    _engine_vs_oracle(50, 2, False, True, 160, 160, cfg, cls_bias=-2.5, scale_factor=np.ones(4, dtype=np.float32))
+
+
+def test_r101_backbone():
+    """SURVEY §8 config A with the R101 backbone ((3,4,23,3) bottlenecks, resnet.py:312-324) at reduced size."""
+    cfg = dict(nms_pre=200, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=30)
+    _engine_vs_oracle(101, 4, True, False, 128, 160, cfg, cls_bias=-2.5, tol=3e-2)
