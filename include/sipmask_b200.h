@@ -68,6 +68,18 @@ int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8
 int smb_mask_upsample2_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
                                       int out_h, int out_w, float thr, smb_stream_t stream);
 
+/* COCO RLE of bit-packed masks on the device (replaces the per-detection `masks[i].cpu().numpy()` + pycocotools
+ * `mask_util.encode(order='F')` tail, sipmask_head.py:645-657).
+ *   mask_bits : [N, mask_h, words] uint32 (pixel x = bit x&31 of word x>>5), cropped to the top-left H x W (= ori_shape)
+ *   n_valid   : device int (number of valid detections, may be NULL = N)
+ *   counts    : [N, cap] uint32 run lengths in COLUMN-major order, starting with the zeros run
+ *   n_counts  : [N] int32: number of runs, 0 for det >= *n_valid, or -(boundaries+1) if cap was too small */
+int smb_mask_rle_counts(const uint32_t* mask_bits, int N, int mask_h, int words, int H, int W, const int* n_valid,
+                        uint32_t* counts, int cap, int* n_counts, smb_stream_t stream);
+/* HOST helper (plain C, no CUDA): pycocotools' rleToString of `n` run lengths; returns the length written, -1 if cap is
+ * too small.  counts is a host pointer. */
+int smb_rle_to_string(const uint32_t* host_counts, int n, char* host_out, int cap);
+
 /* Fully fused mask path (sipmask_head.py:609-633,648-654 in one kernel): prototypes -> selected sub-region dot
  * product -> sigmoid -> crop -> x2 bilinear -> `> thr` -> bit-pack.  pos_masks is never written to memory.
  * Same arguments as smb_mask_assemble; output as smb_mask_upsample2_threshold_pack. */

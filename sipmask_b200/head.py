@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import postproc, rle
+from . import ops, postproc, rle
 from .engine import SipMaskEngine
 
 INF = 1e8
@@ -140,14 +140,17 @@ class SipMaskHead(_HeadBase):
             res = postproc.get_bboxes_single(
                 [t[i] for t in cls_scores], [t[i] for t in bbox_preds], [t[i] for t in centernesses],
                 [t[i] for t in cof_preds], feat_masks[i], self.strides, meta['img_shape'], meta['ori_shape'],
-                meta['scale_factor'], cfg, rescale=rescale, ssd_flag=self.ssd_flag)
+                meta['scale_factor'], cfg, rescale=rescale, ssd_flag=self.ssd_flag, pack=True)
             k = int(res['count'])
             det_bboxes, det_labels = res['det_bboxes'][:k], res['det_labels'][:k]
-            masks = res['masks'][:k].cpu().numpy()                 # ONE device->host copy (the reference does k)
+            # RLE run lengths are computed on the device; the host receives a few KB of counts per detection (the
+            # reference copies k dense masks, one synchronous 4.3 MB D2H each, and encodes them single-threaded)
+            mh, mw = res['mask_hw']
+            rles = ops.masks_to_rle(res['mask_bits'], mh, mw, k)
             labels = det_labels.cpu().numpy()
             cls_segms = [[] for _ in range(self.num_classes - 1)]
             for j in range(k):
-                cls_segms[int(labels[j])].append(rle.encode(masks[j]))
+                cls_segms[int(labels[j])].append(rles[j])
             results.append((det_bboxes, det_labels, cls_segms))
         return results
 

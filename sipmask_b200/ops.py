@@ -276,3 +276,45 @@ def unpack_mask_bits(bits, out_w):
     sh = torch.arange(8, device=b.device, dtype=torch.uint8)
     px = ((b.unsqueeze(-1) >> sh) & 1).reshape(b.shape[0], b.shape[1], -1)
     return px[:, :, :out_w].contiguous()
+
+
+def mask_rle_counts(mask_bits, H, W, n_valid=None, cap=8192):
+    """Device-side COCO RLE (smb_mask_rle_counts): bit-packed masks int32 [N,mask_h,words] cropped to H x W ->
+    (counts uint32-as-int32 [N,cap] column-major run lengths, n_counts int32 [N]).  n_valid: optional device int tensor."""
+    _need_cuda(mask_bits)
+    assert mask_bits.dtype == torch.int32 and mask_bits.is_contiguous() and mask_bits.dim() == 3
+    N, mask_h, words = mask_bits.shape
+    counts = torch.empty((N, cap), dtype=torch.int32, device=mask_bits.device)
+    n_counts = torch.empty((N,), dtype=torch.int32, device=mask_bits.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    L.check(L.lib().smb_mask_rle_counts(L.ptr(mask_bits), N, mask_h, words, int(H), int(W), L.ptr(n_valid), L.ptr(counts),
+                                        int(cap), L.ptr(n_counts), L.stream_ptr()), 'smb_mask_rle_counts')
+    return counts, n_counts
+
+
+def rle_to_string(counts):
+    """Host helper of the ABI (smb_rle_to_string): run lengths (numpy / CPU tensor, any int type) -> pycocotools bytes."""
+    c = np.ascontiguousarray(np.asarray(counts).astype(np.uint32))
+    cap = 8 * c.size + 8
+    buf = ctypes.create_string_buffer(cap)
+    n = L.lib().smb_rle_to_string(c.ctypes.data_as(ctypes.c_void_p), int(c.size), buf, cap)
+    if n < 0:
+        raise L.SmbError('smb_rle_to_string: buffer too small')
+    return buf.raw[:n]
+
+
+def masks_to_rle(mask_bits, H, W, k, cap=8192):
+    """k valid bit-packed masks -> list of k COCO RLE dicts {'size': [H, W], 'counts': bytes}: one kernel, one small D2H
+    (k * runs * 4 bytes instead of k * H * W mask bytes), string packing in C on the host."""
+    if k == 0:
+        return []
+    counts, n = mask_rle_counts(mask_bits[:k].contiguous(), H, W, cap=cap)
+    n_host = n.cpu().numpy()
+    if (n_host < 0).any():                                    # pathological (noise-like) mask: retry with the exact capacity
+        need = int((-n_host).max()) + 1
+        counts, n = mask_rle_counts(mask_bits[:k].contiguous(), H, W, cap=need)
+        n_host = n.cpu().numpy()
+    width = int(n_host.max())
+    c_host = counts[:, :width].cpu().numpy()
+    return [{'size': [int(H), int(W)], 'counts': rle_to_string(c_host[j, :n_host[j]])} for j in range(k)]

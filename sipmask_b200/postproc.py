@@ -17,7 +17,7 @@ def _cl(t):
 
 def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides, img_shape, ori_shape,
                       scale_factor, cfg, rescale=False, ssd_flag=False, cmp_ge=False, mask_thr=0.4,
-                      channel_last=False, feat_mask_layout='chw', box_scales=None, top_k=200, upsample=True):
+                      channel_last=False, feat_mask_layout='chw', box_scales=None, top_k=200, upsample=True, pack=False):
     """Inputs per level: CHW tensors like the reference (channel_last=False) or [h,w,C] fp32 views.
     cfg: dict with nms_pre, score_thr, nms.iou_thr, max_per_img."""
     if not channel_last:
@@ -53,5 +53,9 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
     out = dict(det_bboxes=det, det_labels=lab, idxs_keep=idx, count=cnt, pos_masks=pos, masks=None)
     if upsample:
         tgt = ori_shape if rescale else img_shape
-        out['masks'] = ops.mask_upsample2_threshold(pos, (int(tgt[0]), int(tgt[1])), mask_thr)
+        if pack:            # bit planes [max, H, ceil(W/32)] for the device RLE encoder (ops.masks_to_rle)
+            out['mask_bits'] = ops.mask_upsample2_threshold_pack(pos, (int(tgt[0]), int(tgt[1])), mask_thr)
+            out['mask_hw'] = (int(tgt[0]), int(tgt[1]))
+        else:
+            out['masks'] = ops.mask_upsample2_threshold(pos, (int(tgt[0]), int(tgt[1])), mask_thr)
     return out
