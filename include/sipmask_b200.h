@@ -251,6 +251,15 @@ int smb_upsample_bilinear(const void* x, int in_pitch, void* y, int out_pitch, i
 /* Image preparation: NCHW fp32 -> zero-padded NHWC8 fp16 [N, H+6, W+8, 8] for the 7x7/2 stem. */
 int smb_image_to_nhwc8(const float* img, void* out, int N, int H, int W, smb_stream_t stream);
 
+/* Test-time image pipeline on the device (transforms.py:97-110 Resize(keep_ratio), :335-363 Normalize
+ * (std = 1, to_rgb = False), :274-300 Pad(32); mmcv.imrescale -> cv2.resize(INTER_LINEAR) restated bit-exactly):
+ *   src       : uint8 BGR HWC [src_h, src_w, 3] device image, row pitch in bytes
+ *   dst_h/w   : resized size (mmcv rule: int(h * s + 0.5), s = min(max_long / max(h, w), max_short / min(h, w)))
+ *   out_nhwc8 : the stem's input [H+6, W+8, 8] fp16 (pixel (y,x) at (y+3, x+3)), H x W = padded size >= dst; everything
+ *               outside the resized image is zero (= zero padding AFTER mean subtraction, as in the reference) */
+int smb_preprocess_u8(const uint8_t* src, int src_h, int src_w, int src_pitch_bytes, int dst_h, int dst_w,
+                      const float* host_mean3, void* out_nhwc8, int H, int W, smb_stream_t stream);
+
 /* Stem 7x7/2 conv (3->64) + folded BN + ReLU on the padded NHWC8 image (backbones/resnet.py:448-460). */
 int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, const void* weight448, void* out,
                          smb_conv_plan_t** plan_out);

@@ -173,6 +173,19 @@ def image_to_nhwc8(img, out=None):
     return out
 
 
+def preprocess_u8(src, resized_hw, out, mean):
+    """uint8 BGR HWC CUDA image -> resized (cv2 INTER_LINEAR, bit-exact) - mean -> zero-padded NHWC8 fp16 stem input
+    `out` [1, H+6, W+8, 8] (smb_preprocess_u8)."""
+    assert src.is_cuda and src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3 and src.stride(2) == 1 \
+        and src.stride(1) == 3
+    assert out.dtype == torch.float16 and out.is_contiguous() and out.shape[0] == 1 and out.shape[3] == 8
+    H, W = out.shape[1] - 6, out.shape[2] - 8
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    L.check(L.lib().smb_preprocess_u8(L.ptr(src), int(src.shape[0]), int(src.shape[1]), int(src.stride(0)), int(resized_hw[0]),
+                                      int(resized_hw[1]), m, L.ptr(out), H, W, L.stream_ptr()), 'smb_preprocess_u8')
+    return out
+
+
 def maxpool3x3s2(x, out=None):
     N, H, W, C = x.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1

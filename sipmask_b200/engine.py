@@ -138,6 +138,7 @@ class SipMaskEngine(object):
         self.img = self._t(N, 3, H, W, dtype=torch.float32)
         # ---- stem
         img8 = self._t(N, H + 6, W + 8, 8)
+        self.img8 = img8
         self._add(lambda: C.image_to_nhwc8(self.img, img8), name='image_to_nhwc8')
         wk, b = self._once('stem', lambda: C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'),
                                                               device=self.dev))
@@ -522,6 +523,27 @@ class SipMaskEngine(object):
             self.graph.replay()
         else:
             self._run_ops()
+        return dict(det_bboxes=self.det, det_labels=self.labels, count=self.count, mask_bits=self.mask_bits,
+                    idxs_keep=self.idx)
+
+    def forward_raw(self, img_u8, mean=(102.9801, 115.9465, 122.7717)):
+        """img_u8: uint8 BGR HWC CUDA image straight from the decoder.  Resize (keep ratio, mmcv.imrescale rule towards this
+        engine's img_shape) + mean subtraction + padding + layout run in ONE kernel that writes the stem's input
+        (SURVEY.md 8f-3); the rest of the step is the CUDA graph without its `image_to_nhwc8` node.  The resized size must
+        equal the engine's img_shape (one engine per input resolution in round 1)."""
+        C.preprocess_u8(img_u8, self.img_shape[:2], self.img8, mean)
+        if self.use_graph:
+            if getattr(self, 'graph_raw', None) is None:
+                names = set(self.op_names) - {'image_to_nhwc8', 'fork', 'join'}
+                self._run_ops(only=names)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_ops(only=names)
+                self.graph_raw = g
+            self.graph_raw.replay()
+        else:
+            self._run_ops(only=set(self.op_names) - {'image_to_nhwc8', 'fork', 'join'})
         return dict(det_bboxes=self.det, det_labels=self.labels, count=self.count, mask_bits=self.mask_bits,
                     idxs_keep=self.idx)
 
