@@ -33,8 +33,8 @@ class SipMaskEngine(object):
         self.N, (self.H, self.W) = batch, img_hw
         self.head_only, self.feat_sizes, self.in_channels, self.fcos = head_only, feat_sizes, in_channels, fcos
         self.hp, self.build_post = prefix_head, build_postproc
-        self.two_streams = two_streams
-        self.fork_branches = two_streams and os.environ.get('SMB_FORK_BRANCHES', '1') != '0'
+        self.two_streams = two_streams and os.environ.get('SMB_TWO_STREAMS', '1') != '0'
+        self.fork_branches = self.two_streams and os.environ.get('SMB_FORK_BRANCHES', '1') != '0'
         self.fork_from_layer = int(os.environ.get('SMB_FORK_FROM_LAYER', '1'))      # 0-based residual stage index
         assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
         assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
