@@ -68,6 +68,17 @@ int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8
 int smb_mask_upsample2_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
                                       int out_h, int out_w, float thr, smb_stream_t stream);
 
+/* SipMask++ mask rescoring (sipmask_head.py:200-219,635-643).
+ * smb_conv3x3s2_relu_f32: one ConvModule of `convs_scoring`: NCHW fp32 conv3x3, stride 2, padding 0, + bias, ReLU;
+ *   in [N,Cin,H,W] -> out [N,Cout,(H-3)/2+1,(W-3)/2+1], weight [Cout,Cin,3,3].
+ * smb_mask_rescore: relu(mask_scoring 1x1) -> global max-pool -> the detection's own class -> times det[:,4]:
+ *   feat [N,C,h,w], weight1x1 [num_classes,C], labels int64 [N], det [N,5], n_valid device int (or NULL) -> scores [N]. */
+int smb_conv3x3s2_relu_f32(const float* in, const float* weight, const float* bias, float* out, int N, int Cin, int H,
+                           int W, int Cout, smb_stream_t stream);
+int smb_mask_rescore(const float* feat, int N, int C, int h, int w, const float* weight1x1, const float* bias1x1,
+                     int num_classes, const int64_t* labels, const float* det, const int* n_valid, float* scores,
+                     smb_stream_t stream);
+
 /* COCO RLE of bit-packed masks on the device (replaces the per-detection `masks[i].cpu().numpy()` + pycocotools
  * `mask_util.encode(order='F')` tail, sipmask_head.py:645-657).
  *   mask_bits : [N, mask_h, words] uint32 (pixel x = bit x&31 of word x>>5), cropped to the top-left H x W (= ori_shape)

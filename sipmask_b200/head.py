@@ -76,14 +76,20 @@ class _HeadBase(nn.Module):
                                   '(same parameter names, so checkpoints move both ways)')
 
 
+class _ScoringConv(nn.Module):
+    """Parameter holder with the reference's names: convs_scoring.{i}.conv.{weight,bias} (ConvModule, bias=True, no norm)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 3, stride=2, padding=0, bias=True)
+
+
 class SipMaskHead(_HeadBase):
     def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
                  regress_ranges=((-1, 64), (64, 128), (128, 256), (256, 512), (512, INF)), center_sampling=False,
                  center_sample_radius=1.5, ssd_flag=False, rescoring_flag=False, loss_cls=None, loss_bbox=None,
                  loss_centerness=None, conv_cfg=None, norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
         super().__init__()
-        if rescoring_flag:
-            raise NotImplementedError('rescoring_flag (SipMask++ mask rescoring) is a later row of the scope table')
         if in_channels != 256 or feat_channels != 256:
             raise NotImplementedError('the GroupNorm-statistics epilogue is specialised for 256 feature channels')
         self.num_classes, self.cls_out_channels = num_classes, num_classes - 1
@@ -106,6 +112,10 @@ class SipMaskHead(_HeadBase):
         self.sip_cof = nn.Conv2d(feat_channels, self.nc * 4, 3, padding=1)
         self.sip_mask_lat = nn.Conv2d(512, self.nc, 3, padding=1)
         self.sip_mask_lat0 = nn.Conv2d(768, 512, 1, padding=0)
+        if rescoring_flag:                             # SipMask++ mask rescoring (sipmask_head.py:200-219)
+            ch = [1, 16, 16, 16, 32, 64, 128]
+            self.convs_scoring = nn.Sequential(*[_ScoringConv(ch[i], ch[i + 1]) for i in range(6)])
+            self.mask_scoring = nn.Conv2d(128, self.cls_out_channels, 1)
         self.init_weights()
 
     def init_weights(self):
@@ -119,6 +129,12 @@ class SipMaskHead(_HeadBase):
         nn.init.constant_(self.fcos_cls.bias, float(-np.log((1 - 0.01) / 0.01)))
         nn.init.constant_(self.feat_align.conv_offset.weight, 0.0)
         nn.init.normal_(self.feat_align.conv_adaption.weight, 0, 0.01)
+        if self.rescoring_flag:
+            for m in self.convs_scoring:
+                nn.init.kaiming_normal_(m.conv.weight, mode='fan_out', nonlinearity='relu')
+                nn.init.constant_(m.conv.bias, 0)
+            nn.init.normal_(self.mask_scoring.weight, 0, 0.001)
+            nn.init.constant_(self.mask_scoring.bias, 0)
 
     @torch.no_grad()
     def forward(self, feats):
@@ -140,7 +156,8 @@ class SipMaskHead(_HeadBase):
             res = postproc.get_bboxes_single(
                 [t[i] for t in cls_scores], [t[i] for t in bbox_preds], [t[i] for t in centernesses],
                 [t[i] for t in cof_preds], feat_masks[i], self.strides, meta['img_shape'], meta['ori_shape'],
-                meta['scale_factor'], cfg, rescale=rescale, ssd_flag=self.ssd_flag, pack=True)
+                meta['scale_factor'], cfg, rescale=rescale, ssd_flag=self.ssd_flag, pack=True,
+                rescoring=self._rescoring_weights())
             k = int(res['count'])
             det_bboxes, det_labels = res['det_bboxes'][:k], res['det_labels'][:k]
             # RLE run lengths are computed on the device; the host receives a few KB of counts per detection (the
@@ -151,8 +168,19 @@ class SipMaskHead(_HeadBase):
             cls_segms = [[] for _ in range(self.num_classes - 1)]
             for j in range(k):
                 cls_segms[int(labels[j])].append(rles[j])
-            results.append((det_bboxes, det_labels, cls_segms))
+            if self.rescoring_flag:                      # (cls_segms, mask_scores) like sipmask_head.py:641-643,659-660
+                ms = res['mask_scores'][:k].cpu().numpy()
+                mask_scores = [ms[labels == c] for c in range(self.num_classes - 1)]
+                results.append((det_bboxes, det_labels, (cls_segms, mask_scores)))
+            else:
+                results.append((det_bboxes, det_labels, cls_segms))
         return results
+
+    def _rescoring_weights(self):
+        if not self.rescoring_flag:
+            return None
+        return dict(conv_w=[m.conv.weight for m in self.convs_scoring], conv_b=[m.conv.bias for m in self.convs_scoring],
+                    w1x1=self.mask_scoring.weight, b1x1=self.mask_scoring.bias)
 
 
 class FCOSHead(_HeadBase):

@@ -318,3 +318,32 @@ def masks_to_rle(mask_bits, H, W, k, cap=8192):
     width = int(n_host.max())
     c_host = counts[:, :width].cpu().numpy()
     return [{'size': [int(H), int(W)], 'counts': rle_to_string(c_host[j, :n_host[j]])} for j in range(k)]
+
+
+def conv3x3s2_relu(x, weight, bias):
+    """One `convs_scoring` ConvModule (sipmask_head.py:200-214): NCHW fp32 conv3x3 stride 2 pad 0 + bias + ReLU."""
+    _need_cuda(x, weight, bias)
+    x, weight, bias = x.float().contiguous(), weight.float().contiguous(), bias.float().contiguous()
+    N, Cin, H, W = x.shape
+    Cout = weight.shape[0]
+    assert weight.shape == (Cout, Cin, 3, 3)
+    out = torch.empty((N, Cout, (H - 3) // 2 + 1, (W - 3) // 2 + 1), dtype=torch.float32, device=x.device)
+    L.check(L.lib().smb_conv3x3s2_relu_f32(L.ptr(x), L.ptr(weight), L.ptr(bias), L.ptr(out), N, Cin, H, W, Cout, L.stream_ptr()),
+            'smb_conv3x3s2_relu_f32')
+    return out
+
+
+def mask_rescore(pos_masks, conv_weights, conv_biases, w1x1, b1x1, labels, det, n_valid=None):
+    """SipMask++ rescoring (sipmask_head.py:635-643): pos_masks [N,Hm,Wm] fp32 (cropped stride-2 masks) -> mask_scores [N]."""
+    x = pos_masks.float().unsqueeze(1)
+    for w, b in zip(conv_weights, conv_biases):
+        x = conv3x3s2_relu(x, w, b)
+    N, C, h, w_ = x.shape
+    w1 = w1x1.float().reshape(w1x1.shape[0], -1).contiguous()
+    scores = torch.empty((N,), dtype=torch.float32, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    L.check(L.lib().smb_mask_rescore(L.ptr(x), N, C, h, w_, L.ptr(w1), L.ptr(b1x1.float().contiguous()), int(w1.shape[0]),
+                                     L.ptr(labels.long().contiguous()), L.ptr(det.float().contiguous()), L.ptr(n_valid),
+                                     L.ptr(scores), L.stream_ptr()), 'smb_mask_rescore')
+    return scores

@@ -17,7 +17,8 @@ def _cl(t):
 
 def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides, img_shape, ori_shape,
                       scale_factor, cfg, rescale=False, ssd_flag=False, cmp_ge=False, mask_thr=0.4,
-                      channel_last=False, feat_mask_layout='chw', box_scales=None, top_k=200, upsample=True, pack=False):
+                      channel_last=False, feat_mask_layout='chw', box_scales=None, top_k=200, upsample=True, pack=False,
+                      rescoring=None):
     """Inputs per level: CHW tensors like the reference (channel_last=False) or [h,w,C] fp32 views.
     cfg: dict with nms_pre, score_thr, nms.iou_thr, max_per_img."""
     if not channel_last:
@@ -50,7 +51,10 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
         s4 = np.ones(4, np.float32)
     box_scale = s4 / 2.0
     pos = ops.mask_assemble(feat_mask, det_cofs, det[:, :4].contiguous(), box_scale, layout=feat_mask_layout)
-    out = dict(det_bboxes=det, det_labels=lab, idxs_keep=idx, count=cnt, pos_masks=pos, masks=None)
+    out = dict(det_bboxes=det, det_labels=lab, idxs_keep=idx, count=cnt, pos_masks=pos, masks=None, mask_scores=None)
+    if rescoring is not None:      # SipMask++: dict(conv_w=[6], conv_b=[6], w1x1, b1x1) (sipmask_head.py:635-643)
+        out['mask_scores'] = ops.mask_rescore(pos, rescoring['conv_w'], rescoring['conv_b'], rescoring['w1x1'],
+                                              rescoring['b1x1'], lab, det, n_valid=cnt)
     if upsample:
         tgt = ori_shape if rescale else img_shape
         if pack:            # bit planes [max, H, ceil(W/32)] for the device RLE encoder (ops.masks_to_rle)
