@@ -27,7 +27,7 @@ class SipMaskEngine(object):
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
                  mask_thr=0.4, use_graph=True, pos_dtype=torch.float32, head_only=False, feat_sizes=None, in_channels=256,
                  fcos=False, prefix_head='bbox_head.', build_postproc=True, two_streams=True, share_weights=None,
-                 max_ctas=None, head_max_ctas=None):
+                 max_ctas=None, head_max_ctas=None, backbone_dcn=False):
         L.check(L.lib().smb_check_device(), 'smb_check_device')
         self.dev = torch.device(device)
         self.N, (self.H, self.W) = batch, img_hw
@@ -39,6 +39,7 @@ class SipMaskEngine(object):
         assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
         assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
         self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
+        self.backbone_dcn = backbone_dcn           # SipMask++: DeformConvPack (dg=1) as conv2 of every 3rd block of stages 2-4
         self.ncls = num_classes - 1
         self.strides = tuple(strides)
         self.cfg = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
@@ -167,7 +168,16 @@ class SipMaskEngine(object):
                     idn = self._conv(x, p + 'downsample.0.weight', 1, stride, relu=False, bn=p + 'downsample.1')
                     self._tag = 0
                 t1 = self._conv(x, p + 'conv1.weight', 1, stride, relu=True, bn=p + 'bn1')
-                t2 = self._conv(t1, p + 'conv2.weight', 3, 1, relu=True, bn=p + 'bn2')
+                if self.backbone_dcn and i >= 1 and j % 3 == 0:
+                    # DeformConvPack (resnet.py:146-168,288-291; dcn/deform_conv.py:258-296): 18 offsets from a 3x3 conv
+                    # with bias (fp32 out), dg=1 bilinear gather into the column layout, then the 3x3 weights as a GEMM
+                    off = self._conv(t1, p + 'conv2.conv_offset.weight', 3, 1, bias_key=p + 'conv2.conv_offset.bias',
+                                     out_dtype=torch.float32, cout_pad=32, cout_real=18)
+                    col = self._t(N, t1.shape[1], t1.shape[2], 9 * t1.shape[3])
+                    self._add(lambda t1=t1, off=off, col=col: C.deform_im2col(t1, off, 1, out=col), name='deform_im2col')
+                    t2 = self._conv(col, p + 'conv2.weight', 1, 1, relu=True, bn=p + 'bn2')
+                else:
+                    t2 = self._conv(t1, p + 'conv2.weight', 3, 1, relu=True, bn=p + 'bn2')
                 if side:
                     self._marker('join')
                 elif j == 0:

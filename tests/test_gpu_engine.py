@@ -187,3 +187,27 @@ def test_r101_backbone():
     """SURVEY §8 config A with the R101 backbone ((3,4,23,3) bottlenecks, resnet.py:312-324) at reduced size."""
     cfg = dict(nms_pre=200, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=30)
     _engine_vs_oracle(101, 4, True, False, 128, 160, cfg, cls_bias=-2.5, tol=3e-2)
+
+
+def test_backbone_dcn_sipmask_pp():
+    """SipMask++ backbone: DeformConvPack dg=1 as conv2 of every third block of stages 2-4
+    (resnet.py:146-168,288-291).  FPN outputs within 2e-2 relative L2 of the fp32 oracle."""
+    from oracle import model as M
+    from sipmask_b200 import synth
+    from sipmask_b200.engine import SipMaskEngine
+    H, W = 128, 160
+    sd = synth.detector_state_dict(depth=50, backbone_dcn=True, seed=1, cls_bias=-2.5)
+    img = synth.synthetic_image(H, W, seed=0)
+    net = M.SipMaskDetector(50, backbone_dcn=True)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        feats = net.extract_feat(img)
+    cfg = dict(nms_pre=200, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=30)
+    eng = SipMaskEngine(sd, (H, W), test_cfg=cfg, img_shape=(H, W, 3), use_graph=True, backbone_dcn=True)
+    assert eng.op_names.count('deform_im2col') == 1 + 2 + 2 + 1          # head + stage 2 (blocks 0,3) + stage 3 (0,3) + stage 4 (0)
+    out = eng.forward(img.cuda())
+    torch.cuda.synchronize()
+    for l, (p, r) in enumerate(zip(eng.fpn_outs, feats)):
+        e = _rel(p.float().cpu().permute(0, 3, 1, 2), r)
+        assert e < 2e-2, 'FPN level %d rel err %g' % (l, e)
+    assert int(out['count'][0]) > 0
