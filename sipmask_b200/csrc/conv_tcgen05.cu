@@ -650,8 +650,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         // 16 is in flight (same register budget as one 32-column load).
         uint32_t va[16], vb[16];
         tmem_ld16(t_base + (uint32_t)(col_half * 32), va);
-        // The chunk loop is deliberately NOT unrolled: unrolled it was ~3000 straight-line instructions per tile with no
-        // reuse, and the epilogue ran at instruction-fetch speed (~700 cycles per chunk even with all work disabled).
+        // The chunk loop is rolled (the body is ~400 SASS instructions instead of ~3000 straight-line ones per tile, and
+        // the GroupNorm partials need no dynamically indexed array).  NOTE: rolling it did NOT change the measured
+        // epilogue time (profiles/r01_conv_concurrency_h.txt, run 45); why a chunk still costs ~1.1-1.4k cycles with all
+        // of its work disabled (profiles/r01_epilogue_ablation_debug_bits.txt) is not yet attributed - see DESIGN.md 7.
 #pragma unroll 1
         for (int c64 = 0; c64 < nch; ++c64) {
           {
