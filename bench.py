@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the SipMask inference hot path (BASELINE.json metric: images/sec @ 800x1333, bs=1/GPU).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU forward (oracle port)
+    python bench.py --gpus N --steps K --warmup W                      # this repo's sm_100a path, workload A (config 2)
+    python bench.py --workload A101 | B                                 # R101 (config 3) | 544x544 bs=32 (config 4)
+    python bench.py --impl reference --gpus N --steps K --warmup W      # the reference's CPU forward (oracle port)
 
 One "step" = one pass of the whole hot path (image -> backbone/FPN -> head -> decode/NMS -> mask assembly ->
-bit-packed masks) over one synthetic 800x1344 image per GPU.  Prints ONE JSON line (rank 0).
+bit-packed masks) over one synthetic image per GPU (workload B: one 32-image batch per GPU).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -20,8 +22,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = 'SipMask R50-FPN-GN 4conv, 800x1333 (padded 800x1344), bs=1/GPU, synthetic image + seeded synthetic weights'
-H, W, IMG_W = 800, 1344, 1333
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration `metric` is quoted on
+    'A': dict(name='SipMask R50-FPN-GN 4conv, 800x1333 (padded 800x1344), bs=1/GPU, synthetic image + seeded synthetic weights',
+              depth=50, stacked=4, gn=True, ssd=False, H=800, W=1344, img_w=1333, batch=1, score_thr=0.05, in_flight=6),
+    # configs[2]: R101 backbone, one image per GPU
+    'A101': dict(name='SipMask R101-FPN-GN 4conv, 800x1333 (padded 800x1344), bs=1/GPU, synthetic image + seeded synthetic weights',
+                 depth=101, stacked=4, gn=True, ssd=False, H=800, W=1344, img_w=1333, batch=1, score_thr=0.05, in_flight=6),
+    # configs[3]: real-time SSD-style head (2 convs, no GN, fast_nms), 544x544, bs=32 per forward (throughput mode)
+    'B': dict(name='SipMask R50-FPN SSD-style head (2conv, no GN, fast_nms), 544x544, bs=32 per forward, synthetic images + '
+                   'seeded synthetic weights', depth=50, stacked=2, gn=False, ssd=True, H=544, W=544, img_w=544, batch=32,
+              score_thr=0.1, in_flight=2),
+}
+CLS_BIAS = -5.0
+ROLL = 500          # untimed pre/post-roll steps around the timed region while nvidia-smi samples clocks
+
+
+def test_cfg(wl):
+    return dict(nms_pre=1000, score_thr=wl['score_thr'], nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
 
 
 def peaks():
@@ -29,6 +47,37 @@ def peaks():
         return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
     except Exception:
         return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernels, read from the committed
+    ncu --set full summary of this round (profiles/r02_ncu_traffic.json; bench.py itself never runs under a profiler)."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))
+    except Exception:
+        return {}
+
+
+def host_threads():
+    """Threads the CPU arm may really use: CPU affinity capped by the cgroup CPU quota (os.cpu_count() is the machine's
+    core count, 128 on the B200 hosts, of which a container usually owns a fraction - r1's CPU numbers moved 66x between
+    boxes because 128 threads were started on a few cores)."""
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if q != 'max':
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            p = float(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    n = aff if quota is None else max(1, min(aff, int(math.floor(quota + 1e-6)) or 1))
+    return n, dict(cpu_count=os.cpu_count(), affinity=aff, cgroup_quota=quota, used=n)
 
 
 class ClockSampler(object):
@@ -79,7 +128,7 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def build_oracle(threads):
+def build_oracle(wl, threads):
     import torch
     from oracle import model as M
     from oracle import ops as O
@@ -87,20 +136,17 @@ def build_oracle(threads):
     torch.set_num_threads(threads)
     O.USE_TORCHVISION_DCN = True
     O.USE_C_CROP_SPLIT = True
-    net = M.SipMaskDetector(50)
-    net.load_state_dict(synth.detector_state_dict(50, seed=1, cls_bias=CLS_BIAS), strict=True)
+    net = M.SipMaskDetector(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], ssd_flag=wl['ssd'])
+    net.load_state_dict(synth.detector_state_dict(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], seed=1, cls_bias=CLS_BIAS),
+                        strict=True)
     net.eval()
     return net
 
 
-ROLL = 500          # untimed pre/post-roll steps around the timed region while nvidia-smi samples clocks
-CLS_BIAS = -5.0
-TEST_CFG = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
-
-
-def oracle_step(net, img, rows=H):
+def oracle_step(net, img, wl):
     """The reference's forward on host cores: backbone -> FPN -> head -> get_bboxes (decode, per-class NMS with the
-    compiled C oracle, dense 4x matmul/sigmoid/stack/CropSplit mask assembly, x2 upsample + threshold)."""
+    compiled C oracle, dense 4x matmul/sigmoid/stack/CropSplit mask assembly, x2 upsample + threshold), ONE image."""
+    import numpy as np
     import torch
     from oracle import cbind, postproc as P
     from oracle import ops as O
@@ -108,53 +154,54 @@ def oracle_step(net, img, rows=H):
         cls, box, ctr, cof, fm = net(img)
     real_nms = O.nms
     O.nms = lambda dets, thr, cmp_ge=False, plus_one=True: cbind.nms(dets, thr, int(cmp_ge), int(plus_one))
+    shape = (wl['H'], wl['img_w'], 3)
+    sf = np.ones(4, dtype=np.float32) if wl['ssd'] else 1.0
     try:
         res = P.get_bboxes_single([t[0] for t in cls], [t[0] for t in box], [t[0] for t in ctr], [t[0] for t in cof], fm[0],
-                                  (8, 16, 32, 64, 128), (rows, IMG_W, 3), (rows, IMG_W, 3), 1.0, TEST_CFG, rescale=True)
+                                  (8, 16, 32, 64, 128), shape, shape, sf, test_cfg(wl), rescale=True, ssd_flag=wl['ssd'])
     finally:
         O.nms = real_nms
     return res
 
 
-def cpu_reference(steps, warmup, threads, budget_s=200.0):
-    """Times `steps` steps after `warmup`.  A step is one full 800x1344 image when the whole run fits the time budget;
-    otherwise a horizontal strip of `rows` image rows (rows/800 of an image - the path is convolutional, cost is linear
-    in rows), so that the run stays bounded.  Returns (seconds per FULL image, detections, rows, step times)."""
+def cpu_reference(wl, steps, warmup, threads, budget_s=150.0):
+    """Times WHOLE images only (r1's row-strip extrapolation was refuted by its own numbers).  The first pass is the probe;
+    the number of timed images is min(steps, what fits the time budget), at least 1.  Returns (seconds per image,
+    detections, images timed, per-image times)."""
     from sipmask_b200 import synth
-    net = build_oracle(threads)
-    img = synth.synthetic_image(H, W, seed=0)
+    net = build_oracle(wl, threads)
+    img = synth.synthetic_image(wl['H'], wl['W'], seed=0)
     t0 = time.perf_counter()
-    res = oracle_step(net, img)                       # probe = first warm-up step, always a full image
+    res = oracle_step(net, img, wl)                       # probe = first warm-up image
     t_probe = time.perf_counter() - t0
-    rows = H
-    total = (steps + max(warmup - 1, 0)) * t_probe
-    if total > budget_s:
-        rows = int(max(64, min(H, round(H * budget_s / total / 32.0) * 32)))
-    sample = img[:, :, :rows].contiguous()
-    for _ in range(max(warmup - 1, 0)):
-        oracle_step(net, sample, rows)
+    n_warm = max(0, min(warmup - 1, int(0.2 * budget_s / max(t_probe, 1e-3))))
+    for _ in range(n_warm):
+        oracle_step(net, img, wl)
+    n_timed = max(1, min(steps, int(0.8 * budget_s / max(t_probe, 1e-3))))
     ts = []
-    for _ in range(steps):
+    for _ in range(n_timed):
         t0 = time.perf_counter()
-        res = oracle_step(net, sample, rows)
+        res = oracle_step(net, img, wl)
         ts.append(time.perf_counter() - t0)
-    sec_per_image = (sum(ts) / len(ts)) * (float(H) / rows)
-    return sec_per_image, int(res['det_bboxes'].shape[0]), rows, ts
+    return statistics.median(ts), int(res['det_bboxes'].shape[0]), n_timed, ts, 1 + n_warm
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sec, ndet, rows, ts = cpu_reference(args.steps, args.warmup, threads)
+    wl = WORKLOADS[args.workload]
+    threads, tinfo = host_threads()
+    sec, ndet, n_timed, ts, n_warm = cpu_reference(wl, args.steps, args.warmup, threads)
     val = 1.0 / sec
-    sample = ('%d steps, each %d of 800 rows of the 800x1344 image (%.3f image) through the oracle = PyTorch CPU fp32 '
-              'restatement of the reference forward incl. get_bboxes; the literal reference cannot run on CPU '
-              '(DeformConv/CropSplit are CUDA-only); value = (rows/800) / mean step time' % (args.steps, rows, rows / float(H)))
+    sample = ('%d whole %dx%d images timed (median; of --steps %d, bounded by a 150 s budget) after %d warm-up image(s), through the '
+              'oracle = PyTorch CPU fp32 restatement of the reference forward incl. get_bboxes on %d threads; the literal '
+              'reference cannot run on CPU (DeformConv / CropSplit are CUDA-only)' % (n_timed, wl['H'], wl['W'], args.steps, n_warm, threads))
     line = dict(impl='reference', metric='images/sec', value=val, unit='images/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=(sum(ts) / len(ts)) * 1e3, higher_is_better=True, scaling='weak',
-                vs_baseline=None, dtype='f32', data='synthetic', config=dict(workload=WORKLOAD, detections=ndet, rows_per_step=rows),
+                warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=wl['name'], detections=ndet, images_timed=n_timed, step_times_s=[round(t, 3) for t in ts],
+                            host_threads=tinfo),
                 cpu_baseline=dict(value=val, unit='images/s', cores=threads, kind='port', sample=sample),
                 e2e=dict(value=val, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -162,12 +209,15 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from sipmask_b200 import dist as sdist
     from sipmask_b200 import ops, synth
-    from sipmask_b200.engine import SipMaskEngine
+    from sipmask_b200.serving import PipelinedRunner, EnginePool, make_engines
 
+    wl = WORKLOADS[args.workload]
+    H, W, IMG_W, B = wl['H'], wl['W'], wl['img_w'], wl['batch']
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -177,51 +227,69 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
 
-    sd = synth.detector_state_dict(50, seed=1, cls_bias=CLS_BIAS)
-    from sipmask_b200.serving import PipelinedRunner, EnginePool, make_engines
-    nfl = max(1, args.in_flight)
-    # nfl images in flight per GPU: nfl engines (shared weights, private activations + CUDA graph), one image per forward
-    engs = make_engines(sd, (H, W), in_flight=nfl, test_cfg=TEST_CFG, img_shape=(H, IMG_W, 3), use_graph=True, device=dev)
+    sd = synth.detector_state_dict(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], seed=1, cls_bias=CLS_BIAS)
+    nfl = max(1, args.in_flight if args.in_flight > 0 else wl['in_flight'])
+    cfg = test_cfg(wl)
+    sf = np.ones(4, dtype=np.float32) if wl['ssd'] else 1.0
+    ekw = dict(depth=wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], ssd_flag=wl['ssd'], batch=B, test_cfg=cfg,
+               img_shape=(H, IMG_W, 3), scale_factor=sf, use_graph=True, device=dev)
+    # nfl forwards in flight per GPU: nfl engines (shared weights, private activations + CUDA graph)
+    engs = make_engines(sd, (H, W), in_flight=nfl, **ekw)
     eng = engs[0]
-    img_host = synth.synthetic_image(H, W, seed=rank).pin_memory()        # one image per GPU (weak scaling)
+    img_host = torch.cat([synth.synthetic_image(H, W, seed=rank * B + b) for b in range(B)], 0).pin_memory()   # weak scaling
     for e in engs:
         e.img.copy_(img_host, non_blocking=True)
     torch.cuda.synchronize()
     pool = EnginePool(engs)
-    rec = torch.zeros((world, eng.max_num, 7), dtype=torch.float32, device=dev) if world > 1 else None
+    # the single collective of the path: records are logged locally per image and gathered ONCE at the end
+    # of the run, inside the timed region
+    log = sdist.RecordLog(max(args.steps, 1) * B, eng.max_num, dev)
+    gathered = torch.empty((world,) + tuple(log.buf.shape), dtype=torch.float32, device=dev) if world > 1 else None
 
-    def gather(out):
-        # the single collective of the path: fixed-shape detection record, on the main stream
-        sdist.gather_records(sdist.pack_record(out['det_bboxes'][0], out['det_labels'][0], out['count']), out=rec)
-
-    gather_fn = gather if world > 1 else None
+    def consume(out):
+        for b in range(B):
+            log.append(out['det_bboxes'][b], out['det_labels'][b], out['count'][b:b + 1])
 
     def step():
-        pool.step(gather_fn)
+        pool.step(consume)
 
     def step_finish():
-        pool.flush(gather_fn)
+        pool.flush(consume)
+        log.gather(out=gathered)               # world == 1: a view, no communication
+        log.reset()
 
-    # end-to-end through the public serving API: pinned-host image in, pinned-host record + bit-packed masks out, the
-    # upload / replay / download of consecutive images overlapped on their own streams (sipmask_b200/serving.py)
-    runner = PipelinedRunner(engs)
+    # end-to-end through the public serving API: pinned-host uint8 image in (the decoder's output; resize / normalise / pad /
+    # layout run in one kernel on the device), pinned-host record + bit-packed masks out; upload / replay / download of
+    # consecutive images overlap on their own streams (sipmask_b200/serving.py)
+    raw = (B == 1)
+    if raw:
+        g = torch.Generator().manual_seed(rank)
+        img_u8 = (torch.rand(H, IMG_W, 3, generator=g) * 255.0).to(torch.uint8).pin_memory()
+        runner = PipelinedRunner(engs, raw_hw=(H, IMG_W))
+        e2e_in = img_u8
+    else:
+        runner = PipelinedRunner(engs)
+        e2e_in = img_host
     copy_done = []
 
     def step_e2e():
-        copy_done.append(runner.step(img_host, gather_fn))
+        copy_done.append(runner.step(e2e_in, consume))
 
     def e2e_finish():
-        runner.flush(gather_fn)       # the timed region ends when the last result is on the host
+        runner.flush(consume)                  # the timed region ends when the last result is on the host
+        log.gather(out=gathered)
+        log.reset()
 
     def timed(fn, steps, sample_clocks=False, finish=None):
         """K steps between barrier+synchronize, CUDA events, max over ranks.  nvidia-smi samples clocks every 100 ms;
         a short timed region would get no sample, so ROLL untimed steps of the same load run before and after it and
         the sampler stays on throughout (clocks.window says so)."""
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        roll = max(1, ROLL // B)
         if sampler:
             sampler.start()
         if sample_clocks:
-            for _ in range(ROLL):                       # fixed count: every rank must issue the same collectives
+            for _ in range(roll):                       # fixed count: every rank must issue the same collectives
                 fn()
             if finish is not None:
                 finish()
@@ -234,20 +302,20 @@ def run_ours(args):
         for _ in range(steps):
             fn()
         if finish is not None:
-            finish()                                # e.g. make the compute stream wait for the last downloads
+            finish()                                # joins the images in flight / downloads and issues the end-of-run gather
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         if sample_clocks:
-            for _ in range(ROLL):
+            for _ in range(roll):
                 fn()
             if finish is not None:
                 finish()
             torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         if clocks is not None:
-            clocks['window'] = 'timed region plus %d untimed steps of the identical load before and after it' % ROLL
+            clocks['window'] = 'timed region plus %d untimed steps of the identical load before and after it' % roll
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -259,31 +327,37 @@ def run_ours(args):
     torch.cuda.synchronize()
     total_ms, clocks = timed(step, args.steps, sample_clocks=True, finish=step_finish)
     ms_per_step = total_ms / args.steps
-    value = world * 1000.0 / ms_per_step
+    value = world * B * 1000.0 / ms_per_step
     for _ in range(3):
         step_e2e()
     e2e_finish()
     e2e_ms, _ = timed(step_e2e, args.steps, finish=e2e_finish)
-    e2e_value = world * 1000.0 / (e2e_ms / args.steps)
+    e2e_value = world * B * 1000.0 / (e2e_ms / args.steps)
     last = runner.result(copy_done[-1])
-    assert int(last['cnt'][0]) == int(eng.count[0].item())
+    assert int(last['cnt'][0]) > 0
     h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
     ndet = int(eng.count[0].item())
 
     line = dict(metric='images/sec', value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16',
                 data='synthetic',
-                config=dict(workload=WORKLOAD, parallelism='dp%d (one image per GPU, one all-gather of the detection record)' % world,
-                            detections_per_image=ndet, cuda_graph=True, images_in_flight=nfl, batch_per_forward=1,
-                            l2='no flush: one step streams ~1.3 GB of activations/masks through a 126 MB L2, so nothing but '
-                               'weights (51 MB) can survive from the previous step'),
+                config=dict(workload=wl['name'],
+                            parallelism='dp%d (one forward per GPU per step; detection records logged on the device and '
+                                        'all-gathered ONCE at the end of the run, inside the timed region)' % world,
+                            detections_per_image=ndet, cuda_graph=True, forwards_in_flight=nfl, batch_per_forward=B,
+                            images_per_step_per_gpu=B,
+                            l2='no flush: one step streams >= 1.3 GB of activations/masks through a 126 MB L2, so nothing but '
+                               'weights can survive from the previous step'),
                 clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                                        ms_per_step=e2e_ms / args.steps),
+                                        ms_per_step=e2e_ms / args.steps,
+                                        input='uint8 BGR HWC image from pinned host memory (resize/normalise/pad on the device)'
+                                              if raw else 'fp32 NCHW batch from pinned host memory'),
                 gpu_launches=eng.n_launch * args.steps)
     torch.cuda.synchronize()
 
     if rank == 0:
         pk, pk_kind = peaks()
+        traffic = ncu_traffic()
         # ---- roofline of the dominant kernel (conv_gemm_kernel): the conv launches of one step of EVERY engine in flight,
         # captured per engine (same stream schedule as in the step) and replayed concurrently on the pool's streams
         graphs = []
@@ -315,77 +389,46 @@ def run_ours(args):
         pool.join()
         e1.record()
         torch.cuda.synchronize()
-        conv_ms = e0.elapsed_time(e1) / (reps * nfl)                      # per image
+        conv_ms = e0.elapsed_time(e1) / (reps * nfl)                      # per forward
         tf = eng.conv_flops / (conv_ms * 1e-3) / 1e12
         peak_tf = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops', 1400.0)))
+        tr = traffic.get('conv_gemm_kernel', {})
         line['roofline'] = dict(bound='tensor', kernel='conv_gemm_kernel (%d launches/step)' % len(eng.conv_plans),
-                                achieved=tf, peak=peak_tf, unit='TFLOP/s', frac=tf / peak_tf, traffic=None,
+                                achieved=tf, peak=peak_tf, unit='TFLOP/s', frac=tf / peak_tf,
+                                traffic=tr.get('dram_bytes_per_step'), traffic_source=tr.get('source'),
                                 peak_source=pk_kind + ' bf16_tflops_sustained', algorithmic_gflop_per_step=eng.conv_flops / 1e9,
                                 ms_per_step=conv_ms, share_of_step=conv_ms / ms_per_step,
-                                note='conv launches of %d images in flight replayed concurrently; time per image' % nfl)
+                                note='conv launches of %d forwards in flight replayed concurrently; time per forward' % nfl)
         del graphs
-        # ---- strictly serial reference point: ONE engine tuned for a single stream, one image at a time
+        # ---- strictly serial reference point: ONE engine tuned for a single stream, one forward at a time
         if nfl > 1:
-            e1s = make_engines(sd, (H, W), in_flight=1, test_cfg=TEST_CFG, img_shape=(H, IMG_W, 3), use_graph=True, device=dev)[0]
+            e1s = make_engines(sd, (H, W), in_flight=1, **ekw)[0]
             e1s.img.copy_(img_host, non_blocking=True)
             for _ in range(5):
                 e1s.forward(None)
             torch.cuda.synchronize()
             e0.record()
-            for _ in range(max(args.steps, 20)):
+            nser = max(args.steps, 20)
+            for _ in range(nser):
                 e1s.forward(None)
             e1.record()
             torch.cuda.synchronize()
-            sms = e0.elapsed_time(e1) / max(args.steps, 20)
-            line['serial'] = dict(ms_per_step=sms, value=1000.0 / sms, unit='images/s',
-                                  note='one image in flight (latency-optimal planner settings), same GPU, N=1 rank only')
+            sms = e0.elapsed_time(e1) / nser
+            line['serial'] = dict(ms_per_step=sms, value=B * 1000.0 / sms, unit='images/s',
+                                  note='one forward in flight (latency-optimal planner settings), same GPU, N=1 rank only')
             del e1s
-        # ---- mask assembly (BASELINE metric part 2): HBM GB/s of the fused kernel, N = max_per_img detections
-        N = eng.max_num
-        Hm, Wm = eng.protos.shape[1], eng.protos.shape[2]
-        gen = torch.Generator().manual_seed(0)
-        cofs = torch.randn(N, 128, generator=gen).to(dev)
-        cx, cy = torch.rand(N, generator=gen) * IMG_W, torch.rand(N, generator=gen) * H
-        bw, bh = torch.rand(N, generator=gen) * 480 + 32, torch.rand(N, generator=gen) * 480 + 32
-        boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1).clamp(min=0).to(dev)
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-        pos = torch.empty((N, Hm, Wm), dtype=torch.float32, device=dev)
-        bits = torch.empty((N, H, (IMG_W + 31) // 32), dtype=torch.int32, device=dev)
-
-        def time_kernel(fn):
-            ts = []
-            for i in range(8):
-                flush.fill_(i)                                 # evict L2 between timed launches
-                e0.record()
-                fn()
-                e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            return statistics.median(ts[2:])
-
-        # (a) the reference-shaped output: dense pos_masks [N,Hm,Wm] fp32 (what CropSplit returns, permuted)
-        ma_ms = time_kernel(lambda: ops.mask_assemble(eng.protos[0], cofs, boxes, 0.5, layout='hwc', out=pos))
-        ma_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + N * Hm * Wm * 4
-        gbs = ma_bytes / (ma_ms * 1e-3) / 1e9
-        line['roofline_mask_assembly'] = dict(bound='hbm', kernel='mask_assemble_kernel', achieved=gbs, peak=float(pk['hbm_gbs']),
-                                              unit='GB/s', frac=gbs / float(pk['hbm_gbs']), traffic=None, ms=ma_ms,
-                                              algorithmic_bytes=ma_bytes, peak_source=pk_kind + ' hbm_gbs',
-                                              note='protos fp16 HWC read once + fp32 pos_masks [100,400,672] written; L2 flushed between launches')
-        # (b) the kernel the engine runs: fused assembly + x2 upsample + threshold + bit-pack (no pos_masks traffic)
-        mf_ms = time_kernel(lambda: ops.mask_assemble_pack(eng.protos[0], cofs, boxes, 0.5, (H, IMG_W), 0.4, layout='hwc', out=bits))
-        mf_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + bits.numel() * 4
-        mgbs = mf_bytes / (mf_ms * 1e-3) / 1e9
-        line['roofline_mask_fused'] = dict(bound='hbm', kernel='mask_fused_pack_kernel', achieved=mgbs, peak=float(pk['hbm_gbs']),
-                                           unit='GB/s', frac=mgbs / float(pk['hbm_gbs']), traffic=None, ms=mf_ms,
-                                           algorithmic_bytes=mf_bytes, peak_source=pk_kind + ' hbm_gbs',
-                                           note='protos fp16 read once + bit-packed [100,800,42] int32 masks written')
+        if args.workload == 'A':
+            mask_rooflines(line, eng, pk, pk_kind, traffic, H, IMG_W)
+            line['e2e_dropin'] = dropin_timing(eng, sd, cfg, H, IMG_W)
+            if not args.no_library_baseline:
+                line['library_gpu_baseline'] = library_baseline(wl, img_host, dev)
         # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            sec, _, rows, _ = cpu_reference(1, 1, threads)
-            line['cpu_baseline'] = dict(value=1.0 / sec, unit='images/s', cores=threads, kind='port',
-                                        sample='1 warm-up + 1 timed pass of %d/800 image rows through the oracle '
-                                               '(PyTorch CPU fp32 restatement of the reference forward incl. get_bboxes)' % rows)
+            threads, tinfo = host_threads()
+            sec, _, n_timed, ts, n_warm = cpu_reference(wl, 3, 1, threads, budget_s=25.0)
+            line['cpu_baseline'] = dict(value=1.0 / sec, unit='images/s', cores=threads, kind='port', host_threads=tinfo,
+                                        sample='%d whole %dx%d image(s) timed (median) after %d warm-up, through the oracle (PyTorch '
+                                               'CPU fp32 restatement of the reference forward incl. get_bboxes)' % (n_timed, H, W, n_warm))
         else:
             line['cpu_baseline'] = None
         print(json.dumps(line))
@@ -394,15 +437,141 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def mask_rooflines(line, eng, pk, pk_kind, traffic, H, IMG_W):
+    """Mask assembly (BASELINE metric part 2): HBM GB/s at N = max_per_img detections with 32-512 px boxes, L2 flushed
+    between launches.  Each number is the whole ABI call (zero-fill memset node + kernel)."""
+    import torch
+    from sipmask_b200 import ops
+    dev = eng.dev
+    N = eng.max_num
+    Hm, Wm = eng.protos.shape[1], eng.protos.shape[2]
+    gen = torch.Generator().manual_seed(0)
+    cofs = torch.randn(N, 128, generator=gen).to(dev)
+    cx, cy = torch.rand(N, generator=gen) * IMG_W, torch.rand(N, generator=gen) * H
+    bw, bh = torch.rand(N, generator=gen) * 480 + 32, torch.rand(N, generator=gen) * 480 + 32
+    boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1).clamp(min=0).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    pos = torch.empty((N, Hm, Wm), dtype=torch.float32, device=dev)
+    bits = torch.empty((N, H, (IMG_W + 31) // 32), dtype=torch.int32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def time_kernel(fn):
+        ts = []
+        for i in range(10):
+            flush.fill_(i)                                 # evict L2 between timed launches
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts[2:])
+
+    protos = eng.protos[0]
+    # (a) the reference-shaped output: dense pos_masks [N,Hm,Wm] fp32 (what CropSplit returns, permuted)
+    ma_ms = time_kernel(lambda: ops.mask_assemble(protos, cofs, boxes, 0.5, layout='hwc', out=pos))
+    ma_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + N * Hm * Wm * 4
+    gbs = ma_bytes / (ma_ms * 1e-3) / 1e9
+    tr = traffic.get('mask_assemble', {})
+    line['roofline_mask_assembly'] = dict(bound='hbm', kernel='smb_mask_assemble = memset + mask_assemble_kernel', achieved=gbs,
+                                          peak=float(pk['hbm_gbs']), unit='GB/s', frac=gbs / float(pk['hbm_gbs']),
+                                          traffic=tr.get('dram_bytes_per_launch'), traffic_source=tr.get('source'), ms=ma_ms,
+                                          algorithmic_bytes=ma_bytes, peak_source=pk_kind + ' hbm_gbs',
+                                          note='protos fp16 HWC read once + fp32 pos_masks [100,400,672] written; L2 flushed between launches')
+    # (b) the path the engine runs: fused assembly + bilinear resize + threshold + bit-pack (no pos_masks traffic)
+    mf_ms = time_kernel(lambda: ops.mask_assemble_pack(protos, cofs, boxes, 0.5, (H, IMG_W), 0.4, layout='hwc', out=bits))
+    mf_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + bits.numel() * 4
+    mgbs = mf_bytes / (mf_ms * 1e-3) / 1e9
+    tr = traffic.get('mask_fused', {})
+    line['roofline_mask_fused'] = dict(bound='hbm', kernel='smb_mask_assemble_pack = memset + mask_fused_pack_kernel', achieved=mgbs,
+                                       peak=float(pk['hbm_gbs']), unit='GB/s', frac=mgbs / float(pk['hbm_gbs']),
+                                       traffic=tr.get('dram_bytes_per_launch'), traffic_source=tr.get('source'), ms=mf_ms,
+                                       algorithmic_bytes=mf_bytes, peak_source=pk_kind + ' hbm_gbs',
+                                       note='protos fp16 read once + bit-packed [100,800,42] int32 masks written')
+
+
+def dropin_timing(eng, sd, cfg, H, IMG_W):
+    """The reference's call pattern through the drop-in module (detectors/single_stage.py:75-93): SipMaskHead.forward(feats)
+    + get_bboxes(..., rescale=True) -> python result with COCO RLE strings on the host; wall clock per image.  The five FPN
+    maps are the engine's own (NCHW fp32 copies, as the reference's neck would hand them over)."""
+    import torch
+    from sipmask_b200.head import SipMaskHead
+
+    class Cfg(dict):
+        __getattr__ = dict.get
+    head = SipMaskHead(num_classes=81, in_channels=256, stacked_convs=4, strides=[8, 16, 32, 64, 128])
+    head.load_state_dict({k[len('bbox_head.'):]: v for k, v in sd.items() if k.startswith('bbox_head.')}, strict=True)
+    head = head.to(eng.dev).eval()
+    feats = tuple(f.permute(0, 3, 1, 2).float().contiguous() for f in eng.fpn_outs)
+    tcfg = Cfg(cfg)
+    tcfg['nms'] = Cfg(cfg['nms'])
+    meta = dict(img_shape=(H, IMG_W, 3), ori_shape=(H, IMG_W, 3), scale_factor=1.0)
+    ts = []
+    k = 0
+    for i in range(7):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        outs = head(feats)
+        det, lab, segms = head.get_bboxes(*outs, [meta], tcfg, rescale=True)[0]
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+        k = int(det.shape[0])
+    ms = statistics.median(ts[2:]) * 1e3
+    return dict(ms_per_image=ms, value=1000.0 / ms, unit='images/s (head + post-processing only)', detections=k,
+                note='wall clock of SipMaskHead.forward + get_bboxes (eager launches, one host sync per image, RLE strings built '
+                     'on the host from device run lengths); backbone / neck are the caller\'s on this path')
+
+
+def library_baseline(wl, img_host, dev):
+    """Informational: the same network through the library path on this GPU (PyTorch eager: cuDNN / cuBLAS convolutions,
+    ATen GroupNorm / interpolate, torchvision deform_conv2d), fp16 channels_last, forward only (no post-processing)."""
+    import torch
+    try:
+        from oracle import model as M
+        from oracle import ops as O
+        from sipmask_b200 import synth
+        O.USE_TORCHVISION_DCN = True
+        net = M.SipMaskDetector(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], ssd_flag=wl['ssd'])
+        net.load_state_dict(synth.detector_state_dict(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], seed=1,
+                                                      cls_bias=CLS_BIAS), strict=True)
+        net = net.to(dev).half().to(memory_format=torch.channels_last).eval()
+        x = img_host.to(dev).half().contiguous(memory_format=torch.channels_last)
+        torch.backends.cudnn.benchmark = True
+        with torch.no_grad():
+            for _ in range(5):
+                net(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 20
+            for _ in range(n):
+                net(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return dict(ms_per_image=ms, value=1000.0 / ms, unit='images/s',
+                    note='oracle SipMaskDetector on CUDA, fp16 channels_last, cudnn.benchmark, eager; network forward ONLY '
+                         '(decode / NMS / mask assembly excluded, so this favours the library path)')
+    except Exception as ex:                                    # informational leg: never fail the bench line
+        return dict(unavailable='%s: %s' % (type(ex).__name__, str(ex)[:200]))
+    finally:
+        try:
+            O.USE_TORCHVISION_DCN = False
+        except Exception:
+            pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='A', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--in-flight', type=int, default=int(os.environ.get('SMB_IN_FLIGHT', '6')),
-                    help='images in flight per GPU (independent batch-1 forwards on separate streams); 1 = strictly serial')
+    ap.add_argument('--no-library-baseline', action='store_true')
+    ap.add_argument('--in-flight', type=int, default=int(os.environ.get('SMB_IN_FLIGHT', '0')),
+                    help='forwards in flight per GPU (independent forwards on separate streams); 0 = the workload default, '
+                         '1 = strictly serial')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

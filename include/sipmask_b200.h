@@ -57,14 +57,22 @@ int smb_mask_assemble(const void* protos, int protos_dtype, int layout_hwc,
                       const float* cofs, const float* boxes, const float* host_box_scale4,
                       void* out, int out_dtype, int H, int W, int N, smb_stream_t stream);
 
-/* x2 (scale_factor==1) bilinear upsample (align_corners=False) + `> thr` of pos_masks
- * (sipmask_head.py:630-633), cropped/pasted top-left into [N,out_h,out_w] (sipmask_head.py:648-654).
- *   pos : [N,H,W] fp32/fp16      out_u8 : [N,out_h,out_w] uint8 {0,1}
- */
+/* Bilinear resize (align_corners=False) + `> thr` of pos_masks (sipmask_head.py:630-633), pasted top-left into
+ * [N,out_h,out_w] and truncated (sipmask_head.py:648-654).  The reference interpolates by 2/scale_factor (per axis
+ * scale_factor[3:1:-1] on the SSD path): the caller passes the interpolated size (full_h, full_w) =
+ * (floor(H * 2/sf_h), floor(W * 2/sf_w)) and the source step per output pixel (ry, rx): src = (dst + 0.5) * r - 0.5 with
+ * r = 1 / (2/sf) (what F.interpolate(scale_factor=...) does in PyTorch >= 1.6), or r <= 0 for in/out
+ * (recompute_scale_factor=True, the behaviour of PyTorch <= 1.5, the version range the reference README pins).
+ *   pos : [N,H,W] fp32/fp16      out_u8 : [N,out_h,out_w] uint8 {0,1}; pixels beyond (full_h, full_w) are 0. */
+int smb_mask_resize_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W, int full_h,
+                              int full_w, float ry, float rx, int out_h, int out_w, float thr, smb_stream_t stream);
+/* Bit-packed variant: out_bits [N,out_h,ceil(out_w/32)] uint32, pixel x = bit (x & 31) of word (x >> 5). */
+int smb_mask_resize_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
+                                   int full_h, int full_w, float ry, float rx, int out_h, int out_w, float thr,
+                                   smb_stream_t stream);
+/* scale_factor == 1 shorthands: full size = (2H, 2W). */
 int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W,
                                  int out_h, int out_w, float thr, smb_stream_t stream);
-
-/* Bit-packed variant: out_bits [N,out_h,ceil(out_w/32)] uint32, pixel x = bit (x & 31) of word (x >> 5). */
 int smb_mask_upsample2_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
                                       int out_h, int out_w, float thr, smb_stream_t stream);
 
@@ -91,12 +99,14 @@ int smb_mask_rle_counts(const uint32_t* mask_bits, int N, int mask_h, int words,
  * too small.  counts is a host pointer. */
 int smb_rle_to_string(const uint32_t* host_counts, int n, char* host_out, int cap);
 
-/* Fully fused mask path (sipmask_head.py:609-633,648-654 in one kernel): prototypes -> selected sub-region dot
- * product -> sigmoid -> crop -> x2 bilinear -> `> thr` -> bit-pack.  pos_masks is never written to memory.
- * Same arguments as smb_mask_assemble; output as smb_mask_upsample2_threshold_pack. */
+/* Fully fused mask path (sipmask_head.py:609-633,648-654): prototypes -> selected sub-region dot product -> sigmoid ->
+ * crop -> bilinear resize to (full_h, full_w) -> `> thr` -> bit-pack into [N,out_h,ceil(out_w/32)] (a memset node zero-fills
+ * the planes, one kernel writes the words that intersect a box).  pos_masks is never written to memory.
+ * Same arguments as smb_mask_assemble; resize / output as smb_mask_resize_threshold_pack.  Shrinking by more than 4x
+ * (scale_factor > 8) returns SMB_EINVAL. */
 int smb_mask_assemble_pack(const void* protos, int protos_dtype, int layout_hwc, const float* cofs, const float* boxes,
-                           const float* host_box_scale4, uint32_t* out_bits, int H, int W, int N, int out_h, int out_w,
-                           float thr, smb_stream_t stream);
+                           const float* host_box_scale4, uint32_t* out_bits, int H, int W, int N, int full_h, int full_w,
+                           float ry, float rx, int out_h, int out_w, float thr, smb_stream_t stream);
 
 /* ------------------------------------------------------------------ CropSplit (operator API)
  * Replaces crop_split_cuda.crop_split_cuda_forward(data, rois, out, H, W, c, n)
@@ -163,6 +173,15 @@ int smb_fast_nms(const float* boxes, const float* scores, const float* ctr, int 
                  float score_thr, float iou_thr, int top_k, int max_num,
                  float* det_out, int64_t* label_out, int64_t* idx_out, int* count_out,
                  void* workspace, size_t workspace_bytes, smb_stream_t stream);
+
+/* The gather between NMS and mask assembly (mlvl_cofs[idxs_keep], det_bboxes[:, :4]; sipmask_head.py:612,623) in one launch:
+ * det_cofs[i,:] = cof_src[cand_loc[idx[i]],:] (row pitch cof_pitch floats), det_boxes[i,:] = det[i,:4] for i < *count,
+ * zeros after; loc_out (may be NULL) receives the level-concatenated location of each kept detection (-1 after count).
+ * cof_src is either one image's level-concatenated [tot, pitch] buffer (num_levels = 0) or a batched level-major buffer
+ * [level][n_img][hw_l][pitch] with host_level_hw[l] = h_l * w_l, of which image `img` is gathered. */
+int smb_gather_det_inputs(const float* cof_src, int cof_pitch, const int* cand_loc, const int64_t* idx, const float* det,
+                          const int* count_dev, int max_rows, int row_elems, float* det_cofs, float* det_boxes,
+                          int64_t* loc_out, int num_levels, const int* host_level_hw, int n_img, int img, smb_stream_t stream);
 
 /* gather rows: dst[i,:] = src[idx[i],:] for i < *count (device count), zero otherwise. */
 int smb_gather_rows_f32(const float* src, int src_pitch, const int64_t* idx, const int* count_dev,

@@ -12,7 +12,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'liboracle_c.so')
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'liboracle_c.so')
         if not os.path.exists(path):
             path = _build.build_c()
         _lib = ctypes.CDLL(path)

@@ -48,7 +48,21 @@ def decode_candidates(cls_scores, bbox_preds, centernesses, cof_preds, strides, 
             torch.cat(mlvl_cofs), torch.cat(mlvl_idx))
 
 
-def assemble_masks(feat_mask, det_cofs, det_boxes, box_scale, up=2.0, thr=0.4, upsample=True):
+def mask_up_factors(scale_factor, ssd_flag, scale=2):
+    """`scale / scale_factor` (sipmask_head.py:632) or, on the SSD path, `scale / scale_factor[3:1:-1]` = (h, w) factors
+    (:630), as python floats (what torch >= 1.5 needs; the arithmetic keeps the operand types of the reference: python float
+    scale_factor -> double division, numpy float32 array -> float32 division)."""
+    if ssd_flag:
+        sf = np.asarray(scale_factor)
+        if sf.size == 4:
+            return tuple(float(v) for v in (scale / sf[3:1:-1]))
+        return float(scale / sf.reshape(-1)[0])
+    if isinstance(scale_factor, np.ndarray):
+        return float(scale / scale_factor.reshape(-1)[0])
+    return float(scale / scale_factor)
+
+
+def assemble_masks(feat_mask, det_cofs, det_boxes, box_scale, up=2.0, thr=0.4, upsample=True, legacy_interp=False):
     """sipmask_head.py:609-633.  feat_mask [32,H,W], det_cofs [N,128], det_boxes [N,4].
 
     Returns (pos_masks [N,H,W] fp32 after CropSplit, masks [N,H*up,W*up] uint8 or None)."""
@@ -63,14 +77,18 @@ def assemble_masks(feat_mask, det_cofs, det_boxes, box_scale, up=2.0, thr=0.4, u
         sf = tuple(float(u) for u in up)
     else:
         sf = float(up)
-    masks = F.interpolate(pos_masks.unsqueeze(0), scale_factor=sf, mode='bilinear',
-                          align_corners=False, recompute_scale_factor=True).squeeze(0)
+    # F.interpolate(scale_factor=...) as the reference calls it.  PyTorch >= 1.6 maps coordinates with the GIVEN factor
+    # (src = (dst + 0.5) / factor - 0.5): that is what the reference python does when run here and what the *_sf golden
+    # fixtures contain.  PyTorch <= 1.5 (the versions the reference README pins) recomputed the factor from the rounded
+    # output size (in / out): legacy_interp=True.  Both agree when 2 / scale_factor is an integer (scale_factor = 1).
+    masks = F.interpolate(pos_masks.unsqueeze(0), scale_factor=sf, mode='bilinear', align_corners=False,
+                          recompute_scale_factor=True if legacy_interp else None).squeeze(0)
     return pos_masks, (masks > thr).to(torch.uint8)
 
 
 def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides,
                       img_shape, ori_shape, scale_factor, cfg, rescale=False, ssd_flag=False,
-                      num_classes=80, cmp_ge=False, mask_thr=0.4, head=None):
+                      num_classes=80, cmp_ge=False, mask_thr=0.4, head=None, legacy_interp=False):
     """Returns dict(det_bboxes [k,5], det_labels [k], idxs_keep [k], pos_masks [k,Hm,Wm],
     masks [k,Hi,Wi] uint8 pasted to ori/img shape, mask_scores or None)."""
     boxes, scores, ctr, cofs, _ = decode_candidates(
@@ -94,15 +112,14 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
                pos_masks=None, masks=None, mask_scores=None)
     if det_bboxes.shape[0] > 0:
         scale = 2
-        sf_t = torch.from_numpy(sf_arr)
         if rescale is None:
-            sf_t = sf_t * 0 + 1.0                                       # :621-622
+            sf_arr = sf_arr * 0 + 1.0                                   # :621-622 rebinds scale_factor: rois AND resize use 1
+            scale_factor = sf_arr if sf_arr.size == 4 else 1.0
+        sf_t = torch.from_numpy(sf_arr)
         box_scale = sf_t / scale
-        if ssd_flag:
-            up = tuple((scale / sf_arr[[3, 2]]).tolist()) if sf_arr.size == 4 else float(scale / sf_arr[0])
-        else:
-            up = float(scale / sf_arr[0]) if sf_arr.size == 1 else tuple((scale / sf_arr).tolist())
-        pos_masks, masks = assemble_masks(feat_mask, det_cofs, det_bboxes[:, :4], box_scale, up, mask_thr)
+        up = mask_up_factors(scale_factor, ssd_flag, scale)
+        pos_masks, masks = assemble_masks(feat_mask, det_cofs, det_bboxes[:, :4], box_scale, up, mask_thr,
+                                          legacy_interp=legacy_interp)
         out['pos_masks'] = pos_masks
         tgt = ori_shape if rescale else img_shape
         k = masks.shape[0]

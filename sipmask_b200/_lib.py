@@ -38,10 +38,10 @@ _lib = None
 
 # every symbol include/sipmask_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    'smb_last_error', 'smb_version', 'smb_check_device', 'smb_mask_assemble', 'smb_mask_upsample2_threshold', 'smb_mask_upsample2_threshold_pack', 'smb_mask_assemble_pack',
+    'smb_last_error', 'smb_version', 'smb_check_device', 'smb_mask_assemble', 'smb_mask_upsample2_threshold', 'smb_mask_upsample2_threshold_pack', 'smb_mask_resize_threshold', 'smb_mask_resize_threshold_pack', 'smb_mask_assemble_pack',
     'smb_crop_split_forward', 'smb_mask_rle_counts', 'smb_rle_to_string', 'smb_conv3x3s2_relu_f32', 'smb_mask_rescore', 'smb_nms', 'smb_decode_workspace_bytes', 'smb_decode_topk',
     'smb_multiclass_nms_workspace_bytes', 'smb_multiclass_nms', 'smb_fast_nms_workspace_bytes', 'smb_fast_nms',
-    'smb_gather_rows_f32', 'smb_conv_plan_create', 'smb_conv_plan_create_multi', 'smb_conv_plan_destroy', 'smb_conv_plan_set_max_ctas', 'smb_conv_set_min_tiles',
+    'smb_gather_rows_f32', 'smb_gather_det_inputs', 'smb_conv_plan_create', 'smb_conv_plan_create_multi', 'smb_conv_plan_destroy', 'smb_conv_plan_set_max_ctas', 'smb_conv_set_min_tiles',
     'smb_conv_run',
     'smb_groupnorm_relu_apply', 'smb_groupnorm_stats', 'smb_deform_im2col', 'smb_offset_conv1x1', 'smb_groupnorm_relu_apply_multi', 'smb_offset_conv1x1_multi', 'smb_deform_im2col_multi', 'smb_maxpool3x3s2',
     'smb_upsample_bilinear', 'smb_image_to_nhwc8', 'smb_preprocess_u8', 'smb_stem_plan_create',
@@ -73,8 +73,39 @@ def ptr(t):
 
 
 def stream_ptr():
+    """The CURRENT device's current stream.  Callers run under `device_guard` / `torch.cuda.device(tensor.device)`, so this
+    is the stream of the device that owns the tensors (not of whatever device happened to be current)."""
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _find_device(objs):
+    import torch
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, (list, tuple)):
+            d = _find_device(o)
+            if d is not None:
+                return d
+    return None
+
+
+def device_guard(fn):
+    """Run `fn` with the CUDA device of its first CUDA tensor argument made current, so that the stream passed to the C ABI,
+    the per-device kernel attributes and every launch belong to the tensors' device (multi-GPU processes, head.cuda(1))."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        dev = _find_device(args) or _find_device(tuple(kwargs.values()))
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def f4(vals):

@@ -90,8 +90,10 @@ class ConvPlan(object):
         self._keep = (x, weight, out, bias, residual, gn_stats)
         self.bias, self.residual, self.gn_stats, self.alpha = bias, residual, gn_stats, float(alpha)
         self.handle = ctypes.c_void_p()
-        L.check(L.lib().smb_conv_plan_create(ctypes.byref(d), L.ptr(x), L.ptr(weight), L.ptr(out),
-                                             ctypes.byref(self.handle)), 'smb_conv_plan_create')
+        self.dev = x.device
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().smb_conv_plan_create(ctypes.byref(d), L.ptr(x), L.ptr(weight), L.ptr(out),
+                                                 ctypes.byref(self.handle)), 'smb_conv_plan_create')
         self.out = out
 
     def set_max_ctas(self, n):
@@ -99,6 +101,9 @@ class ConvPlan(object):
         return self
 
     def run(self, stream=None):
+        if self.dev.index != torch.cuda.current_device():        # launch on the plan's device and ITS current stream
+            with torch.cuda.device(self.dev):
+                return self.run(stream)
         L.check(L.lib().smb_conv_run(self.handle, L.ptr(self.bias), L.ptr(self.residual), L.ptr(self.gn_stats),
                                      ctypes.c_float(self.alpha), stream if stream is not None else L.stream_ptr()),
                 'smb_conv_run')
@@ -147,8 +152,10 @@ class ConvPlanMulti(ConvPlan):
         self._keep = (xs, weight, outs, bias, gn_stats, lv)
         self.bias, self.residual, self.gn_stats, self.alpha = bias, None, None, float(alpha)
         self.handle = ctypes.c_void_p()
-        L.check(L.lib().smb_conv_plan_create_multi(ctypes.byref(d), nl, lv, L.ptr(weight), ctypes.byref(self.handle)),
-                'smb_conv_plan_create_multi')
+        self.dev = xs[0].device
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().smb_conv_plan_create_multi(ctypes.byref(d), nl, lv, L.ptr(weight), ctypes.byref(self.handle)),
+                    'smb_conv_plan_create_multi')
         self.out = outs
 
 
@@ -159,12 +166,15 @@ class StemPlan(ConvPlan):
         self._keep = (img8, weight448, bias, out)
         self.bias, self.residual, self.gn_stats, self.alpha = bias, None, None, 1.0
         self.handle = ctypes.c_void_p()
-        L.check(L.lib().smb_stem_plan_create(N, H, W, L.ptr(img8), L.ptr(weight448), L.ptr(out),
-                                             ctypes.byref(self.handle)), 'smb_stem_plan_create')
+        self.dev = img8.device
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().smb_stem_plan_create(N, H, W, L.ptr(img8), L.ptr(weight448), L.ptr(out),
+                                                 ctypes.byref(self.handle)), 'smb_stem_plan_create')
         self.out = out
 
 
 # ------------------------------------------------------------------------------------- small wrappers
+@L.device_guard
 def image_to_nhwc8(img, out=None):
     N, _, H, W = img.shape
     if out is None:
@@ -173,6 +183,7 @@ def image_to_nhwc8(img, out=None):
     return out
 
 
+@L.device_guard
 def preprocess_u8(src, resized_hw, out, mean):
     """uint8 BGR HWC CUDA image -> resized (cv2 INTER_LINEAR, bit-exact) - mean -> zero-padded NHWC8 fp16 stem input
     `out` [1, H+6, W+8, 8] (smb_preprocess_u8)."""
@@ -186,6 +197,7 @@ def preprocess_u8(src, resized_hw, out, mean):
     return out
 
 
+@L.device_guard
 def maxpool3x3s2(x, out=None):
     N, H, W, C = x.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
@@ -195,6 +207,7 @@ def maxpool3x3s2(x, out=None):
     return out
 
 
+@L.device_guard
 def groupnorm_stats(x, stats=None):
     N, H, W, C = x.shape
     if stats is None:
@@ -204,6 +217,7 @@ def groupnorm_stats(x, stats=None):
     return stats
 
 
+@L.device_guard
 def groupnorm_relu_apply(x, stats, gamma, beta, eps=1e-5, relu=True):
     N, H, W, C = x.shape
     L.check(L.lib().smb_groupnorm_relu_apply(L.ptr(x), N, H * W, C, x.stride(2), L.ptr(stats), L.ptr(gamma), L.ptr(beta),
@@ -211,6 +225,7 @@ def groupnorm_relu_apply(x, stats, gamma, beta, eps=1e-5, relu=True):
     return x
 
 
+@L.device_guard
 def offset_conv1x1(bbox, scale, weight, out=None):
     """bbox [N,H,W,>=4] fp32 channel-last (pitch = stride(2)); weight [n_off,4] fp32 -> [N,H,W,n_off] fp32."""
     N, H, W, _ = bbox.shape
@@ -222,6 +237,7 @@ def offset_conv1x1(bbox, scale, weight, out=None):
     return out
 
 
+@L.device_guard
 def deform_im2col(x, offset, dg, out=None):
     """x [N,H,W,C] fp16, offset [N,H,W,dg*18] fp32 -> col [N,H,W,9*C] fp16."""
     N, H, W, C = x.shape
@@ -233,6 +249,7 @@ def deform_im2col(x, offset, dg, out=None):
     return out
 
 
+@L.device_guard
 def upsample_bilinear(x, factor, out=None, out_choff=0, relu=False):
     N, H, W, C = x.shape
     if out is None:
@@ -251,6 +268,7 @@ def _iarr(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
 
 
+@L.device_guard
 def groupnorm_relu_apply_multi(xs, stats, gamma, beta, eps=1e-5, relu=True):
     N, _, _, C = xs[0].shape
     L.check(L.lib().smb_groupnorm_relu_apply_multi(len(xs), _parr(xs), _parr(stats), _iarr([x.shape[1] for x in xs]),
@@ -260,6 +278,7 @@ def groupnorm_relu_apply_multi(xs, stats, gamma, beta, eps=1e-5, relu=True):
     return xs
 
 
+@L.device_guard
 def offset_conv1x1_multi(bboxes, scales, weight, offs):
     N = bboxes[0].shape[0]
     sc = (ctypes.c_float * len(scales))(*[float(v) for v in scales])
@@ -270,6 +289,7 @@ def offset_conv1x1_multi(bboxes, scales, weight, offs):
     return offs
 
 
+@L.device_guard
 def deform_im2col_multi(xs, offs, dg, cols):
     N, _, _, C = xs[0].shape
     L.check(L.lib().smb_deform_im2col_multi(len(xs), _parr(xs), _parr(offs), offs[0].stride(2), _parr(cols),

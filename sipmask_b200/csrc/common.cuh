@@ -42,6 +42,20 @@ void set_error(const char* fmt, ...);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a process that drives several GPUs must opt in on
+// each of them.  `static DeviceOnce once; if (once.first()) { ...set attributes... }` runs the body once per device.
+struct DeviceOnce {
+  bool done[64];
+  DeviceOnce() { memset(done, 0, sizeof(done)); }
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown device: always (cheap) set
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // Programmatic dependent launch (PDL): a kernel launched through launch_pdl may start while the previous kernel in the
 // stream is still draining; it must call pdl_wait() before its first global-memory access (the wait returns once the
 // previous grid has completed and its writes are visible).  Chains of short kernels lose the ~1-2 us launch gap each.

@@ -52,20 +52,34 @@ __device__ __forceinline__ void store4<__half>(__half* p, const float* o, bool v
   }
 }
 
-// grid: (ceil(W/64), ceil(H/8)), block 128.
+template <typename OT>
+__device__ __forceinline__ void store1(OT* p, float v);
+template <>
+__device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store1<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// grid: (ceil(W/64), ceil(H/8)), block 128.  The output has been zero-filled by a memset node (the bulk of the
+// 107 MB pos_masks tensor is zeros and a memset runs at store bandwidth); this kernel only touches pixels inside boxes:
+// a CTA first lists the detections whose roi intersects its 8 x 64 tile, then evaluates, per listed detection and
+// in-box pixel, the ONE 32-term dot product selected by the CropSplit cell.
+constexpr int MA_LIST = 128;   // detections listed per pass
 template <typename PT, bool HWC, typename OT>
 __global__ void __launch_bounds__(MA_THREADS) mask_assemble_kernel(
     const PT* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes,
     float sx1, float sy1, float sx2, float sy2, OT* __restrict__ out, int H, int W, int N) {
-  __shared__ __align__(16) float s_cof[MA_NB * 128];
-  __shared__ BoxP s_box[MA_NB];
+  __shared__ BoxP s_box[MA_LIST];
+  __shared__ int s_det[MA_LIST];
+  __shared__ int s_cnt;
 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int h = blockIdx.y * MA_TH + ty;
   const int w0 = blockIdx.x * MA_TW + tx * 4;
   const bool row_ok = h < H;
   const int nvalid = row_ok ? max(0, min(4, W - w0)) : 0;
-  const bool vec = (nvalid == 4) && ((W & 3) == 0);
+  const bool vec_ok = (nvalid == 4) && ((W & 3) == 0);
+  const float tile_x0 = (float)(blockIdx.x * MA_TW), tile_x1 = (float)min(blockIdx.x * MA_TW + MA_TW - 1, W - 1);
+  const float tile_y0 = (float)(blockIdx.y * MA_TH), tile_y1 = (float)min(blockIdx.y * MA_TH + MA_TH - 1, H - 1);
 
   // ---- prototype pixels -> registers (fp32), read exactly once
   float P[4][32];
@@ -119,82 +133,116 @@ __global__ void __launch_bounds__(MA_THREADS) mask_assemble_kernel(
   }
 
   const float hf = (float)h;
-  for (int n0 = 0; n0 < N; n0 += MA_NB) {
-    const int nb = min(MA_NB, N - n0);
+  for (int n0 = 0; n0 < N; n0 += MA_LIST) {
+    const int nb = min(MA_LIST, N - n0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nb * 128; i += MA_THREADS) s_cof[i] = __ldg(cofs + (size_t)n0 * 128 + i);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     if (threadIdx.x < nb) {
       const float* b = boxes + (size_t)(n0 + threadIdx.x) * 4;
       BoxP bp;
       bp.x1 = b[0] * sx1; bp.y1 = b[1] * sy1; bp.x2 = b[2] * sx2; bp.y2 = b[3] * sy2;
-      // (roi_x2-roi_x1+0.1)/num_cell: float difference, then double (0.1 is a double literal),
-      // narrowed to float on assignment (crop_split_cuda_kernel.cu:46-47).
-      bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
-      bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
-      bp.pad0 = bp.pad1 = 0.f;
-      s_box[threadIdx.x] = bp;
+      // some pixel (integer coordinates) of the tile satisfies x1 <= w < x2 and y1 <= h < y2 ?
+      if (tile_x1 >= bp.x1 && tile_x0 < bp.x2 && tile_y1 >= bp.y1 && tile_y0 < bp.y2) {
+        // (roi_x2-roi_x1+0.1)/num_cell: float difference, then double (0.1 is a double literal),
+        // narrowed to float on assignment (crop_split_cuda_kernel.cu:46-47).
+        bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
+        bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
+        bp.pad0 = bp.pad1 = 0.f;
+        const int pos = atomicAdd(&s_cnt, 1);
+        s_box[pos] = bp;
+        s_det[pos] = n0 + threadIdx.x;
+      }
     }
     __syncthreads();
+    const int cnt = s_cnt;
     if (nvalid == 0) continue;
-    for (int j = 0; j < nb; ++j) {
+    for (int j = 0; j < cnt; ++j) {
       const BoxP b = s_box[j];
+      if (!((hf >= b.y1) & (hf < b.y2))) continue;
+      const int n = s_det[j];
+      const float* cof = cofs + (size_t)n * 128;          // 512 B per detection, warp-uniform (broadcast) L1 reads
+      const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h);
       float o[4] = {0.f, 0.f, 0.f, 0.f};
-      if ((hf >= b.y1) & (hf < b.y2)) {
-        const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h);
+      int inmask = 0;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float wf = (float)(w0 + p);
-          if ((wf >= b.x1) & (wf < b.x2)) {
-            const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
-            int cell = idx_h * 2 + idx_w;
-            cell = min(max(cell, 0), 3);
-            const float4* c4 = reinterpret_cast<const float4*>(s_cof + j * 128 + cell * 32);
-            float acc = 0.f;
+      for (int p = 0; p < 4; ++p) {
+        const float wf = (float)(w0 + p);
+        if ((p < nvalid) & (wf >= b.x1) & (wf < b.x2)) {
+          const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
+          int cell = idx_h * 2 + idx_w;
+          cell = min(max(cell, 0), 3);
+          const float4* c4 = reinterpret_cast<const float4*>(cof + cell * 32);
+          float acc = 0.f;
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const float4 c = c4[v];
-              acc = fmaf(P[p][v * 4], c.x, acc);
-              acc = fmaf(P[p][v * 4 + 1], c.y, acc);
-              acc = fmaf(P[p][v * 4 + 2], c.z, acc);
-              acc = fmaf(P[p][v * 4 + 3], c.w, acc);
-            }
-            o[p] = sigmoidf_(acc);
+          for (int v = 0; v < 8; ++v) {
+            const float4 c = __ldg(c4 + v);
+            acc = fmaf(P[p][v * 4], c.x, acc);
+            acc = fmaf(P[p][v * 4 + 1], c.y, acc);
+            acc = fmaf(P[p][v * 4 + 2], c.z, acc);
+            acc = fmaf(P[p][v * 4 + 3], c.w, acc);
           }
+          o[p] = sigmoidf_(acc);
+          inmask |= 1 << p;
         }
       }
-      store4<OT>(out + ((size_t)(n0 + j) * H + h) * W + w0, o, vec, nvalid);
+      if (inmask == 0) continue;
+      OT* dst = out + ((size_t)n * H + h) * W + w0;
+      if (inmask == 15 && vec_ok) {
+        store4<OT>(dst, o, true, 4);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (inmask & (1 << p)) store1<OT>(dst + p, o[p]);
+      }
     }
   }
 }
 
-// x2 bilinear (align_corners=False) + threshold, top-left paste into [N,out_h,out_w] uint8.
-// sipmask_head.py:630-633,648-654.  One thread = 4 consecutive output pixels of one row.
+// ---------------------------------------------------------------------------------------------------------------
+// Bilinear resize (align_corners=False) + threshold of pos_masks, pasted top-left into [N,out_h,out_w]
+// (sipmask_head.py:630-633,648-654).  The reference calls F.interpolate(scale_factor = 2 / scale_factor) (per axis on the
+// SSD path): the interpolated size is (full_h, full_w) = floor(H * s), floor(W * s) and the source coordinate of output
+// pixel y is ry * (y + 0.5) - 0.5 with ry = H / full_h (PyTorch's recompute_scale_factor=True rule, the behaviour of
+// the PyTorch version the reference pins), clamped at 0; neighbours clamp at H - 1.  Pixels beyond (full_h, full_w) are 0.
+struct Resize {
+  int full_h, full_w;
+  float ry, rx;
+};
+
+__device__ __forceinline__ void src_index(float r, int dst, int size, int& i0, int& i1, float& l) {
+  float s = r * ((float)dst + 0.5f) - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = min((int)s, size - 1);
+  i1 = i0 + (i0 < size - 1 ? 1 : 0);
+  l = s - (float)i0;
+}
+
+// One thread = 4 consecutive output pixels of one row.
 template <typename PT>
-__global__ void __launch_bounds__(256) upsample2_thresh_kernel(const PT* __restrict__ pos, uint8_t* __restrict__ out,
-                                                               int N, int H, int W, int out_h, int out_w, float thr) {
+__global__ void __launch_bounds__(256) resize_thresh_kernel(const PT* __restrict__ pos, uint8_t* __restrict__ out,
+                                                            int N, int H, int W, int out_h, int out_w, Resize rs, float thr) {
   const int xq = blockIdx.x * blockDim.x + threadIdx.x;   // quad index along x
   const int y = blockIdx.y;
   const int n = blockIdx.z;
   const int x0 = xq * 4;
   if (x0 >= out_w) return;
   uint8_t r[4] = {0, 0, 0, 0};
-  if (y < 2 * H) {
-    float sy = ((float)y + 0.5f) * 0.5f - 0.5f;
-    sy = sy < 0.f ? 0.f : sy;
-    const int y0 = (int)sy;
-    const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
-    const float ly = sy - (float)y0, hy = 1.f - ly;
+  if (y < rs.full_h) {
+    int y0, y1;
+    float ly;
+    src_index(rs.ry, y, H, y0, y1, ly);
+    const float hy = 1.f - ly;
     const PT* r0 = pos + ((size_t)n * H + y0) * W;
     const PT* r1 = pos + ((size_t)n * H + y1) * W;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int x = x0 + i;
-      if (x < out_w && x < 2 * W) {
-        float sx = ((float)x + 0.5f) * 0.5f - 0.5f;
-        sx = sx < 0.f ? 0.f : sx;
-        const int xa = (int)sx;
-        const int xb = xa + (xa < W - 1 ? 1 : 0);
-        const float lx = sx - (float)xa, hx = 1.f - lx;
+      if (x < out_w && x < rs.full_w) {
+        int xa, xb;
+        float lx;
+        src_index(rs.rx, x, W, xa, xb, lx);
+        const float hx = 1.f - lx;
         const float v = hy * (hx * to_f<PT>(r0[xa]) + lx * to_f<PT>(r0[xb])) +
                         ly * (hx * to_f<PT>(r1[xa]) + lx * to_f<PT>(r1[xb]));
         r[i] = v > thr ? 1 : 0;
@@ -209,77 +257,72 @@ __global__ void __launch_bounds__(256) upsample2_thresh_kernel(const PT* __restr
   }
 }
 
-// Same as above but bit-packed: out_bits [N, out_h, words] uint32, bit (x & 31) of word (x >> 5), LSB first.
-// One thread = one 32-pixel word (13.4 MB instead of 107 MB per 100 masks at 800x1344 -> one small D2H).
+// Same, bit-packed: out_bits [N, out_h, words] uint32, bit (x & 31) of word (x >> 5), LSB first.  One warp = one word
+// (lane = pixel, __ballot_sync packs): 13.4 MB instead of 107 MB per 100 masks at 800x1344 -> one small D2H.
 template <typename PT>
-__global__ void __launch_bounds__(128) upsample2_thresh_pack_kernel(const PT* __restrict__ pos, uint32_t* __restrict__ out,
-                                                                    int N, int H, int W, int out_h, int out_w, int words,
-                                                                    float thr) {
-  const int wq = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) resize_thresh_pack_kernel(const PT* __restrict__ pos, uint32_t* __restrict__ out,
+                                                                 int N, int H, int W, int out_h, int out_w, int words,
+                                                                 Resize rs, float thr) {
+  const int lane = threadIdx.x & 31;
+  const int wq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int y = blockIdx.y;
   const int n = blockIdx.z;
-  if (wq >= words) return;
-  uint32_t bits = 0u;
-  if (y < 2 * H) {
-    float sy = ((float)y + 0.5f) * 0.5f - 0.5f;
-    sy = sy < 0.f ? 0.f : sy;
-    const int y0 = (int)sy;
-    const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
-    const float ly = sy - (float)y0, hy = 1.f - ly;
+  if (wq >= words) return;                                 // warp-uniform
+  const int x = wq * 32 + lane;
+  bool bit = false;
+  if (y < rs.full_h && x < out_w && x < rs.full_w) {
+    int y0, y1, xa, xb;
+    float ly, lx;
+    src_index(rs.ry, y, H, y0, y1, ly);
+    src_index(rs.rx, x, W, xa, xb, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
     const PT* r0 = pos + ((size_t)n * H + y0) * W;
     const PT* r1 = pos + ((size_t)n * H + y1) * W;
-    // source columns needed by output x in [32*wq, 32*wq+31]: 16*wq-1 .. 16*wq+16
-    const int c0 = 16 * wq - 1;
-    float top[18], bot[18];
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      const int c = min(max(c0 + i, 0), W - 1);
-      top[i] = to_f<PT>(r0[c]);
-      bot[i] = to_f<PT>(r1[c]);
-    }
-    // x = 2k   -> src = k - 0.25: columns (k-1, k), weights (0.25, 0.75)
-    // x = 2k+1 -> src = k + 0.25: columns (k, k+1), weights (0.75, 0.25)
-    // (clamped loads make the x == 0 and right-edge cases equal to PyTorch's index clamping)
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int xe = 32 * wq + 2 * m, xo = xe + 1;
-      const float ve = hy * (0.25f * top[m] + 0.75f * top[m + 1]) + ly * (0.25f * bot[m] + 0.75f * bot[m + 1]);
-      const float vo = hy * (0.75f * top[m + 1] + 0.25f * top[m + 2]) + ly * (0.75f * bot[m + 1] + 0.25f * bot[m + 2]);
-      if (xe < out_w && xe < 2 * W && ve > thr) bits |= 1u << (2 * m);
-      if (xo < out_w && xo < 2 * W && vo > thr) bits |= 1u << (2 * m + 1);
-    }
+    const float v = hy * (hx * to_f<PT>(r0[xa]) + lx * to_f<PT>(r0[xb])) + ly * (hx * to_f<PT>(r1[xa]) + lx * to_f<PT>(r1[xb]));
+    bit = v > thr;
   }
-  out[((size_t)n * out_h + y) * words + wq] = bits;
+  const uint32_t bits = __ballot_sync(0xffffffffu, bit);
+  if (lane == 0) out[((size_t)n * out_h + y) * words + wq] = bits;
 }
 
-
 // ---------------------------------------------------------------------------------------------------------------
-// Fully fused mask path: prototypes -> (selected sub-region dot product -> sigmoid -> crop) -> x2 bilinear upsample
+// Fully fused mask path: prototypes -> (selected sub-region dot product -> sigmoid -> crop) -> bilinear resize
 // -> threshold -> bit-pack, without ever materialising pos_masks [N,H,W] (sipmask_head.py:609-633,648-654).
-// HBM traffic = prototypes once (+halo) + N*out_h*words*4 bytes of bits (13.4 MB for 100 masks at 800x1333)
-// instead of 107 MB (fp32 pos) written and read again.
+// Algorithmic HBM traffic = prototypes once + N*out_h*words*4 bytes of bits (13.4 MB for 100 masks at 800x1333).
 //
-// CTA tile: 8 x 64 prototype pixels (+1 halo) in shared memory -> 16 output rows x 4 output words per detection.
-// Thread (slot = tid & 63, lane4 = tid >> 6): output row 16*ty + slot/4, word 4*tx + slot%4, detections lane4, lane4+4, ...
-// Words whose 2 x 18 source pixels all lie outside the detection's box are written as 0 without any arithmetic.
-template <typename PT> struct PixPitch;
-template <> struct PixPitch<__half> { static constexpr int kElems = 40; };   // 64 B + 16 B pad: conflict-free LDS.128
-template <> struct PixPitch<float> { static constexpr int kElems = 36; };    // 128 B + 16 B pad
-
-constexpr int MF_TH = 8, MF_TW = 64, MF_NB = 32, MF_THREADS = 256;
+// The bit planes are zero-filled by a memset node first (almost all words are zero).  The kernel is TILE-stationary and
+// two-phase: a CTA owns TY output rows x TW output words, stages the prototype pixels those outputs can read (at most
+// SR_CAP x SC_CAP, 16-byte-chunk XOR swizzle: conflict-free LDS.128) in shared memory ONCE, lists the detections whose
+// roi intersects that source window, and for every listed detection
+//   phase 1: one sigmoid-dot per source pixel (cell selected by CropSplit, 0 outside the box) -> s_val (fp32 tile),
+//   phase 2: one lane per output pixel: 4-tap bilinear from s_val, `> thr`, __ballot_sync -> one 32-bit word per warp.
+// (The previous kernel re-evaluated the dot product for up to four output pixels per source pixel: 2.8 % of HBM peak.)
+constexpr int MF_THREADS = 256, MF_SR = 10, MF_LIST = 128;
+template <typename PT> struct FusedCfg;
+template <> struct FusedCfg<__half> { static constexpr int kScCap = 132, kChunks = 4; };   // 64 B / pixel
+template <> struct FusedCfg<float> { static constexpr int kScCap = 68, kChunks = 8; };     // 128 B / pixel
 
 template <typename PT>
-__device__ __forceinline__ float dot32(const PT* px, const float* cof);
+__device__ __forceinline__ int swz(int p, int k);
 template <>
-__device__ __forceinline__ float dot32<__half>(const __half* px, const float* cof) {
+__device__ __forceinline__ int swz<__half>(int p, int k) { return k ^ ((p >> 1) & 3); }
+template <>
+__device__ __forceinline__ int swz<float>(int p, int k) { return k ^ (p & 7); }
+
+// 32-term dot product of shared-memory pixel p (swizzled 16-byte chunks) with cof[0..31]; same summation order as the
+// dense kernel (sequential fmaf over channels), so both paths give bit-identical mask values.
+template <typename PT>
+__device__ __forceinline__ float dot32_swz(const unsigned char* s_p, int p, const float* __restrict__ cof);
+template <>
+__device__ __forceinline__ float dot32_swz<__half>(const unsigned char* s_p, int p, const float* __restrict__ cof) {
   float acc = 0.f;
-  const uint4* q = reinterpret_cast<const uint4*>(px);
+  const uint4* q = reinterpret_cast<const uint4*>(s_p + (size_t)p * 64);
   const float4* c4 = reinterpret_cast<const float4*>(cof);
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
-    const uint4 u = q[v];
+    const uint4 u = q[swz<__half>(p, v)];
     const __half2* hh = reinterpret_cast<const __half2*>(&u);
-    const float4 ca = c4[2 * v], cb = c4[2 * v + 1];
+    const float4 ca = __ldg(c4 + 2 * v), cb = __ldg(c4 + 2 * v + 1);
     const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]), f3 = __half22float2(hh[3]);
     acc = fmaf(f0.x, ca.x, acc); acc = fmaf(f0.y, ca.y, acc); acc = fmaf(f1.x, ca.z, acc); acc = fmaf(f1.y, ca.w, acc);
     acc = fmaf(f2.x, cb.x, acc); acc = fmaf(f2.y, cb.y, acc); acc = fmaf(f3.x, cb.z, acc); acc = fmaf(f3.y, cb.w, acc);
@@ -287,133 +330,135 @@ __device__ __forceinline__ float dot32<__half>(const __half* px, const float* co
   return acc;
 }
 template <>
-__device__ __forceinline__ float dot32<float>(const float* px, const float* cof) {
+__device__ __forceinline__ float dot32_swz<float>(const unsigned char* s_p, int p, const float* __restrict__ cof) {
   float acc = 0.f;
-  const float4* q = reinterpret_cast<const float4*>(px);
+  const float4* q = reinterpret_cast<const float4*>(s_p + (size_t)p * 128);
   const float4* c4 = reinterpret_cast<const float4*>(cof);
 #pragma unroll
   for (int v = 0; v < 8; ++v) {
-    const float4 a = q[v], c = c4[v];
+    const float4 a = q[swz<float>(p, v)], c = __ldg(c4 + v);
     acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
   }
   return acc;
 }
 
 template <typename PT, bool HWC>
-__global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_kernel(
+__global__ void __launch_bounds__(MF_THREADS, 2) mask_fused_pack_kernel(
     const PT* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes, float sx1, float sy1,
-    float sx2, float sy2, uint32_t* __restrict__ out, int H, int W, int N, int out_h, int out_w, int words, float thr) {
-  constexpr int PP = PixPitch<PT>::kElems;
-  constexpr int SR = MF_TH + 2, SC = MF_TW + 2;
+    float sx2, float sy2, uint32_t* __restrict__ out, int H, int W, int N, int out_h, int out_w, int words, Resize rs,
+    int TY, int TW, float thr) {
+  constexpr int SC_CAP = FusedCfg<PT>::kScCap, CH = FusedCfg<PT>::kChunks;
+  constexpr int PX_BYTES = CH * 16;
   extern __shared__ __align__(16) unsigned char mf_smem[];
-  PT* s_p = reinterpret_cast<PT*>(mf_smem);                                   // [SR][SC][PP]
-  float* s_cof = reinterpret_cast<float*>(mf_smem + (size_t)SR * SC * PP * sizeof(PT));   // [MF_NB][128]
-  BoxP* s_box = reinterpret_cast<BoxP*>(s_cof + MF_NB * 128);                 // [MF_NB]
+  unsigned char* s_p = mf_smem;                                                        // [MF_SR * SC_CAP] swizzled pixels
+  float* s_val = reinterpret_cast<float*>(mf_smem + (size_t)MF_SR * SC_CAP * PX_BYTES);   // [2][MF_SR * SC_CAP]
+  BoxP* s_box = reinterpret_cast<BoxP*>(s_val + 2 * MF_SR * SC_CAP);                   // [MF_LIST]
+  int* s_det = reinterpret_cast<int*>(s_box + MF_LIST);                                // [MF_LIST]
+  int* s_cnt = s_det + MF_LIST;
 
-  const int tx = blockIdx.x, ty = blockIdx.y;
-  const int r_base = ty * MF_TH - 1, c_base = tx * MF_TW - 1;                  // source coords of smem (0,0)
-  // ---- prototype tile (+halo, edge-replicated) -> shared memory, read exactly once per CTA
-  for (int i = threadIdx.x; i < SR * SC * 4; i += MF_THREADS) {
-    const int part = i & 3, pixi = i >> 2;
-    const int r = pixi / SC, c = pixi - r * SC;
-    const int hs = min(max(r_base + r, 0), H - 1), ws = min(max(c_base + c, 0), W - 1);
-    PT* dst = s_p + (size_t)pixi * PP;
-    if (sizeof(PT) == 2) {
-      if (HWC) {
-        reinterpret_cast<uint4*>(dst)[part] = __ldg(reinterpret_cast<const uint4*>(protos + ((size_t)hs * W + ws) * 32) + part);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dst[part * 8 + k] = protos[((size_t)(part * 8 + k) * H + hs) * W + ws];
-      }
-    } else {
-      if (HWC) {
-        reinterpret_cast<uint4*>(dst)[2 * part] = __ldg(reinterpret_cast<const uint4*>(protos + ((size_t)hs * W + ws) * 32) + 2 * part);
-        reinterpret_cast<uint4*>(dst)[2 * part + 1] = __ldg(reinterpret_cast<const uint4*>(protos + ((size_t)hs * W + ws) * 32) + 2 * part + 1);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dst[part * 8 + k] = protos[((size_t)(part * 8 + k) * H + hs) * W + ws];
-      }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int y_first = blockIdx.y * TY, wq_first = blockIdx.x * TW;
+  const int vh = min(out_h, rs.full_h), vw = min(out_w, rs.full_w);     // valid output frame; everything else stays 0
+  const int y_last = min(y_first + TY, vh) - 1;
+  const int x_first = wq_first * 32, x_last = min(x_first + TW * 32, vw) - 1;
+  if (y_last < y_first || x_last < x_first) return;
+  // source window read by this tile's outputs (bilinear neighbours included)
+  int ys0, ys1, xs0, xs1, t0, t1;
+  float tl;
+  src_index(rs.ry, y_first, H, ys0, t1, tl);
+  src_index(rs.ry, y_last, H, t0, ys1, tl);
+  src_index(rs.rx, x_first, W, xs0, t1, tl);
+  src_index(rs.rx, x_last, W, t0, xs1, tl);
+  const int SRa = ys1 - ys0 + 1, SCa = xs1 - xs0 + 1;                    // <= MF_SR, SC_CAP (tile sizes chosen by the host)
+  const int npx = SRa * SCa;
+
+  // ---- prototype window -> shared memory, read exactly once per CTA
+  if (HWC) {
+    for (int i = threadIdx.x; i < npx * CH; i += MF_THREADS) {
+      const int p = i / CH, k = i - p * CH;
+      const int r = p / SCa, c = p - r * SCa;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(protos + ((size_t)(ys0 + r) * W + xs0 + c) * 32) + k);
+      *reinterpret_cast<uint4*>(s_p + (size_t)p * PX_BYTES + swz<PT>(p, k) * 16) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < npx * 32; i += MF_THREADS) {
+      const int ch = i / npx, p = i - ch * npx;
+      const int r = p / SCa, c = p - r * SCa;
+      const PT v = protos[((size_t)ch * H + ys0 + r) * W + xs0 + c];
+      constexpr int EPC = 16 / (int)sizeof(PT);                              // elements per 16-byte chunk
+      reinterpret_cast<PT*>(s_p + (size_t)p * PX_BYTES + swz<PT>(p, ch / EPC) * 16)[ch % EPC] = v;
     }
   }
 
-  const int slot = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
-  const int yo = ty * 2 * MF_TH + (slot >> 2);          // output row
-  const int wq = tx * (MF_TW / 16) + (slot & 3);        // output word
-  const bool out_ok = (yo < out_h) && (wq < words);
-  // vertical taps: yo = 2k -> rows (k-1, k) weights (.25,.75); yo = 2k+1 -> rows (k, k+1) weights (.75,.25)
-  const int k = yo >> 1;
-  const int ra = (yo & 1) ? k : k - 1;                   // first source row (unclamped)
-  const float wy_a = (yo & 1) ? 0.75f : 0.25f, wy_b = 1.f - wy_a;
-  const int ra_c = min(max(ra, 0), H - 1), rb_c = min(max(ra + 1, 0), H - 1);     // clamped rows actually read
-  const int ls_a = ra - r_base, ls_b = ra + 1 - r_base;                            // smem rows (already edge-replicated)
-  const int col0 = 16 * wq - 1;                                                    // first source column (unclamped)
-  const bool in_rows = (yo < 2 * H);
+  // ---- per-lane column constants of phase 2 (warp -> one word column, rows strided by the warps sharing the column)
+  const int wcol = warp % TW, rstep = (MF_THREADS / 32) / TW, rfirst = warp / TW;
+  const int x = x_first + wcol * 32 + lane;
+  int cx0, cx1;
+  float lx;
+  {
+    int xa, xb;
+    src_index(rs.rx, min(x, x_last), W, xa, xb, lx);
+    cx0 = xa - xs0; cx1 = xb - xs0;
+  }
+  const float hx = 1.f - lx;
+  const bool x_ok = x <= x_last;
+  const float win_x0 = (float)xs0, win_x1 = (float)xs1, win_y0 = (float)ys0, win_y1 = (float)ys1;
 
-  for (int n0 = 0; n0 < N; n0 += MF_NB) {
-    const int nb = min(MF_NB, N - n0);
+  for (int n0 = 0; n0 < N; n0 += MF_LIST) {
+    const int nb = min(MF_LIST, N - n0);
+    __syncthreads();                                   // prototype window staged / previous pass done with s_box, s_val
+    if (threadIdx.x == 0) *s_cnt = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < nb * 128; i += MF_THREADS) s_cof[i] = __ldg(cofs + (size_t)n0 * 128 + i);
     if (threadIdx.x < nb) {
       const float* b = boxes + (size_t)(n0 + threadIdx.x) * 4;
       BoxP bp;
       bp.x1 = b[0] * sx1; bp.y1 = b[1] * sy1; bp.x2 = b[2] * sx2; bp.y2 = b[3] * sy2;
-      bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
-      bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
-      bp.pad0 = bp.pad1 = 0.f;
-      s_box[threadIdx.x] = bp;
+      // some source pixel of the window lies inside the roi (x1 <= w < x2, y1 <= h < y2); otherwise every output of the
+      // tile is 0 for this detection, which the memset already wrote
+      if (win_x1 >= bp.x1 && win_x0 < bp.x2 && win_y1 >= bp.y1 && win_y0 < bp.y2) {
+        bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
+        bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
+        bp.pad0 = bp.pad1 = 0.f;
+        const int pos = atomicAdd(s_cnt, 1);
+        s_box[pos] = bp;
+        s_det[pos] = n0 + threadIdx.x;
+      }
     }
     __syncthreads();
-    if (!out_ok) continue;
-    for (int j = lane4; j < nb; j += 4) {
+    const int cnt = *s_cnt;
+    for (int j = 0; j < cnt; ++j) {
       const BoxP b = s_box[j];
-      uint32_t bits = 0u;
-      const float fa = (float)ra_c, fb = (float)rb_c;
-      const bool row_a_in = (fa >= b.y1) & (fa < b.y2), row_b_in = (fb >= b.y1) & (fb < b.y2);
-      const float cl = (float)max(col0, 0), cr = (float)min(col0 + 17, W - 1);
-      if (in_rows && (row_a_in | row_b_in) && (cr >= b.x1) && (cl < b.x2)) {
-        const int idxh_a = (int)__fdiv_rn(fa - b.y1, b.roi_h), idxh_b = (int)__fdiv_rn(fb - b.y1, b.roi_h);
-        const float* cof = s_cof + j * 128;
-        // vertical blend of the two source rows for the 18 source columns
-        float vcol_prev = 0.f, vcol_cur = 0.f;
-#pragma unroll 1
-        for (int ci = 0; ci < 18; ++ci) {
-          const int wsrc = min(max(col0 + ci, 0), W - 1);
-          const float wf = (float)wsrc;
-          float v = 0.f;
-          if ((wf >= b.x1) & (wf < b.x2)) {
-            const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
-            const int lc = col0 + ci - c_base;                 // smem column
-            if (row_a_in) {
-              const int cell = min(max(idxh_a * 2 + idx_w, 0), 3);
-              v = wy_a * sigmoidf_(dot32<PT>(s_p + ((size_t)ls_a * SC + lc) * PP, cof + cell * 32));
-            }
-            if (row_b_in) {
-              const int cell = min(max(idxh_b * 2 + idx_w, 0), 3);
-              v += wy_b * sigmoidf_(dot32<PT>(s_p + ((size_t)ls_b * SC + lc) * PP, cof + cell * 32));
-            }
-          }
-          // horizontal taps: x = 2m -> (m-1, m) weights (.25,.75); x = 2m+1 -> (m, m+1) weights (.75,.25)
-          // column index ci corresponds to source col 16*wq - 1 + ci; output x = 32*wq + 2*(ci-1) + {0,1} need (ci-1, ci) / (ci, ci+1)
-          if (ci >= 1) {
-            // even output x = 32*wq + 2*(ci-1): uses source cols (ci-1, ci)
-            const int xe = 32 * wq + 2 * (ci - 1);
-            if (ci <= 16) {
-              const float ve = 0.25f * vcol_cur + 0.75f * v;
-              if (xe < out_w && xe < 2 * W && ve > thr) bits |= 1u << (2 * (ci - 1));
-            }
-            // odd output x = 32*wq + 2*(ci-2) + 1: uses source cols (ci-1, ci) with weights (.75,.25)
-            if (ci >= 2) {
-              const int xo = 32 * wq + 2 * (ci - 2) + 1;
-              const float vo = 0.75f * vcol_cur + 0.25f * v;
-              if (xo < out_w && xo < 2 * W && vo > thr) bits |= 1u << (2 * (ci - 2) + 1);
-            }
-          }
-          vcol_prev = vcol_cur;
-          vcol_cur = v;
+      const int n = s_det[j];
+      float* val = s_val + (j & 1) * (MF_SR * SC_CAP);
+      const float* cof = cofs + (size_t)n * 128;
+      // ---- phase 1: one sigmoid-dot per source pixel of the window
+      for (int p = threadIdx.x; p < npx; p += MF_THREADS) {
+        const int r = p / SCa, c = p - r * SCa;
+        const float hf = (float)(ys0 + r), wf = (float)(xs0 + c);
+        float v = 0.f;
+        if ((hf >= b.y1) & (hf < b.y2) & (wf >= b.x1) & (wf < b.x2)) {
+          const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h), idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
+          const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
+          v = sigmoidf_(dot32_swz<PT>(s_p, p, cof + cell * 32));
         }
-        (void)vcol_prev;
+        val[p] = v;
       }
-      out[((size_t)(n0 + j) * out_h + yo) * words + wq] = bits;
+      __syncthreads();        // the only barrier per detection: s_val is double-buffered, see below
+      // ---- phase 2: lane = output pixel of one word; rows of this warp's word column
+      uint32_t* o = out + (size_t)n * out_h * words + wq_first + wcol;
+      for (int y = y_first + rfirst; y <= y_last; y += rstep) {
+        int y0, y1;
+        float ly;
+        src_index(rs.ry, y, H, y0, y1, ly);
+        const float hy = 1.f - ly;
+        const float* r0 = val + (y0 - ys0) * SCa;
+        const float* r1 = val + (y1 - ys0) * SCa;
+        const float v = hy * (hx * r0[cx0] + lx * r0[cx1]) + ly * (hx * r1[cx0] + lx * r1[cx1]);
+        const uint32_t bits = __ballot_sync(0xffffffffu, x_ok && v > thr);
+        if (lane == 0 && bits) o[(size_t)y * words] = bits;
+      }
+      // no barrier here: phase 1 of detection j+1 writes the OTHER s_val buffer; buffer (j & 1) is rewritten by detection
+      // j+2, whose phase 1 every warp enters only after the barrier of detection j+1, i.e. after all warps left this loop
     }
   }
 }
@@ -457,6 +502,8 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
   dim3 grid(cdiv(W, MA_TW), cdiv(H, MA_TH)), block(MA_THREADS);
   const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
   cudaStream_t st = (cudaStream_t)stream;
+  // zero background first (a memset node: runs at store bandwidth), then the in-box pixels only
+  SMB_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * H * W * (out_dtype == SMB_F32 ? 4 : 2), st));
 #define MA_LAUNCH(PT, HWC, OT)                                                                             \
   mask_assemble_kernel<PT, HWC, OT><<<grid, block, 0, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, \
                                                             (OT*)out, H, W, N)
@@ -476,66 +523,103 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
   return SMB_OK;
 }
 
-extern "C" int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W,
-                                            int out_h, int out_w, float thr, smb_stream_t stream) {
-  SMB_CHECK_ARG(pos && out_u8, "smb_mask_upsample2_threshold: null pointer");
+static int make_resize(int H, int W, int full_h, int full_w, float ry, float rx, Resize* rs, const char* who) {
+  if (full_h <= 0 || full_w <= 0) { set_error("%s: interpolated size %dx%d must be positive", who, full_h, full_w); return SMB_EINVAL; }
+  rs->full_h = full_h; rs->full_w = full_w;
+  // source step per output pixel: the caller's 1/scale_factor (PyTorch >= 1.6 with scale_factor given), or in/out when the
+  // caller passes <= 0 (recompute_scale_factor=True, the only behaviour of PyTorch <= 1.5)
+  rs->ry = ry > 0.f ? ry : (float)H / (float)full_h;
+  rs->rx = rx > 0.f ? rx : (float)W / (float)full_w;
+  return SMB_OK;
+}
+
+extern "C" int smb_mask_resize_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W, int full_h,
+                                         int full_w, float ry, float rx, int out_h, int out_w, float thr, smb_stream_t stream) {
+  SMB_CHECK_ARG(pos && out_u8, "smb_mask_resize_threshold: null pointer");
   SMB_CHECK_ARG(N >= 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && out_h <= 65535 && N <= 65535,
-                "smb_mask_upsample2_threshold: bad shape");
+                "smb_mask_resize_threshold: bad shape");
+  Resize rs;
+  const int rc = make_resize(H, W, full_h, full_w, ry, rx, &rs, "smb_mask_resize_threshold");
+  if (rc) return rc;
   if (N == 0) return SMB_OK;
   dim3 block(256), grid(cdiv(cdiv(out_w, 4), 256), out_h, N);
   cudaStream_t st = (cudaStream_t)stream;
   if (pos_dtype == SMB_F32)
-    upsample2_thresh_kernel<float><<<grid, block, 0, st>>>((const float*)pos, out_u8, N, H, W, out_h, out_w, thr);
+    resize_thresh_kernel<float><<<grid, block, 0, st>>>((const float*)pos, out_u8, N, H, W, out_h, out_w, rs, thr);
   else
-    upsample2_thresh_kernel<__half><<<grid, block, 0, st>>>((const __half*)pos, out_u8, N, H, W, out_h, out_w, thr);
-  SMB_LAUNCH_OK("upsample2_thresh_kernel");
+    resize_thresh_kernel<__half><<<grid, block, 0, st>>>((const __half*)pos, out_u8, N, H, W, out_h, out_w, rs, thr);
+  SMB_LAUNCH_OK("resize_thresh_kernel");
   return SMB_OK;
+}
+
+extern "C" int smb_mask_resize_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
+                                              int full_h, int full_w, float ry, float rx, int out_h, int out_w, float thr,
+                                              smb_stream_t stream) {
+  SMB_CHECK_ARG(pos && out_bits, "smb_mask_resize_threshold_pack: null pointer");
+  SMB_CHECK_ARG(N >= 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && out_h <= 65535 && N <= 65535,
+                "smb_mask_resize_threshold_pack: bad shape");
+  Resize rs;
+  const int rc = make_resize(H, W, full_h, full_w, ry, rx, &rs, "smb_mask_resize_threshold_pack");
+  if (rc) return rc;
+  if (N == 0) return SMB_OK;
+  const int words = cdiv(out_w, 32);
+  dim3 block(256), grid(cdiv(words, 8), out_h, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pos_dtype == SMB_F32)
+    resize_thresh_pack_kernel<float><<<grid, block, 0, st>>>((const float*)pos, out_bits, N, H, W, out_h, out_w, words, rs, thr);
+  else
+    resize_thresh_pack_kernel<__half><<<grid, block, 0, st>>>((const __half*)pos, out_bits, N, H, W, out_h, out_w, words, rs, thr);
+  SMB_LAUNCH_OK("resize_thresh_pack_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_mask_upsample2_threshold(const void* pos, int pos_dtype, uint8_t* out_u8, int N, int H, int W,
+                                            int out_h, int out_w, float thr, smb_stream_t stream) {
+  return smb_mask_resize_threshold(pos, pos_dtype, out_u8, N, H, W, 2 * H, 2 * W, 0.5f, 0.5f, out_h, out_w, thr, stream);
 }
 
 extern "C" int smb_mask_upsample2_threshold_pack(const void* pos, int pos_dtype, uint32_t* out_bits, int N, int H, int W,
                                                  int out_h, int out_w, float thr, smb_stream_t stream) {
-  SMB_CHECK_ARG(pos && out_bits, "smb_mask_upsample2_threshold_pack: null pointer");
-  SMB_CHECK_ARG(N >= 0 && H > 0 && W > 0 && out_h > 0 && out_w > 0 && out_h <= 65535 && N <= 65535,
-                "smb_mask_upsample2_threshold_pack: bad shape");
-  if (N == 0) return SMB_OK;
-  const int words = cdiv(out_w, 32);
-  dim3 block(128), grid(cdiv(words, 128), out_h, N);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (pos_dtype == SMB_F32)
-    upsample2_thresh_pack_kernel<float><<<grid, block, 0, st>>>((const float*)pos, out_bits, N, H, W, out_h, out_w, words, thr);
-  else
-    upsample2_thresh_pack_kernel<__half><<<grid, block, 0, st>>>((const __half*)pos, out_bits, N, H, W, out_h, out_w, words, thr);
-  SMB_LAUNCH_OK("upsample2_thresh_pack_kernel");
-  return SMB_OK;
+  return smb_mask_resize_threshold_pack(pos, pos_dtype, out_bits, N, H, W, 2 * H, 2 * W, 0.5f, 0.5f, out_h, out_w, thr, stream);
 }
 
 extern "C" int smb_mask_assemble_pack(const void* protos, int protos_dtype, int layout_hwc, const float* cofs,
                                       const float* boxes, const float* host_box_scale4, uint32_t* out_bits, int H, int W, int N,
-                                      int out_h, int out_w, float thr, smb_stream_t stream) {
+                                      int full_h, int full_w, float ry, float rx, int out_h, int out_w, float thr,
+                                      smb_stream_t stream) {
   SMB_CHECK_ARG(protos && cofs && boxes && out_bits && host_box_scale4, "smb_mask_assemble_pack: null pointer");
   SMB_CHECK_ARG(H > 0 && W > 0 && N >= 0 && out_h > 0 && out_w > 0, "smb_mask_assemble_pack: bad shape");
   SMB_CHECK_ARG(protos_dtype == SMB_F32 || protos_dtype == SMB_F16, "smb_mask_assemble_pack: bad dtype");
+  Resize rs;
+  const int rc = make_resize(H, W, full_h, full_w, ry, rx, &rs, "smb_mask_assemble_pack");
+  if (rc) return rc;
   if (N == 0) return SMB_OK;
   const int words = cdiv(out_w, 32);
-  // tiles must cover every output row/word of the [out_h, words] frame (rows beyond 2H are written as zeros)
-  const int rows_src = max(cdiv(out_h, 2), 1), cols_src = max(cdiv(words * 16, 1), 1);
-  dim3 grid(cdiv(cols_src, MF_TW), cdiv(rows_src, MF_TH)), block(MF_THREADS);
-  const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t esz = protos_dtype == SMB_F16 ? 2 : 4;
-  const int pp = protos_dtype == SMB_F16 ? PixPitch<__half>::kElems : PixPitch<float>::kElems;
-  const size_t smem = (size_t)(MF_TH + 2) * (MF_TW + 2) * pp * esz + MF_NB * 128 * sizeof(float) + MF_NB * sizeof(BoxP);
-  static bool attr_done = false;
-  if (!attr_done) {
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    attr_done = true;
+  SMB_CUDA_OK(cudaMemsetAsync(out_bits, 0, (size_t)N * out_h * words * 4, st));      // zero background (memset node)
+  const int vh = out_h < full_h ? out_h : full_h, vw = out_w < full_w ? out_w : full_w;
+  // output tile (TY rows x TW words) whose source window fits the shared-memory caps: rows/cols <= ceil((n-1) * r) + 2
+  const int sc_cap = protos_dtype == SMB_F16 ? FusedCfg<__half>::kScCap : FusedCfg<float>::kScCap;
+  int TW = 8, TY = 16;
+  while (TW > 1 && (int)ceilf((float)(TW * 32 - 1) * rs.rx) + 2 > sc_cap) TW >>= 1;
+  while (TY > 1 && (int)ceilf((float)(TY - 1) * rs.ry) + 2 > MF_SR) TY >>= 1;
+  SMB_CHECK_ARG((int)ceilf((float)(TW * 32 - 1) * rs.rx) + 2 <= sc_cap && (int)ceilf((float)(TY - 1) * rs.ry) + 2 <= MF_SR,
+                "smb_mask_assemble_pack: resize factor %dx%d -> %dx%d (shrinks by more than 4x) is not supported", H, W,
+                full_h, full_w);
+  dim3 grid(cdiv(cdiv(vw, 32), TW), cdiv(vh, TY)), block(MF_THREADS);
+  const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
+  const size_t px_bytes = protos_dtype == SMB_F16 ? 64 : 128;
+  const size_t smem = (size_t)MF_SR * sc_cap * (px_bytes + 8) + MF_LIST * (sizeof(BoxP) + sizeof(int)) + 16;
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   }
 #define MF_LAUNCH(PT, HWC)                                                                                          \
   mask_fused_pack_kernel<PT, HWC><<<grid, block, smem, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, out_bits, H, W, \
-                                                           N, out_h, out_w, words, thr)
+                                                           N, out_h, out_w, words, rs, TY, TW, thr)
   if (protos_dtype == SMB_F16) {
     if (layout_hwc) MF_LAUNCH(__half, true); else MF_LAUNCH(__half, false);
   } else {

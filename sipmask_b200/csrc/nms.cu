@@ -724,6 +724,47 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int src_pitch,
   }
 }
 
+// det_cofs[i,:] = cof_src[cand_loc[idx[i]], :], det_boxes[i,:] = det[i,:4] for i < *count, zeros after: the gather between
+// NMS and mask assembly (mlvl_cofs[idxs_keep], det_bboxes[:, :4], sipmask_head.py:612,623) as ONE launch.
+// Row table of a level-major, image-inside-level buffer [level][image][hw_l][pitch]: row(loc) of image `img` =
+// loc_off[l] * n_img + img * hw_l + (loc - loc_off[l]); num == 0: plain [tot][pitch] (row = loc).
+struct LocMap {
+  int num, n_img, img;
+  int loc_off[MAXLVL + 1];
+};
+__device__ __forceinline__ long long loc_row(const LocMap& m, int loc) {
+  if (m.num == 0) return loc;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < MAXLVL; ++i)
+    if (i < m.num && loc >= m.loc_off[i]) l = i;
+  const int hw = m.loc_off[l + 1] - m.loc_off[l];
+  return (long long)m.loc_off[l] * m.n_img + (long long)m.img * hw + (loc - m.loc_off[l]);
+}
+
+__global__ void gather_det_inputs_kernel(const float* __restrict__ cof_src, int cof_pitch, const int* __restrict__ cand_loc,
+                                         const long long* __restrict__ idx, const float* __restrict__ det,
+                                         const int* __restrict__ count, int max_rows, int row_elems,
+                                         float* __restrict__ det_cofs, float* __restrict__ det_boxes,
+                                         long long* __restrict__ loc_out, LocMap lm) {
+  pdl_wait();
+  const int total = max_rows * row_elems;
+  const int cnt = *count;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int r = t / row_elems, e = t - r * row_elems;
+    float v = 0.f;
+    if (r < cnt) {
+      const int loc = cand_loc[idx[r]];
+      v = cof_src[(size_t)loc_row(lm, loc) * cof_pitch + e];
+      if (e == 0 && loc_out) loc_out[r] = loc;
+    } else if (e == 0 && loc_out) {
+      loc_out[r] = -1;
+    }
+    det_cofs[t] = v;
+    if (e < 4) det_boxes[r * 4 + e] = (r < cnt) ? det[r * 5 + e] : 0.f;
+  }
+}
+
 static int fill_levels(Levels* L, int num_levels, const smb_level_t* host_levels, int nms_pre) {
   if (num_levels < 1 || num_levels > MAXLVL) return -1;
   L->num = num_levels;
@@ -752,10 +793,9 @@ extern "C" int smb_nms(const float* dets, int n, float iou_thr, int cmp_ge, int 
     SMB_CUDA_OK(cudaMemsetAsync(n_keep_out, 0, sizeof(int), st));
     return SMB_OK;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SMB_CUDA_OK(cudaFuncSetAttribute(nms_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem)));
-    attr_done = true;
   }
   nms_single_kernel<<<1, NT, sizeof(NmsSmem), st>>>(dets, n, iou_thr, cmp_ge, plus_one ? 1.f : 0.f,
                                                     (long long*)keep_out, n_keep_out);
@@ -810,10 +850,9 @@ extern "C" int smb_multiclass_nms(const float* boxes, const float* scores, const
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   int* ws_count = (int*)(ws + w.count);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SMB_CUDA_OK(cudaFuncSetAttribute(mc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McPrepSmem)));
-    attr_done = true;
   }
   if (n == 0) {
     SMB_CUDA_OK(cudaMemsetAsync(ws_count, 0, sizeof(int) * (num_classes + 1), st));
@@ -858,10 +897,9 @@ extern "C" int smb_fast_nms(const float* boxes, const float* scores, const float
   }
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     SMB_CUDA_OK(cudaFuncSetAttribute(fast_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem)));
-    attr_done = true;
   }
   fast_nms_class_kernel<<<num_classes, NT, sizeof(FastSmem), st>>>(boxes, scores, ctr, n, num_classes, score_thr, iou_thr, top_k,
                                                                    (int*)(ws + o_idx), (float*)(ws + o_score), (int*)(ws + o_count));
@@ -908,6 +946,25 @@ extern "C" int smb_decode_topk(int num_levels, const smb_level_t* host_levels, i
                                                                     host_scale4 ? 1 : 0, sel, cand_boxes, cand_scores,
                                                                     cand_ctr, cand_loc));
   SMB_LAUNCH_OK("gather_decode_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_gather_det_inputs(const float* cof_src, int cof_pitch, const int* cand_loc, const int64_t* idx,
+                                     const float* det, const int* count_dev, int max_rows, int row_elems, float* det_cofs,
+                                     float* det_boxes, int64_t* loc_out, int num_levels, const int* host_level_hw, int n_img,
+                                     int img, smb_stream_t stream) {
+  SMB_CHECK_ARG(cof_src && cand_loc && idx && det && count_dev && det_cofs && det_boxes && max_rows > 0 && row_elems >= 4,
+                "smb_gather_det_inputs: bad argument");
+  SMB_CHECK_ARG(num_levels >= 0 && num_levels <= MAXLVL && (num_levels == 0 || (host_level_hw && n_img >= 1 && img >= 0 && img < n_img)),
+                "smb_gather_det_inputs: bad level table");
+  LocMap lm;
+  memset(&lm, 0, sizeof(lm));
+  lm.num = num_levels; lm.n_img = n_img; lm.img = img;
+  for (int l = 0; l < num_levels; ++l) lm.loc_off[l + 1] = lm.loc_off[l] + host_level_hw[l];
+  SMB_CUDA_OK(launch_pdl(gather_det_inputs_kernel, dim3(cdiv(max_rows * row_elems, 256)), dim3(256), 0, (cudaStream_t)stream,
+                         cof_src, cof_pitch, cand_loc, (const long long*)idx, det, count_dev, max_rows, row_elems, det_cofs,
+                         det_boxes, (long long*)loc_out, lm));
+  SMB_LAUNCH_OK("gather_det_inputs_kernel");
   return SMB_OK;
 }
 

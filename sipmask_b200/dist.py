@@ -40,3 +40,63 @@ def unpack_records(gathered):
         k = int(rec[:, 6].sum().item())
         res.append((rec[:k, :5].clone(), rec[:k, 5].to(torch.long)))
     return res
+
+
+class RecordLog(object):
+    """Detection records of a whole run, gathered ONCE at the end (north_star: "a single NCCL all-gather of detections at
+    the end only").  `append` writes one image's [max,7] record into the next row of a device buffer on the caller's stream
+    (no communication); `gather` is the single collective: [cap,max,7] per rank -> [world,cap,max,7] on every rank.
+    Per-image gathering (`gather_records` after every image) put a latency-bound 2.8 KB collective on the critical path of
+    every step (r1: scaling efficiency 0.96 already at 2 GPUs)."""
+
+    def __init__(self, capacity, max_num, device):
+        self.buf = torch.zeros((capacity, max_num, 7), dtype=torch.float32, device=device)
+        self.cap, self.n = capacity, 0
+        self._ar = torch.arange(max_num, device=device).view(max_num, 1)
+
+    def append(self, det_bboxes, det_labels, count):
+        row = self.buf[self.n % self.cap]
+        row[:, :5].copy_(det_bboxes, non_blocking=True)
+        row[:, 5:6].copy_(det_labels.view(-1, 1), non_blocking=True)
+        row[:, 6:7].copy_(self._ar < count.view(1, 1), non_blocking=True)
+        self.n += 1
+
+    def reset(self):
+        self.n = 0
+
+    def gather(self, out=None):
+        """-> [world, cap, max, 7]; rows >= number of appended images are stale / zero."""
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if world == 1:
+            return self.buf.unsqueeze(0)
+        if out is None:
+            out = self.buf.new_empty((world,) + tuple(self.buf.shape))
+        if dist.get_backend() == 'nccl':
+            dist.all_gather_into_tensor(out, self.buf)
+        else:
+            parts = [torch.empty_like(self.buf) for _ in range(world)]
+            dist.all_gather(parts, self.buf)
+            out.copy_(torch.stack(parts, 0))
+        return out
+
+
+def gather_rle(counts, n_counts):
+    """Instance masks across ranks (apis/test.py:117-147 gathers the complete result incl. segm RLEs): the fixed-capacity
+    run-length tensors of ops.mask_rle_counts - counts [max,cap] int32, n_counts [max] int32 - all-gathered as they are
+    (two collectives of static shape).  Returns ([world,max,cap], [world,max])."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return counts.unsqueeze(0), n_counts.unsqueeze(0)
+    oc = counts.new_empty((world,) + tuple(counts.shape))
+    on = n_counts.new_empty((world,) + tuple(n_counts.shape))
+    if dist.get_backend() == 'nccl':
+        dist.all_gather_into_tensor(oc, counts.contiguous())
+        dist.all_gather_into_tensor(on, n_counts.contiguous())
+    else:
+        pc = [torch.empty_like(counts) for _ in range(world)]
+        pn = [torch.empty_like(n_counts) for _ in range(world)]
+        dist.all_gather(pc, counts.contiguous())
+        dist.all_gather(pn, n_counts.contiguous())
+        oc.copy_(torch.stack(pc, 0))
+        on.copy_(torch.stack(pn, 0))
+    return oc, on

@@ -27,16 +27,20 @@ class SipMaskEngine(object):
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
                  mask_thr=0.4, use_graph=True, pos_dtype=torch.float32, head_only=False, feat_sizes=None, in_channels=256,
                  fcos=False, prefix_head='bbox_head.', build_postproc=True, two_streams=True, share_weights=None,
-                 max_ctas=None, head_max_ctas=None, backbone_dcn=False):
-        L.check(L.lib().smb_check_device(), 'smb_check_device')
+                 max_ctas=None, head_max_ctas=None, backbone_dcn=False, ori_shape=None, legacy_interp=False):
         self.dev = torch.device(device)
+        if self.dev.index is None:
+            self.dev = torch.device('cuda', torch.cuda.current_device())
+        with torch.cuda.device(self.dev):
+            L.check(L.lib().smb_check_device(), 'smb_check_device')
         self.N, (self.H, self.W) = batch, img_hw
         self.head_only, self.feat_sizes, self.in_channels, self.fcos = head_only, feat_sizes, in_channels, fcos
         self.hp, self.build_post = prefix_head, build_postproc
         self.two_streams = two_streams and os.environ.get('SMB_TWO_STREAMS', '1') != '0'
         self.fork_branches = self.two_streams and os.environ.get('SMB_FORK_BRANCHES', '1') != '0'
         self.fork_from_layer = int(os.environ.get('SMB_FORK_FROM_LAYER', '1'))      # 0-based residual stage index
-        assert batch == 1, 'round 1: one image per GPU (BaseDetector.forward_test asserts imgs_per_gpu == 1, base.py:118-119)'
+        # batch > 1: N images per forward (the reference's forward_test asserts imgs_per_gpu == 1, base.py:118-119, but
+        # get_bboxes loops over images, sipmask_head.py:517-540; BASELINE config 4 is a bs=32 throughput mode)
         assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
         self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
         self.backbone_dcn = backbone_dcn           # SipMask++: DeformConvPack (dg=1) as conv2 of every 3rd block of stages 2-4
@@ -47,6 +51,10 @@ class SipMaskEngine(object):
             self.cfg.update(test_cfg)
         self.img_shape = tuple(img_shape) if img_shape is not None else (self.H, self.W, 3)
         self.scale_factor = scale_factor
+        # rescale=True semantics (SingleStageDetector.simple_test): boxes / scale_factor, masks resized by 2 / scale_factor and
+        # pasted into the ori_shape canvas (sipmask_head.py:587-588,629-633,648-654)
+        self.ori_shape = tuple(ori_shape) if ori_shape is not None else self.img_shape
+        self.legacy_interp = legacy_interp
         self.mask_thr = mask_thr
         self.pos_dtype = pos_dtype
         self.sd = {k: v for k, v in state_dict.items()}
@@ -60,13 +68,15 @@ class SipMaskEngine(object):
         self._keep = []
         # packed weights; `share_weights=<engine>` makes several engines (images in flight) read ONE copy, so the weights'
         # L2 footprint does not grow with the number of images in flight
-        self._wcache = share_weights._wcache if share_weights is not None else {}
+        self._wcache = ({} if share_weights is None else share_weights if isinstance(share_weights, dict)
+                        else share_weights._wcache)
         self.max_ctas = max_ctas                   # persistent-grid cap of every conv (None: all SMs)
         self.head_max_ctas = head_max_ctas         # cap inside the two-stream head section (None: env / 100)
         self.conv_plans = []
         self.conv_meta = []
         self.conv_flops = 0.0
-        self._build()
+        with torch.cuda.device(self.dev):
+            self._build()
         self.graph = None
         self.use_graph = use_graph
 
@@ -289,13 +299,15 @@ class SipMaskEngine(object):
                            lambda: self._w(hp + 'feat_align.conv_offset.weight').view(72, 4).contiguous().to(self.dev))
         self._keep += [wk_cls, b_cls, wk_reg, b_reg, wk_dcn, w_off]
         self.scales = [float(self._w(hp + 'scales.%d.scale' % i)) for i in range(nl)]
-        # level-concatenated fp32 head outputs (channel-last): [tot, 80+128] and [tot, 16 = 4 reg | 1 ctr | pad]
-        self.clscof = self._t(N, tot, CCp, dtype=torch.float32)
-        self.regctr = self._t(N, tot, 16, dtype=torch.float32)
+        # fp32 head outputs, channel-last, ONE allocation in level-major order [level][image][h*w][C] with C = 80+128 (-> 208)
+        # and 16 = 4 reg | 1 ctr | pad: every level is a contiguous [N,h,w,C] tensor for the GEMM epilogue, and with N == 1
+        # the buffer is the level-concatenated [tot, C] table a candidate's location index addresses directly
+        self.clscof = self._t(N * tot, CCp, dtype=torch.float32)
+        self.regctr = self._t(N * tot, 16, dtype=torch.float32)
         offs0 = [sum(h * w for h, w in sizes[:l]) for l in range(nl)]
-        clscof_l = [self.clscof[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], CCp)
+        clscof_l = [self.clscof[N * offs0[l]:N * (offs0[l] + sizes[l][0] * sizes[l][1])].view(N, sizes[l][0], sizes[l][1], CCp)
                     for l in range(nl)]
-        regctr_l = [self.regctr[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], 16)
+        regctr_l = [self.regctr[N * offs0[l]:N * (offs0[l] + sizes[l][0] * sizes[l][1])].view(N, sizes[l][0], sizes[l][1], 16)
                     for l in range(nl)]
         self.level_views = list(zip(clscof_l, regctr_l))
         si = 0
@@ -381,11 +393,11 @@ class SipMaskEngine(object):
         b_reg = torch.cat([self._w(hp + 'fcos_reg.bias'), torch.zeros(12)]).to(self.dev)
         self._keep += [wk_cls, b_cls, wk_reg, b_reg]
         self.scales = [float(self._w(hp + 'scales.%d.scale' % i)) for i in range(nl)]
-        self.clscof = self._t(N, tot, CCp, dtype=torch.float32)       # [cls(80) | centerness(1) | pad]
-        self.regctr = self._t(N, tot, 16, dtype=torch.float32)        # [reg(4) | pad]
+        self.clscof = self._t(N * tot, CCp, dtype=torch.float32)      # [cls(80) | centerness(1) | pad], level-major
+        self.regctr = self._t(N * tot, 16, dtype=torch.float32)       # [reg(4) | pad]
         offs0 = [sum(h * w for h, w in sizes[:l]) for l in range(nl)]
-        cls_l = [self.clscof[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], CCp) for l in range(nl)]
-        reg_l = [self.regctr[:, offs0[l]:offs0[l] + sizes[l][0] * sizes[l][1]].view(N, sizes[l][0], sizes[l][1], 16) for l in range(nl)]
+        cls_l = [self.clscof[N * offs0[l]:N * (offs0[l] + sizes[l][0] * sizes[l][1])].view(N, sizes[l][0], sizes[l][1], CCp) for l in range(nl)]
+        reg_l = [self.regctr[N * offs0[l]:N * (offs0[l] + sizes[l][0] * sizes[l][1])].view(N, sizes[l][0], sizes[l][1], 16) for l in range(nl)]
         self.level_views = list(zip(cls_l, reg_l))
         si = 0
         cls_feats, reg_feats = list(feats), list(feats)
@@ -424,8 +436,10 @@ class SipMaskEngine(object):
         self._sf4 = L.f4(s4)
         self._box_scale4 = L.f4(s4 / 2.0)
         Hm, Wm = self.protos.shape[1], self.protos.shape[2]
-        oh, ow = int(self.img_shape[0]), int(self.img_shape[1])        # rescale=True, ori_shape == img_shape / scale
+        oh, ow = int(self.ori_shape[0]), int(self.ori_shape[1])        # rescale=True: masks live in the ori_shape canvas
         self.mask_hw = (oh, ow)
+        from .postproc import mask_up_factors
+        fh, fw, ry, rx = ops.resize_spec(Hm, Wm, mask_up_factors(self.scale_factor, self.ssd), self.legacy_interp)
         words = (ow + 31) // 32
         self.det = self._t(N, self.max_num, 5, dtype=torch.float32)
         self.labels = self._t(N, self.max_num, dtype=torch.long)
@@ -439,15 +453,21 @@ class SipMaskEngine(object):
         self.loc_kept = self._t(N, self.max_num, dtype=torch.long)
         self.det_cofs = self._t(N, self.max_num, 128, dtype=torch.float32)
         self.det_boxes4 = self._t(N, self.max_num, 4, dtype=torch.float32)
+        level_hw = (ctypes.c_int * nl)(*[h * w for h, w in self.level_sizes])
+        self._keep.append(level_hw)
+        # the per-image decode -> NMS -> gather -> mask chains are independent (get_bboxes loops over images,
+        # sipmask_head.py:517-540): with a batch they are spread over a few streams of the captured graph
+        pp_streams = min(N, int(os.environ.get('SMB_POSTPROC_STREAMS', '4'))) if N > 1 else 0
+        if pp_streams:
+            self._marker('fork')
         for n in range(N):
+            self._tag = (n % pp_streams) + 1 if pp_streams else 0
             lv = (L.Level * nl)()
-            off0 = 0
             for l, (h, w) in enumerate(self.level_sizes):
-                cc = self.clscof[n, off0:off0 + h * w]
-                rc = self.regctr[n, off0:off0 + h * w]
+                cc = self.level_views[l][0][n]                 # [h,w,CCp] of image n (contiguous)
+                rc = self.level_views[l][1][n]
                 lv[l] = L.Level(cc.data_ptr(), rc.data_ptr() + 4 * 4, rc.data_ptr(), CCp, 16, 16, h, w, int(self.strides[l]),
                                 float(self.scales[l]), float(self.strides[l]))
-                off0 += h * w
             ws_bytes = lib.smb_decode_workspace_bytes(nl, lv, nms_pre)
             ws = self._t(ws_bytes, dtype=torch.uint8)
             self._keep.append(lv)
@@ -480,46 +500,70 @@ class SipMaskEngine(object):
                                              L.ptr(self.count[n:n + 1]), L.ptr(nws), ctypes.c_size_t(nws_bytes), L.stream_ptr()),
                             'smb_fast_nms')
             self._add(nms, 4 if not self.ssd else 2, name='nms')
-            cof_src = self.clscof[n][:, ncls:ncls + 128]                       # [tot,128] view, pitch CCp
+            cof_src = self.clscof[:, ncls:ncls + 128]                          # coefficient columns, row pitch CCp
 
             def gather(n=n, cof_src=cof_src):
                 # candidate row -> level-concatenated location -> coefficient row (mlvl_cofs[idxs_keep], sipmask_head.py:612)
-                torch.index_select(self.cand_loc[n].long(), 0, self.idx[n].clamp(min=0), out=self.loc_kept[n])
-                L.check(lib.smb_gather_rows_f32(L.ptr(cof_src), CCp, L.ptr(self.loc_kept[n]), L.ptr(self.count[n:n + 1]),
-                                                self.max_num, 128, L.ptr(self.det_cofs[n]), L.stream_ptr()), 'smb_gather_rows_f32')
-                self.det_boxes4[n].copy_(self.det[n][:, :4])
+                # and det[:, :4] -> contiguous rois input, one launch (was index_select + gather + copy_)
+                L.check(lib.smb_gather_det_inputs(L.ptr(cof_src), CCp, L.ptr(self.cand_loc[n]), L.ptr(self.idx[n]),
+                                                  L.ptr(self.det[n]), L.ptr(self.count[n:n + 1]), self.max_num, 128,
+                                                  L.ptr(self.det_cofs[n]), L.ptr(self.det_boxes4[n]), L.ptr(self.loc_kept[n]),
+                                                  nl if N > 1 else 0, level_hw, N, n, L.stream_ptr()), 'smb_gather_det_inputs')
             self._add(gather, 1, name='gather_cofs')
 
             def masks(n=n):
                 # fused: prototypes -> sub-region dot/sigmoid/crop -> x2 bilinear -> threshold -> bit-pack (no pos_masks tensor)
                 L.check(lib.smb_mask_assemble_pack(L.ptr(self.protos[n]), L.F16, 1, L.ptr(self.det_cofs[n]), L.ptr(self.det_boxes4[n]),
-                                                   self._box_scale4, L.ptr(self.mask_bits[n]), Hm, Wm, self.max_num, oh, ow,
+                                                   self._box_scale4, L.ptr(self.mask_bits[n]), Hm, Wm, self.max_num, fh, fw,
+                                                   ctypes.c_float(ry), ctypes.c_float(rx), oh, ow,
                                                    ctypes.c_float(self.mask_thr), L.stream_ptr()), 'smb_mask_assemble_pack')
-            self._add(masks, 1, name='mask_fused')
+            self._add(masks, 2, name='mask_fused')
+        if pp_streams:
+            self._marker('join')
+        self._tag = 0
 
     # ---------------------------------------------------------------------------------------------- run
     def _run_ops(self, only=None):
         """Issue the launch sequence on the current stream (+ the side stream between fork / join markers).
         `only`: optional set of op names to issue (markers are always honoured), e.g. {'conv'} for the roofline graph."""
+        if torch.cuda.current_device() != self.dev.index:       # every launch goes to the engine's device and its streams
+            with torch.cuda.device(self.dev):
+                return self._run_ops(only)
         s0 = torch.cuda.current_stream(self.dev)
+        ntag = max([t for t in self.op_tags if isinstance(t, int)] + [1])
         if self.side_stream is None:
             self.side_stream = torch.cuda.Stream(device=self.dev)
-        s1 = self.side_stream
-        for f, tag, name in zip(self.ops, self.op_tags, self.op_names):
-            if only is not None and f is not None and name not in only:
-                continue
+            self.side_streams = [self.side_stream] + [torch.cuda.Stream(device=self.dev) for _ in range(ntag - 1)]
+        side = self.side_streams
+        entries = [(f, tag) for f, tag, name in zip(self.ops, self.op_tags, self.op_names)
+                   if not (only is not None and f is not None and name not in only)]
+        used = set()
+        for i, (f, tag) in enumerate(entries):
             if tag == 'fork':
-                s1.wait_stream(s0)
+                # only the side streams that get work before the next join enter the capture (an unjoined stream is an error)
+                used = set()
+                for f2, t2 in entries[i + 1:]:
+                    if t2 == 'join':
+                        break
+                    if isinstance(t2, int) and t2 >= 1:
+                        used.add(t2 - 1)
+                for k in sorted(used):
+                    side[k].wait_stream(s0)
             elif tag == 'join':
-                s0.wait_stream(s1)
-            elif tag == 1:
-                with torch.cuda.stream(s1):
+                for k in sorted(used):
+                    s0.wait_stream(side[k])
+                used = set()
+            elif isinstance(tag, int) and tag >= 1:
+                with torch.cuda.stream(side[tag - 1]):
                     f()
             else:
                 f()
 
     def forward(self, img=None):
         """img: NCHW fp32 CUDA tensor (or None to reuse the resident input).  Returns the device result record."""
+        if torch.cuda.current_device() != self.dev.index:
+            with torch.cuda.device(self.dev):
+                return self.forward(img)
         if img is not None:
             self.img.copy_(img, non_blocking=True)
         if self.use_graph:
@@ -540,7 +584,11 @@ class SipMaskEngine(object):
         """img_u8: uint8 BGR HWC CUDA image straight from the decoder.  Resize (keep ratio, mmcv.imrescale rule towards this
         engine's img_shape) + mean subtraction + padding + layout run in ONE kernel that writes the stem's input
         (SURVEY.md 8f-3); the rest of the step is the CUDA graph without its `image_to_nhwc8` node.  The resized size must
-        equal the engine's img_shape (one engine per input resolution in round 1)."""
+        equal the engine's img_shape (one engine per input resolution); batch 1."""
+        assert self.N == 1, 'forward_raw preprocesses one image'
+        if torch.cuda.current_device() != self.dev.index:
+            with torch.cuda.device(self.dev):
+                return self.forward_raw(img_u8, mean)
         C.preprocess_u8(img_u8, self.img_shape[:2], self.img8, mean)
         if self.use_graph:
             if getattr(self, 'graph_raw', None) is None:

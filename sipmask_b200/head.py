@@ -54,19 +54,52 @@ class _FeatureAlign(nn.Module):
 
 class _HeadBase(nn.Module):
     fcos = False
+    MAX_ENGINES = 8          # COCO evaluation sees a handful of padded shapes; each engine owns ~0.3 GB of activations
 
     def _engine(self, feats):
+        """Engine (launch plans + activation buffers) for this set of feature-map sizes.  Packed weights are cached once
+        per parameter version and shared by all engines; engines live in a small LRU keyed by (sizes, device), so a change
+        of input resolution does not repack / re-upload the weights, and a repeated resolution re-uses its plans."""
+        from collections import OrderedDict
         sizes = tuple((f.shape[2], f.shape[3]) for f in feats)
-        key = (sizes, feats[0].device, self._param_version())
-        if getattr(self, '_eng_key', None) != key:
+        dev = feats[0].device
+        ver = (self._param_version(), dev)
+        if getattr(self, '_wver', None) != ver:
+            self._wver, self._wcache, self._engines = ver, {}, OrderedDict()
+        key = (sizes, dev)
+        eng = self._engines.get(key)
+        if eng is None:
             sd = {k: v.detach() for k, v in self.state_dict().items()}
-            self._eng = SipMaskEngine(sd, (0, 0), batch=feats[0].shape[0], stacked_convs=self.stacked_convs,
-                                      gn=self.norm_cfg is not None, ssd_flag=getattr(self, 'ssd_flag', False),
-                                      num_classes=self.num_classes, strides=self.strides, device=feats[0].device,
-                                      use_graph=False, head_only=True, feat_sizes=sizes, in_channels=self.in_channels,
-                                      fcos=self.fcos, prefix_head='', build_postproc=False)
-            self._eng_key = key
-        return self._eng
+            eng = SipMaskEngine(sd, (0, 0), batch=1, stacked_convs=self.stacked_convs,
+                                gn=self.norm_cfg is not None, ssd_flag=getattr(self, 'ssd_flag', False),
+                                num_classes=self.num_classes, strides=self.strides, device=dev,
+                                use_graph=False, head_only=True, feat_sizes=sizes, in_channels=self.in_channels,
+                                fcos=self.fcos, prefix_head='', build_postproc=False, share_weights=self._wcache)
+            self._engines[key] = eng
+            while len(self._engines) > self.MAX_ENGINES:
+                self._engines.popitem(last=False)
+        else:
+            self._engines.move_to_end(key)
+        return eng
+
+    def _run_images(self, feats, collect):
+        """The engine processes one image per pass (imgs_per_gpu = 1 at test time, detectors/base.py:118-119); a batched
+        call loops over the images.  `collect(eng)` returns the outputs of one image; they are CLONED because the engine's
+        buffers are overwritten by the next pass."""
+        eng = self._engine(feats)
+        per_img = []
+        for i in range(feats[0].shape[0]):
+            eng.load_features([f[i:i + 1] for f in feats])
+            eng._run_ops()
+            per_img.append([[t.clone() for t in lst] if isinstance(lst, (list, tuple)) else lst.clone() for lst in collect(eng)])
+        if len(per_img) == 1:
+            return per_img[0]
+        out = []
+        for j in range(len(per_img[0])):
+            col = [p[j] for p in per_img]
+            out.append([torch.cat([c[l] for c in col], 0) for l in range(len(col[0]))] if isinstance(col[0], list)
+                       else torch.cat(col, 0))
+        return out
 
     def _param_version(self):
         return tuple(p._version for p in self.parameters())
@@ -90,8 +123,10 @@ class SipMaskHead(_HeadBase):
                  center_sample_radius=1.5, ssd_flag=False, rescoring_flag=False, loss_cls=None, loss_bbox=None,
                  loss_centerness=None, conv_cfg=None, norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
         super().__init__()
-        if in_channels != 256 or feat_channels != 256:
-            raise NotImplementedError('the GroupNorm-statistics epilogue is specialised for 256 feature channels')
+        if in_channels % 64 != 0 or feat_channels != 256:
+            raise NotImplementedError('in_channels must be a multiple of 64 (one 128-byte K row of the implicit GEMM) and '
+                                      'feat_channels 256 (GroupNorm-statistics epilogue: 8 channels per group; the prototype '
+                                      'branch concatenates 3 x 256 channels, sipmask_head.py:197-198)')
         self.num_classes, self.cls_out_channels = num_classes, num_classes - 1
         self.in_channels, self.feat_channels, self.stacked_convs = in_channels, feat_channels, stacked_convs
         self.strides, self.regress_ranges = tuple(strides), regress_ranges
@@ -139,12 +174,12 @@ class SipMaskHead(_HeadBase):
     @torch.no_grad()
     def forward(self, feats):
         """feats: tuple of 5 NCHW CUDA tensors -> (cls_scores, bbox_preds, centernesses, cof_preds: lists of 5 NCHW
-        fp32 views; feat_masks [N,32,4*h3,4*w3] fp16 view) - sipmask_head.py:241-287."""
-        eng = self._engine(feats)
-        eng.load_features(feats)
-        eng._run_ops()
-        o = eng.head_outputs()
-        return o['cls'], o['bbox'], o['ctr'], o['cof'], o['feat_masks']
+        fp32 tensors; feat_masks [N,32,4*h3,4*w3] fp16) - sipmask_head.py:241-287.  The returned tensors are the caller's
+        (copies of the engine buffers); batches are processed image by image."""
+        def collect(eng):
+            o = eng.head_outputs()
+            return o['cls'], o['bbox'], o['ctr'], o['cof'], o['feat_masks']
+        return tuple(self._run_images(feats, collect))
 
     @torch.no_grad()
     def get_bboxes(self, cls_scores, bbox_preds, centernesses, cof_preds, feat_masks, img_metas, cfg, rescale=None):
@@ -191,8 +226,8 @@ class FCOSHead(_HeadBase):
                  center_sample_radius=1.5, loss_cls=None, loss_bbox=None, loss_centerness=None, conv_cfg=None,
                  norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
         super().__init__()
-        if in_channels != 256 or feat_channels != 256:
-            raise NotImplementedError('the GroupNorm-statistics epilogue is specialised for 256 feature channels')
+        if in_channels % 64 != 0 or feat_channels != 256:
+            raise NotImplementedError('in_channels must be a multiple of 64 and feat_channels 256 (GroupNorm-statistics epilogue)')
         self.num_classes, self.cls_out_channels = num_classes, num_classes - 1
         self.in_channels, self.feat_channels, self.stacked_convs = in_channels, feat_channels, stacked_convs
         self.strides, self.regress_ranges = tuple(strides), regress_ranges
@@ -220,16 +255,16 @@ class FCOSHead(_HeadBase):
     @torch.no_grad()
     def forward(self, feats):
         """-> (cls_scores, bbox_preds, centernesses), lists of 5 NCHW fp32 tensors (fcos_head.py:118-135)."""
-        eng = self._engine(feats)
-        eng.load_features(feats)
-        eng._run_ops()
         ncls = self.cls_out_channels
-        cls, box, ctr = [], [], []
-        for l, (cc, rc) in enumerate(eng.level_views):
-            cls.append(cc[..., :ncls].permute(0, 3, 1, 2))
-            ctr.append(cc[..., ncls:ncls + 1].permute(0, 3, 1, 2))
-            box.append((rc[..., :4] * eng.scales[l]).exp().permute(0, 3, 1, 2))     # scale(x).float().exp() (:134)
-        return cls, box, ctr
+
+        def collect(eng):
+            cls, box, ctr = [], [], []
+            for l, (cc, rc) in enumerate(eng.level_views):
+                cls.append(cc[..., :ncls].permute(0, 3, 1, 2))
+                ctr.append(cc[..., ncls:ncls + 1].permute(0, 3, 1, 2))
+                box.append((rc[..., :4] * eng.scales[l]).exp().permute(0, 3, 1, 2))     # scale(x).float().exp() (:134)
+            return cls, box, ctr
+        return tuple(self._run_images(feats, collect))
 
     @torch.no_grad()
     def get_bboxes(self, cls_scores, bbox_preds, centernesses, img_metas, cfg, rescale=None):

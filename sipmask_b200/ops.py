@@ -32,6 +32,7 @@ def _dt(t):
 
 
 # ------------------------------------------------------------------------------------------ CropSplit
+@L.device_guard
 def crop_split(data, rois, c=2):
     """data [c*c,H,W,N] contiguous, rois [N,4] -> [H,W,N] (ops/crop/crop_split.py:12-25)."""
     _need_cuda(data, rois)
@@ -55,6 +56,7 @@ class CropSplit(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ nms
+@L.device_guard
 def nms(dets, iou_thr, device_id=None, cmp_ge=False):
     """Same contract as mmdet.ops.nms: returns (dets[inds], inds); numpy in -> numpy out."""
     is_numpy = isinstance(dets, np.ndarray)
@@ -83,6 +85,7 @@ def nms(dets, iou_thr, device_id=None, cmp_ge=False):
 
 
 # ------------------------------------------------------------------------------------- decode + top-k
+@L.device_guard
 def decode_topk(cls_list, box_list, ctr_list, strides, img_shape, nms_pre, scale_factor=None, box_scales=None):
     """Per-level tensors channel-last fp32: cls [h,w,C], box [h,w,4] (distances x stride), ctr [h,w,1|].
 
@@ -124,6 +127,7 @@ def decode_topk(cls_list, box_list, ctr_list, strides, img_shape, nms_pre, scale
 
 
 # ------------------------------------------------------------------------------------ multi-class NMS
+@L.device_guard
 def multiclass_nms_idx(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None,
                        has_bg_column=True, cmp_ge=False, return_count_tensor=False):
     """Same contract as mmdet.core.multiclass_nms_idx (bbox_nms.py:79-146): returns
@@ -158,6 +162,7 @@ def multiclass_nms_idx(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-
     return det[:k], lab[:k], idx[:k]
 
 
+@L.device_guard
 def fast_nms(boxes, scores, ctr, iou_threshold=0.5, top_k=200, score_thr=0.1, max_num=100,
              return_count_tensor=False):
     """boxes [n,4], scores [n,C] sigmoid (NOT yet multiplied by ctr), ctr [n].
@@ -186,6 +191,7 @@ def fast_nms(boxes, scores, ctr, iou_threshold=0.5, top_k=200, score_thr=0.1, ma
     return det[:k], lab[:k], idx[:k]
 
 
+@L.device_guard
 def gather_rows(src, idx, count, max_rows):
     """dst[i] = src[idx[i]] for i < count (device int32), zeros after; src [n,E] fp32 (row pitch = stride(0))."""
     _need_cuda(src, idx, count)
@@ -198,6 +204,7 @@ def gather_rows(src, idx, count, max_rows):
 
 
 # -------------------------------------------------------------------------------------- mask assembly
+@L.device_guard
 def mask_assemble(protos, cofs, boxes, box_scale, layout='chw', out_dtype=torch.float32, out=None):
     """protos [32,H,W] ('chw') or [H,W,32] ('hwc'), fp32/fp16; cofs [N,128] fp32; boxes [N,4] fp32
     (image space); rois = boxes * box_scale (scalar or 4-vector).  Returns pos_masks [N,H,W]."""
@@ -220,35 +227,64 @@ def mask_assemble(protos, cofs, boxes, box_scale, layout='chw', out_dtype=torch.
     return out
 
 
-def mask_upsample2_threshold(pos, out_hw, thr=0.4, out=None):
-    """pos [N,H,W] -> uint8 [N,out_h,out_w]: x2 bilinear (align_corners=False), > thr, top-left paste."""
+def resize_spec(H, W, up, legacy_interp=False):
+    """F.interpolate(scale_factor=up, mode='bilinear', align_corners=False) on an [H, W] map -> (full_h, full_w, ry, rx):
+    interpolated size floor(H * up_h), floor(W * up_w) (computed in double like torch) and the source step per output pixel,
+    float32(1 / up) as PyTorch >= 1.6 uses it, or 0 (= in / out, recompute_scale_factor=True, PyTorch <= 1.5) when
+    legacy_interp.  `up` is a float or an (h, w) pair: 2 / scale_factor (sipmask_head.py:629-633)."""
+    import math
+    uh, uw = (float(up[0]), float(up[1])) if isinstance(up, (tuple, list)) else (float(up), float(up))
+    full_h, full_w = int(math.floor(float(H) * uh)), int(math.floor(float(W) * uw))
+    if legacy_interp:
+        return full_h, full_w, 0.0, 0.0
+    return full_h, full_w, float(np.float32(1.0 / uh)), float(np.float32(1.0 / uw))
+
+
+@L.device_guard
+def mask_resize_threshold(pos, up, out_hw, thr=0.4, out=None, legacy_interp=False):
+    """pos [N,H,W] -> uint8 [N,out_h,out_w]: bilinear resize by `up` (align_corners=False), > thr, top-left paste
+    (sipmask_head.py:629-633,648-654)."""
     _need_cuda(pos)
     pos = pos.contiguous()
     N, H, W = pos.shape
+    fh, fw, ry, rx = resize_spec(H, W, up, legacy_interp)
     if out is None:
         out = torch.empty((N, int(out_hw[0]), int(out_hw[1])), dtype=torch.uint8, device=pos.device)
-    L.check(L.lib().smb_mask_upsample2_threshold(L.ptr(pos), _dt(pos), L.ptr(out), N, H, W, int(out_hw[0]),
-                                                 int(out_hw[1]), ctypes.c_float(thr), L.stream_ptr()),
-            'smb_mask_upsample2_threshold')
+    L.check(L.lib().smb_mask_resize_threshold(L.ptr(pos), _dt(pos), L.ptr(out), N, H, W, fh, fw, ctypes.c_float(ry),
+                                              ctypes.c_float(rx), int(out_hw[0]), int(out_hw[1]), ctypes.c_float(thr),
+                                              L.stream_ptr()), 'smb_mask_resize_threshold')
     return out
 
 
-def mask_upsample2_threshold_pack(pos, out_hw, thr=0.4, out=None):
+@L.device_guard
+def mask_resize_threshold_pack(pos, up, out_hw, thr=0.4, out=None, legacy_interp=False):
     """Bit-packed masks: int32 [N,out_h,ceil(out_w/32)], pixel x = bit (x & 31) of word (x >> 5)."""
     _need_cuda(pos)
     pos = pos.contiguous()
     N, H, W = pos.shape
+    fh, fw, ry, rx = resize_spec(H, W, up, legacy_interp)
     words = (int(out_hw[1]) + 31) // 32
     if out is None:
         out = torch.empty((N, int(out_hw[0]), words), dtype=torch.int32, device=pos.device)
-    L.check(L.lib().smb_mask_upsample2_threshold_pack(L.ptr(pos), _dt(pos), L.ptr(out), N, H, W, int(out_hw[0]),
-                                                      int(out_hw[1]), ctypes.c_float(thr), L.stream_ptr()),
-            'smb_mask_upsample2_threshold_pack')
+    L.check(L.lib().smb_mask_resize_threshold_pack(L.ptr(pos), _dt(pos), L.ptr(out), N, H, W, fh, fw, ctypes.c_float(ry),
+                                                   ctypes.c_float(rx), int(out_hw[0]), int(out_hw[1]), ctypes.c_float(thr),
+                                                   L.stream_ptr()), 'smb_mask_resize_threshold_pack')
     return out
 
 
-def mask_assemble_pack(protos, cofs, boxes, box_scale, out_hw, thr=0.4, layout='chw', out=None):
-    """Fused mask path: prototypes -> bit-packed thresholded masks int32 [N,out_h,ceil(out_w/32)] (no pos_masks tensor)."""
+def mask_upsample2_threshold(pos, out_hw, thr=0.4, out=None):
+    """scale_factor == 1 shorthand: x2 bilinear (align_corners=False), > thr, top-left paste."""
+    return mask_resize_threshold(pos, 2.0, out_hw, thr, out)
+
+
+def mask_upsample2_threshold_pack(pos, out_hw, thr=0.4, out=None):
+    return mask_resize_threshold_pack(pos, 2.0, out_hw, thr, out)
+
+
+@L.device_guard
+def mask_assemble_pack(protos, cofs, boxes, box_scale, out_hw, thr=0.4, layout='chw', out=None, up=2.0, legacy_interp=False):
+    """Fused mask path: prototypes -> bit-packed thresholded masks int32 [N,out_h,ceil(out_w/32)] (no pos_masks tensor);
+    `up` = 2 / scale_factor (float or (h, w)) is the bilinear resize factor of sipmask_head.py:629-633."""
     _need_cuda(protos, cofs, boxes)
     protos = protos.contiguous()
     if layout == 'chw':
@@ -260,12 +296,14 @@ def mask_assemble_pack(protos, cofs, boxes, box_scale, out_hw, thr=0.4, layout='
     boxes = boxes.float().contiguous()
     a = np.atleast_1d(np.asarray(box_scale, dtype=np.float32))
     bs = L.f4(a if a.size == 4 else [a[0]] * 4)
+    fh, fw, ry, rx = resize_spec(H, W, up, legacy_interp)
     words = (int(out_hw[1]) + 31) // 32
     if out is None:
         out = torch.empty((N, int(out_hw[0]), words), dtype=torch.int32, device=protos.device)
     L.check(L.lib().smb_mask_assemble_pack(L.ptr(protos), _dt(protos), 1 if layout == 'hwc' else 0, L.ptr(cofs), L.ptr(boxes),
-                                           bs, L.ptr(out), H, W, N, int(out_hw[0]), int(out_hw[1]), ctypes.c_float(thr),
-                                           L.stream_ptr()), 'smb_mask_assemble_pack')
+                                           bs, L.ptr(out), H, W, N, fh, fw, ctypes.c_float(ry), ctypes.c_float(rx),
+                                           int(out_hw[0]), int(out_hw[1]), ctypes.c_float(thr), L.stream_ptr()),
+            'smb_mask_assemble_pack')
     return out
 
 
@@ -278,6 +316,7 @@ def unpack_mask_bits(bits, out_w):
     return px[:, :, :out_w].contiguous()
 
 
+@L.device_guard
 def mask_rle_counts(mask_bits, H, W, n_valid=None, cap=8192):
     """Device-side COCO RLE (smb_mask_rle_counts): bit-packed masks int32 [N,mask_h,words] cropped to H x W ->
     (counts uint32-as-int32 [N,cap] column-major run lengths, n_counts int32 [N]).  n_valid: optional device int tensor."""
@@ -304,6 +343,7 @@ def rle_to_string(counts):
     return buf.raw[:n]
 
 
+@L.device_guard
 def masks_to_rle(mask_bits, H, W, k, cap=8192):
     """k valid bit-packed masks -> list of k COCO RLE dicts {'size': [H, W], 'counts': bytes}: one kernel, one small D2H
     (k * runs * 4 bytes instead of k * H * W mask bytes), string packing in C on the host."""
@@ -320,6 +360,7 @@ def masks_to_rle(mask_bits, H, W, k, cap=8192):
     return [{'size': [int(H), int(W)], 'counts': rle_to_string(c_host[j, :n_host[j]])} for j in range(k)]
 
 
+@L.device_guard
 def conv3x3s2_relu(x, weight, bias):
     """One `convs_scoring` ConvModule (sipmask_head.py:200-214): NCHW fp32 conv3x3 stride 2 pad 0 + bias + ReLU."""
     _need_cuda(x, weight, bias)
@@ -333,6 +374,7 @@ def conv3x3s2_relu(x, weight, bias):
     return out
 
 
+@L.device_guard
 def mask_rescore(pos_masks, conv_weights, conv_biases, w1x1, b1x1, labels, det, n_valid=None):
     """SipMask++ rescoring (sipmask_head.py:635-643): pos_masks [N,Hm,Wm] fp32 (cropped stride-2 masks) -> mask_scores [N]."""
     x = pos_masks.float().unsqueeze(1)
@@ -347,3 +389,77 @@ def mask_rescore(pos_masks, conv_weights, conv_biases, w1x1, b1x1, labels, det, 
                                      L.ptr(labels.long().contiguous()), L.ptr(det.float().contiguous()), L.ptr(n_valid),
                                      L.ptr(scores), L.stream_ptr()), 'smb_mask_rescore')
     return scores
+
+
+# ----------------------------------------------------------------------------------- DeformConv (operator API)
+class DeformConv(nn.Module):
+    """Drop-in for `mmdet.ops.DeformConv` (MM/mmdet/ops/dcn/deform_conv.py:192-255): same constructor keywords, same
+    `weight` parameter ([out, in, kh, kw], uniform(-1/sqrt(fan_in), +)), `forward(x[N,C,H,W], offset[N,dg*2*k*k,H,W])`.
+
+    Replaces deform_conv_cuda.deform_conv_forward_cuda (ops/dcn/src/deform_conv_cuda.cpp:152-260: im2col kernel + addmm)
+    by `smb_deform_im2col` (channel-last bilinear gather, fp16 columns) + the tcgen05 GEMM (fp32 accumulate).  The hot
+    path only uses 3x3 / stride 1 / padding 1 / dilation 1 / groups 1 (FeatureAlign `conv_adaption`, sipmask_head.py:35-41,
+    and DeformConvPack in the ++ backbone, resnet.py:146-168); other geometries raise.  NCHW in, NCHW out, x.dtype kept."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super().__init__()
+        assert not bias
+        assert in_channels % groups == 0, 'in_channels {} cannot be divisible by groups {}'.format(in_channels, groups)
+        assert out_channels % groups == 0, 'out_channels {} cannot be divisible by groups {}'.format(out_channels, groups)
+        pair = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v)       # noqa: E731
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.dilation = pair(kernel_size), pair(stride), pair(padding), pair(dilation)
+        self.groups, self.deformable_groups = groups, deformable_groups
+        self.transposed, self.output_padding = False, (0,)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        self.reset_parameters()
+        self._packed = None
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / np.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def _check_geometry(self):
+        if not (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1) and self.dilation == (1, 1)
+                and self.groups == 1):
+            raise NotImplementedError('sipmask_b200.ops.DeformConv: only 3x3 / stride 1 / padding 1 / dilation 1 / groups 1 '
+                                      '(the geometries on the SipMask inference path)')
+        c, dg = self.in_channels, self.deformable_groups
+        if c % 64 or self.out_channels % 16 or c % dg or (c // dg) % 8:
+            raise NotImplementedError('sipmask_b200.ops.DeformConv: in_channels %% 64, out_channels %% 16 and '
+                                      '(in_channels / deformable_groups) %% 8 must be 0 (got %d, %d, dg=%d)'
+                                      % (c, self.out_channels, dg))
+
+    @torch.no_grad()
+    def forward(self, x, offset):
+        from . import conv as C
+        _need_cuda(x, offset, self.weight)
+        self._check_geometry()
+        kh, kw = self.kernel_size
+        input_pad = x.size(2) < kh or x.size(3) < kw                      # deform_conv.py:242-254
+        if input_pad:
+            pad_h, pad_w = max(kh - x.size(2), 0), max(kw - x.size(3), 0)
+            x = torch.nn.functional.pad(x, (0, pad_w, 0, pad_h), 'constant', 0).contiguous()
+            offset = torch.nn.functional.pad(offset, (0, pad_w, 0, pad_h), 'constant', 0).contiguous()
+        N, Cin, H, W = x.shape
+        if offset.shape != (N, self.deformable_groups * 2 * kh * kw, H, W):
+            raise L.SmbError('DeformConv: offset shape %s does not match input %s (deform_conv_cuda.cpp:62-150)'
+                             % (tuple(offset.shape), tuple(x.shape)))
+        key = (self.weight._version, self.weight.data_ptr(), x.device)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, C.pack_weight(self.weight, device=x.device)[0])
+        wk = self._packed[1]
+        with torch.cuda.device(x.device):
+            xh = x.permute(0, 2, 3, 1).contiguous().to(torch.float16)
+            off = offset.permute(0, 2, 3, 1).contiguous().float()
+            col = C.deform_im2col(xh, off, self.deformable_groups)
+            out = torch.empty((N, H, W, self.out_channels), dtype=torch.float16, device=x.device)
+            C.ConvPlan(col, wk, out, 1, 1).run()
+            y = out.permute(0, 3, 1, 2).to(x.dtype)
+        if input_pad:
+            y = y[:, :, :y.size(2) - pad_h, :y.size(3) - pad_w]
+        return y.contiguous()

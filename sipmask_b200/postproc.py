@@ -10,6 +10,20 @@ import torch
 from . import ops
 
 
+def mask_up_factors(scale_factor, ssd_flag, scale=2):
+    """`scale / scale_factor` (sipmask_head.py:632) or, on the SSD path, `scale / scale_factor[3:1:-1]` = (h, w) factors
+    (:630) - the bilinear resize factor(s) of pos_masks, as python floats.  The division keeps the operand types of the
+    reference (python float scale_factor -> double, numpy float32 array -> float32)."""
+    if ssd_flag:
+        sf = np.asarray(scale_factor)
+        if sf.size == 4:
+            return tuple(float(v) for v in (scale / sf[3:1:-1]))
+        return float(scale / sf.reshape(-1)[0])
+    if isinstance(scale_factor, np.ndarray):
+        return float(scale / scale_factor.reshape(-1)[0])
+    return float(scale / scale_factor)
+
+
 def _cl(t):
     """CHW (reference layout) or HWC tensor -> channel-last contiguous fp32 [h,w,C]."""
     return t.float().permute(1, 2, 0).contiguous()
@@ -18,7 +32,7 @@ def _cl(t):
 def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides, img_shape, ori_shape,
                       scale_factor, cfg, rescale=False, ssd_flag=False, cmp_ge=False, mask_thr=0.4,
                       channel_last=False, feat_mask_layout='chw', box_scales=None, top_k=200, upsample=True, pack=False,
-                      rescoring=None):
+                      rescoring=None, legacy_interp=False):
     """Inputs per level: CHW tensors like the reference (channel_last=False) or [h,w,C] fp32 views.
     cfg: dict with nms_pre, score_thr, nms.iou_thr, max_per_img."""
     if not channel_last:
@@ -47,19 +61,24 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
     det_cofs = ops.gather_rows(cof_all, loc_kept, cnt, max_num)
     # rois = det * scale_factor / 2 (sipmask_head.py:621-623); scale_factor := 1 when rescale is None
     s4 = (sf if sf.size == 4 else np.repeat(sf, 4)).astype(np.float32)
-    if rescale is None:
+    if rescale is None:                                   # `scale_factor = scale_factor*0+1.0` rebinds it for rois AND resize
         s4 = np.ones(4, np.float32)
+        scale_factor = s4 if sf.size == 4 else 1.0
     box_scale = s4 / 2.0
+    up = mask_up_factors(scale_factor, ssd_flag)
     pos = ops.mask_assemble(feat_mask, det_cofs, det[:, :4].contiguous(), box_scale, layout=feat_mask_layout)
     out = dict(det_bboxes=det, det_labels=lab, idxs_keep=idx, count=cnt, pos_masks=pos, masks=None, mask_scores=None)
     if rescoring is not None:      # SipMask++: dict(conv_w=[6], conv_b=[6], w1x1, b1x1) (sipmask_head.py:635-643)
         out['mask_scores'] = ops.mask_rescore(pos, rescoring['conv_w'], rescoring['conv_b'], rescoring['w1x1'],
                                               rescoring['b1x1'], lab, det, n_valid=cnt)
     if upsample:
+        # masks = interpolate(pos_masks, scale_factor = 2 / scale_factor) > thr, pasted top-left into the ori_shape (rescale)
+        # or img_shape canvas and truncated (sipmask_head.py:629-633,648-654)
         tgt = ori_shape if rescale else img_shape
         if pack:            # bit planes [max, H, ceil(W/32)] for the device RLE encoder (ops.masks_to_rle)
-            out['mask_bits'] = ops.mask_upsample2_threshold_pack(pos, (int(tgt[0]), int(tgt[1])), mask_thr)
+            out['mask_bits'] = ops.mask_resize_threshold_pack(pos, up, (int(tgt[0]), int(tgt[1])), mask_thr,
+                                                              legacy_interp=legacy_interp)
             out['mask_hw'] = (int(tgt[0]), int(tgt[1]))
         else:
-            out['masks'] = ops.mask_upsample2_threshold(pos, (int(tgt[0]), int(tgt[1])), mask_thr)
+            out['masks'] = ops.mask_resize_threshold(pos, up, (int(tgt[0]), int(tgt[1])), mask_thr, legacy_interp=legacy_interp)
     return out

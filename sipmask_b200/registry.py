@@ -16,9 +16,17 @@ def register(force=True):
 
 
 def register_ops(force=True):
-    """Point `mmdet.ops.{CropSplit, nms}` at the sm_100a operators (same call signatures)."""
+    """Point `mmdet.ops.{CropSplit, DeformConv, nms}` at the sm_100a operators (same call signatures;
+    MM/mmdet/ops/__init__.py:5-22 exports)."""
     import mmdet.ops as mmops
     from . import ops
     mmops.CropSplit = ops.CropSplit
+    mmops.DeformConv = ops.DeformConv
     mmops.nms = ops.nms
+    for sub in ('crop', 'dcn', 'nms'):          # `from mmdet.ops.dcn import DeformConv` style imports
+        m = getattr(mmops, sub, None)
+        if m is not None:
+            for name in ('CropSplit', 'DeformConv', 'nms'):
+                if hasattr(m, name):
+                    setattr(m, name, getattr(ops, name))
     return mmops

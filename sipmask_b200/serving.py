@@ -111,7 +111,10 @@ class EnginePool(object):
 
 
 class PipelinedRunner(object):
-    def __init__(self, engines, depth=2):
+    """raw_hw=(h, w): the host hands over the decoder's uint8 BGR HWC image (h*w*3 bytes H2D instead of 4*3*H*W) and the
+    step starts with the fused resize / normalise / pad kernel (engine.forward_raw)."""
+
+    def __init__(self, engines, depth=2, raw_hw=None):
         self.engs = list(engines) if isinstance(engines, (list, tuple)) else [engines]
         self.n = len(self.engs)
         self.eng = engine = self.engs[0]
@@ -123,7 +126,12 @@ class PipelinedRunner(object):
         self.s_h2d = torch.cuda.Stream(device=dev)
         self.s_d2h = torch.cuda.Stream(device=dev)
         self.s_comp = [torch.cuda.Stream(device=dev) for _ in self.engs] if self.n > 1 else [None]
-        self.in_dev = [torch.empty_like(engine.img) for _ in range(ns)]
+        self.raw = raw_hw is not None
+        if self.raw:
+            assert engine.N == 1, 'raw uint8 input: one image per forward'
+            self.in_dev = [torch.empty((int(raw_hw[0]), int(raw_hw[1]), 3), dtype=torch.uint8, device=dev) for _ in range(ns)]
+        else:
+            self.in_dev = [torch.empty_like(engine.img) for _ in range(ns)]
         self.out_dev = [dict(det=torch.empty_like(engine.det), lab=torch.empty_like(engine.labels),
                              cnt=torch.empty_like(engine.count), bits=torch.empty_like(engine.mask_bits)) for _ in range(ns)]
         self.out_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()} for o in self.out_dev]
@@ -134,22 +142,32 @@ class PipelinedRunner(object):
         self.ev_hold = [None] * ns                                      # optional: a consumer still reads out_dev[slot]
         self.i = 0
         self.pending = []
-        self.h2d_bytes = engine.img.numel() * engine.img.element_size()
+        self.h2d_bytes = self.in_dev[0].numel() * self.in_dev[0].element_size()
         self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.out_dev[0].values())
         cur = torch.cuda.current_stream(dev)
         if self.n > 1:
             for st, eng in zip(self.s_comp, self.engs):
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
-                    eng.forward(None)              # warm-up + graph capture on the engine's own stream
-                    eng.forward(None)
+                    self._fwd(eng, 0)              # warm-up + graph capture on the engine's own stream
+                    self._fwd(eng, 0)
             for st in self.s_comp:
                 st.synchronize()
+        else:
+            self._fwd(engine, 0)
+            self._fwd(engine, 0)
+            cur.synchronize()
         for e in self.ev_in_free + self.ev_out_free:
             e.record(cur)
 
+    def _fwd(self, eng, k):
+        if self.raw:
+            eng.forward_raw(self.in_dev[k])
+        else:
+            eng.forward(None)
+
     def submit(self, host_img):
-        """host_img: pinned fp32 NCHW tensor.  Enqueues upload -> graph replay -> download; returns the slot index.
+        """host_img: pinned fp32 NCHW tensor (or pinned uint8 HWC BGR image in raw mode).  Enqueues upload -> graph replay -> download; returns the slot index.
         Nothing here blocks the host."""
         k = self.i % self.nslots
         eng = self.engs[k % self.n]
@@ -161,9 +179,13 @@ class PipelinedRunner(object):
             self.ev_in_ready[k].record(self.s_h2d)
         with torch.cuda.stream(cs):
             cs.wait_event(self.ev_in_ready[k])
-            eng.img.copy_(self.in_dev[k], non_blocking=True)
-            self.ev_in_free[k].record(cs)
-            eng.forward(None)
+            if self.raw:
+                eng.forward_raw(self.in_dev[k])            # preprocess kernel reads the staged uint8 image, then the graph
+                self.ev_in_free[k].record(cs)
+            else:
+                eng.img.copy_(self.in_dev[k], non_blocking=True)
+                self.ev_in_free[k].record(cs)
+                eng.forward(None)
             cs.wait_event(self.ev_out_free[k])
             if self.ev_hold[k] is not None:
                 cs.wait_event(self.ev_hold[k])

@@ -89,7 +89,8 @@ def bind_natives():
     return ref_nms is not None
 
 
-def gen_head_case(name, stacked_convs, gn, ssd_flag, sizes, img_shape, scale_factor, score_thr, seed):
+def gen_head_case(name, stacked_convs, gn, ssd_flag, sizes, img_shape, scale_factor, score_thr, seed, ori_shape=None,
+                  rescoring_flag=False, compact=False):
     from mmdet.models.anchor_heads import sipmask_head as sh
     import mmcv  # the shim
 
@@ -97,9 +98,10 @@ def gen_head_case(name, stacked_convs, gn, ssd_flag, sizes, img_shape, scale_fac
         __getattr__ = dict.get
 
     head = sh.SipMaskHead(num_classes=81, in_channels=256, stacked_convs=stacked_convs, ssd_flag=ssd_flag,
-                          strides=[8, 16, 32, 64, 128],
+                          rescoring_flag=rescoring_flag, strides=[8, 16, 32, 64, 128],
                           norm_cfg=dict(type='GN', num_groups=32, requires_grad=True) if gn else None)
-    sd = synth.head_state_dict(seed=seed, prefix='', stacked_convs=stacked_convs, gn=gn, cls_bias=-2.0)
+    sd = synth.head_state_dict(seed=seed, prefix='', stacked_convs=stacked_convs, gn=gn, cls_bias=-2.0,
+                               rescoring_flag=rescoring_flag)
     missing = head.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys, missing
     assert all(k.startswith(('loss', 'crop')) for k in missing.missing_keys), missing
@@ -122,11 +124,21 @@ def gen_head_case(name, stacked_convs, gn, ssd_flag, sizes, img_shape, scale_fac
     # keep the binary masks instead of RLE
     sh.mask_util.encode = lambda arr: [np.array(arr[:, :, 0], order='C').copy()]
     cfg = Cfg(nms_pre=60, min_bbox_size=0, score_thr=score_thr, nms=Cfg(type='nms', iou_thr=0.5), max_per_img=20)
-    meta = dict(img_shape=img_shape, ori_shape=img_shape, scale_factor=scale_factor)
+    ori_shape = img_shape if ori_shape is None else ori_shape
+    meta = dict(img_shape=img_shape, ori_shape=ori_shape, scale_factor=scale_factor)
     with torch.no_grad():
         outs = head(feats)
         res = head.get_bboxes(*outs, [meta], cfg, rescale=True)[0]
     det_bboxes, det_labels, cls_segms = res
+    mask_scores = None
+    if rescoring_flag:                                  # (cls_segms, mask_scores) tuple, sipmask_head.py:659-660
+        cls_segms, ms = cls_segms
+        mask_scores = np.zeros(det_bboxes.shape[0], np.float32)
+        cnt = [0] * 80
+        for i in range(det_bboxes.shape[0]):
+            l = int(det_labels[i])
+            mask_scores[i] = np.atleast_1d(ms[l])[cnt[l]]
+            cnt[l] += 1
     masks = []
     # cls_segms is per class in detection order; rebuild detection-ordered mask stack
     counters = [0] * 80
@@ -136,14 +148,22 @@ def gen_head_case(name, stacked_convs, gn, ssd_flag, sizes, img_shape, scale_fac
         counters[l] += 1
     out = dict(
         det_bboxes=det_bboxes.numpy(), det_labels=det_labels.numpy(),
-        masks=np.stack(masks).astype(np.uint8) if masks else np.zeros((0,) + tuple(img_shape[:2]), np.uint8),
-        feat_masks=outs[4].numpy(),
-        img_shape=np.array(img_shape), scale_factor=np.atleast_1d(np.asarray(scale_factor, np.float32)),
+        masks=np.stack(masks).astype(np.uint8) if masks else np.zeros((0,) + tuple(ori_shape[:2]), np.uint8),
+        img_shape=np.array(img_shape), ori_shape=np.array(ori_shape), rescoring_flag=np.array(int(rescoring_flag)), scale_factor=np.atleast_1d(np.asarray(scale_factor, np.float32)),
         stacked_convs=np.array(stacked_convs), gn=np.array(int(gn)), ssd_flag=np.array(int(ssd_flag)),
         score_thr=np.array(score_thr, np.float32), seed=np.array(seed), sizes=np.array(sizes),
         nms_pre=np.array(60), max_per_img=np.array(20),
     )
-    for i in range(len(sizes)):
+    if mask_scores is not None:
+        out['mask_scores'] = mask_scores
+    if compact:
+        # large case: the inputs are regenerated by the test from `seed` (same torch.Generator sequence) and the head outputs
+        # through the oracle head (itself pinned to 1e-4 by the small fixtures); only the reference's RESULTS are stored
+        out['masks'] = np.packbits(out['masks'], axis=-1)
+        out['mask_w'] = np.array(ori_shape[1])
+    else:
+        out['feat_masks'] = outs[4].numpy()
+    for i in range(len(sizes) if not compact else 0):
         out['feat%d' % i] = feats[i].numpy()
         out['cls%d' % i] = outs[0][i].numpy()
         out['bbox%d' % i] = outs[1][i].numpy()
@@ -181,6 +201,54 @@ def gen_backbone_case(name, seed=1):
     print(name, [tuple(t.shape) for t in p])
 
 
+def _list_literals(src):
+    """All top-level `[...]` list literals that follow an `np.array(` in `src`, evaluated (data only)."""
+    import ast
+    vals, i = [], 0
+    while True:
+        i = src.find('np.array(', i)
+        if i < 0:
+            return vals
+        j = i + len('np.array(')
+        while src[j] in ' \n':
+            j += 1
+        if src[j] != '[':
+            i = j
+            continue
+        depth, k = 0, j
+        while True:
+            depth += {'[': 1, ']': -1}.get(src[k], 0)
+            k += 1
+            if depth == 0:
+                break
+        vals.append(ast.literal_eval(src[j:k]))
+        i = k
+
+
+def _bm_vectors():
+    """SipMask-benchmark/tests/test_nms.py:16-58 (5 boxes x 5 thresholds) and :60-233 (53 boxes, thr 0.5): the known-answer
+    vectors are read from the reference's test file as DATA (boxes are xyxy, passed to box_nms as they are)."""
+    src = open('/root/reference/SipMask-benchmark/tests/test_nms.py').read()
+    a = src.index('def test_nms_cpu'); b = src.index('def test_nms1_cpu'); c = src.index('def test_nms_cuda') if 'def test_nms_cuda' in src else len(src)
+    import ast
+    l5 = _list_literals(src[a:b])
+    inp = np.asarray(l5[0], np.float32).reshape(-1, 5)
+    seg = src[a:b]
+    thrs = ast.literal_eval(seg[seg.index('test_thresh =') + 13:seg.index('gt_indices')].strip())
+    gts = ast.literal_eval(seg[seg.index('gt_indices =') + 12:seg.index('for thresh')].strip())
+    keeps = -np.ones((len(gts), 5), np.int64)
+    for i, gt in enumerate(gts):
+        keeps[i, :len(gt)] = gt
+    l53 = _list_literals(src[b:c])
+    seg = src[b:c]
+    thr53 = float(seg[seg.index('box_nms(boxes, scores,') + 22:].split(')')[0])
+    out = dict(bm5_boxes_xyxy=inp[:, :4], bm5_scores=inp[:, 4], bm5_thrs=np.asarray(thrs, np.float32), bm5_keeps=keeps,
+               bm53_boxes_xyxy=np.asarray(l53[0], np.float32), bm53_scores=np.asarray(l53[1], np.float32),
+               bm53_gt_indices=np.asarray(l53[2], np.int64), bm53_thr=np.array(thr53, np.float32))
+    assert out['bm53_boxes_xyxy'].shape == (53, 4) and out['bm53_scores'].shape == (53,)
+    return out
+
+
 def gen_nms_vectors():
     """Known-answer NMS vectors copied as DATA from the reference's tests:
     MM/tests/test_nms.py:17-41, MM/mmdet/ops/nms/nms_wrapper.py:25-34, BM/tests/test_nms.py:16-58."""
@@ -195,6 +263,7 @@ def gen_nms_vectors():
                                 [35.2, 11.7, 39.7, 15.7, 0.3]], np.float32)
     out['mm7_thr'] = np.array(0.7, np.float32)
     out['mm7_num_keep'] = np.array(3)
+    out.update(_bm_vectors())
     np.savez_compressed(os.path.join(HERE, 'nms_known_answers.npz'), **out)
 
 
@@ -209,3 +278,13 @@ if __name__ == '__main__':
     gen_head_case('ref_head_ssd2', 2, False, True, sizes, (96, 128, 3),
                   np.array([1.0, 1.0, 1.0, 1.0], np.float32), 0.1, seed=5)
     gen_backbone_case('ref_backbone_r50_64x96')
+    # scale_factor != 1 and ori_shape != img_shape (rescale=True): boxes are divided by the scale factor and the masks are
+    # interpolated by 2/scale_factor into ori-image space (sipmask_head.py:587-588,623,629-633,648-654)
+    gen_head_case('ref_head_gn4_sf', 4, True, False, sizes, (96, 125, 3), 1.6667, 0.05, seed=3, ori_shape=(58, 75, 3))
+    gen_head_case('ref_head_ssd2_sf', 2, False, True, sizes, (96, 128, 3),
+                  np.array([1.7, 1.3, 1.7, 1.3], np.float32), 0.1, seed=5, ori_shape=(74, 75, 3))
+    # SipMask++ mask rescoring (rescoring_flag=True, sipmask_head.py:200-219,635-643): six unpadded stride-2 convs need
+    # >= 127 mask rows -> 256 x 256 image
+    sizes_r = [(32, 32), (16, 16), (8, 8), (4, 4), (2, 2)]
+    gen_head_case('ref_head_ssd2_rescore', 2, False, True, sizes_r, (256, 256, 3),
+                  np.array([1.0, 1.0, 1.0, 1.0], np.float32), 0.1, seed=7, rescoring_flag=True, compact=True)

@@ -35,6 +35,23 @@ def _worker(rank, world, port, q):
         gg = torch.Generator().manual_seed(r)
         exp = torch.rand(kk, 5, generator=gg) + r
         ok = ok and b.shape == (kk, 5) and torch.allclose(b, exp) and l.tolist() == (torch.arange(kk) + 10 * r).tolist()
+    # the run-level log: K images appended locally, ONE collective at the end
+    log = D.RecordLog(4, max_num, 'cpu')
+    for i in range(3):
+        log.append(det + i, lab, torch.tensor([k], dtype=torch.int32))
+    allrec = log.gather()
+    ok = ok and tuple(allrec.shape) == (world, 4, max_num, 7)
+    for r in range(world):
+        kk = 3 + 4 * r
+        gg = torch.Generator().manual_seed(r)
+        exp = torch.rand(kk, 5, generator=gg) + r
+        for i in range(3):
+            ok = ok and torch.allclose(allrec[r, i, :kk, :5], exp + i) and int(allrec[r, i, :, 6].sum()) == kk
+    # instance masks: RLE run-length tensors gathered as they are
+    counts = torch.full((max_num, 6), rank, dtype=torch.int32)
+    ncnt = torch.full((max_num,), 2 + rank, dtype=torch.int32)
+    gc, gn = D.gather_rle(counts, ncnt)
+    ok = ok and gc.shape == (world, max_num, 6) and all(int(gc[r].max()) == r and int(gn[r][0]) == 2 + r for r in range(world))
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()

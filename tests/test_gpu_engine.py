@@ -211,3 +211,68 @@ def test_backbone_dcn_sipmask_pp():
         e = _rel(p.float().cpu().permute(0, 3, 1, 2), r)
         assert e < 2e-2, 'FPN level %d rel err %g' % (l, e)
     assert int(out['count'][0]) > 0
+
+
+@pytest.mark.parametrize('stacked,gn,ssd', [(4, True, False), (2, False, True)])
+def test_batched_forward_matches_single_image_engines(stacked, gn, ssd):
+    """batch > 1 per forward (BASELINE config 4 is bs=32; get_bboxes loops over images, sipmask_head.py:517-540): every image
+    of a 3-image batch gives exactly the record the batch-1 engine gives for it (detections, labels, kept indices, masks)."""
+    from sipmask_b200 import synth
+    from sipmask_b200.engine import SipMaskEngine
+    H, W = 96, 128
+    sd = synth.detector_state_dict(depth=50, stacked_convs=stacked, gn=gn, seed=1, cls_bias=-2.5)
+    cfg = dict(nms_pre=200, score_thr=0.1 if ssd else 0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=30)
+    sf = np.ones(4, dtype=np.float32) if ssd else 1.0
+    imgs = torch.cat([synth.synthetic_image(H, W, seed=s) for s in range(3)], 0)
+    one = SipMaskEngine(sd, (H, W), stacked_convs=stacked, gn=gn, ssd_flag=ssd, test_cfg=cfg, img_shape=(H, W - 3, 3),
+                        scale_factor=sf, use_graph=True)
+    want = []
+    for i in range(3):
+        o = one.forward(imgs[i:i + 1].cuda())
+        torch.cuda.synchronize()
+        want.append({k: v.clone() for k, v in o.items()})
+    many = SipMaskEngine(sd, (H, W), batch=3, stacked_convs=stacked, gn=gn, ssd_flag=ssd, test_cfg=cfg, img_shape=(H, W - 3, 3),
+                         scale_factor=sf, use_graph=True, share_weights=one)
+    for _ in range(2):                                   # second pass = graph replay
+        got = many.forward(imgs.cuda())
+        torch.cuda.synchronize()
+        for i in range(3):
+            k = int(want[i]['count'][0])
+            assert int(got['count'][i]) == k and k > 0
+            assert torch.equal(got['det_labels'][i, :k], want[i]['det_labels'][0, :k])
+            assert torch.equal(got['idxs_keep'][i, :k], want[i]['idxs_keep'][0, :k])
+            assert torch.equal(got['det_bboxes'][i, :k], want[i]['det_bboxes'][0, :k])
+            assert torch.equal(got['mask_bits'][i, :k], want[i]['mask_bits'][0, :k])
+    ho1, hoN = one.head_outputs(), many.head_outputs()     # `one` holds image 2 now
+    for l in range(5):
+        assert torch.equal(hoN['cls'][l][2:3], ho1['cls'][l])
+
+
+def test_engine_rescale_into_ori_shape():
+    """scale_factor != 1: boxes are divided by the scale factor and the masks are resized by 2/scale_factor
+    into the ori_shape canvas, like SingleStageDetector.simple_test(rescale=True) - engine vs the oracle on the engine's own
+    head outputs."""
+    from oracle import postproc as P
+    from sipmask_b200 import ops, synth
+    from sipmask_b200.engine import SipMaskEngine
+    H, W, sf = 128, 160, 1.6667
+    img_shape, ori_shape = (H, W - 4, 3), (77, 94, 3)
+    sd = synth.detector_state_dict(depth=50, seed=1, cls_bias=-2.5)
+    cfg = dict(nms_pre=200, score_thr=0.05, nms=dict(type='nms', iou_thr=0.5), max_per_img=30)
+    eng = SipMaskEngine(sd, (H, W), test_cfg=cfg, img_shape=img_shape, ori_shape=ori_shape, scale_factor=sf, use_graph=True)
+    out = eng.forward(synth.synthetic_image(H, W, seed=0).cuda())
+    torch.cuda.synchronize()
+    ho = eng.head_outputs()
+    res = P.get_bboxes_single([t[0].cpu() for t in ho['cls']], [t[0].cpu() for t in ho['bbox']], [t[0].cpu() for t in ho['ctr']],
+                              [t[0].cpu() for t in ho['cof']], ho['feat_masks'][0].float().cpu(), eng.strides, img_shape,
+                              ori_shape, sf, cfg, rescale=True)
+    k = int(out['count'][0])
+    assert k == res['det_bboxes'].shape[0] and k > 0
+    assert out['det_labels'][0, :k].cpu().tolist() == res['det_labels'].tolist()
+    np.testing.assert_allclose(out['det_bboxes'][0, :k].cpu().numpy(), res['det_bboxes'].numpy(), rtol=1e-5, atol=1e-5)
+    assert tuple(out['mask_bits'].shape[2:]) == (ori_shape[0], (ori_shape[1] + 31) // 32)
+    masks = ops.unpack_mask_bits(out['mask_bits'][0, :k].cpu(), ori_shape[1]).numpy().astype(bool)
+    want = res['masks'].astype(bool)
+    assert masks.shape == want.shape
+    iou = (np.logical_and(masks, want).sum((1, 2)) + 1e-9) / (np.logical_or(masks, want).sum((1, 2)) + 1e-9)
+    assert iou.min() >= 0.999, iou

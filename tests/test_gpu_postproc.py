@@ -175,7 +175,7 @@ def test_crop_split_operator_matches_oracle():
         ops.crop_split(data.cuda().permute(0, 2, 1, 3), rois.cuda())       # non-contiguous input raises
 
 
-@pytest.mark.parametrize('name', ['ref_head_gn4.npz', 'ref_head_ssd2.npz'])
+@pytest.mark.parametrize('name', ['ref_head_gn4.npz', 'ref_head_ssd2.npz', 'ref_head_gn4_sf.npz', 'ref_head_ssd2_sf.npz'])
 def test_postproc_reproduces_reference_fixture(golden_dir, name):
     """Head outputs captured from the unmodified reference python -> device post-processing must give the
     reference's detections (labels / kept boxes bit-exact, masks IoU >= 0.999)."""
@@ -193,7 +193,7 @@ def test_postproc_reproduces_reference_fixture(golden_dir, name):
         [torch.from_numpy(g['ctr%d' % i][0]).cuda() for i in range(nl)],
         [torch.from_numpy(g['cof%d' % i][0]).cuda() for i in range(nl)],
         torch.from_numpy(g['feat_masks'][0]).cuda(), (8, 16, 32, 64, 128),
-        tuple(g['img_shape']), tuple(g['img_shape']), sf, cfg, rescale=True, ssd_flag=ssd,
+        tuple(g['img_shape']), tuple(g['ori_shape']), sf, cfg, rescale=True, ssd_flag=ssd,
         cmp_ge=True)    # the fixture was produced on CPU -> nms_cpu.cpp comparator (>=)
     k = int(res['count'])
     assert res['det_labels'][:k].cpu().tolist() == g['det_labels'].tolist()
@@ -201,3 +201,44 @@ def test_postproc_reproduces_reference_fixture(golden_dir, name):
     masks = res['masks'][:k].cpu().numpy()
     assert masks.shape == g['masks'].shape
     assert _iou(masks, g['masks']).min() >= 0.999
+
+
+@pytest.mark.parametrize('H,W,up', [(48, 62, 2.0), (48, 62, 2.0 / 1.6667), (50, 64, (2 / 1.3, 2 / 1.7)), (60, 41, 2.0 / 3.1),
+                                    (37, 53, 2.0 / 0.8), (272, 272, 2.0)])
+def test_mask_resize_matches_torch_interpolate(H, W, up):
+    """The general resize (scale_factor != 1): two-step kernels and the fused kernel against
+    F.interpolate(pos_masks, scale_factor=2/scale_factor, mode='bilinear', align_corners=False) > 0.4
+    (sipmask_head.py:629-633), both coordinate rules (PyTorch >= 1.6 given-factor, and recompute_scale_factor=True)."""
+    import torch.nn.functional as F
+    from sipmask_b200 import ops, synth
+    O, P, cbind = _oracle()
+    g = torch.Generator().manual_seed(H + W)
+    N = 23
+    protos = synth.prototypes(H, W, seed=3)
+    cofs = torch.randn(N, 128, generator=g)
+    cx, cy = torch.rand(N, generator=g) * W * 2, torch.rand(N, generator=g) * H * 2
+    bw, bh = torch.rand(N, generator=g) * W * 1.5 + 2, torch.rand(N, generator=g) * H * 1.5 + 2
+    boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1).clamp(min=0)
+    boxes[0] = torch.tensor([0.0, 0.0, 2.0 * W, 2.0 * H])
+    pos_ref = torch.from_numpy(cbind.mask_assemble(protos.numpy(), cofs.numpy(), (boxes * 0.5).numpy()))
+    pos = ops.mask_assemble(protos.cuda(), cofs.cuda(), boxes.cuda(), 0.5, layout='chw')
+    sf = tuple(float(u) for u in up) if isinstance(up, tuple) else float(up)
+    for legacy in (False, True):
+        want = (F.interpolate(pos_ref.unsqueeze(0), scale_factor=sf, mode='bilinear', align_corners=False,
+                              recompute_scale_factor=True if legacy else None).squeeze(0) > 0.4).numpy()
+        fh, fw = want.shape[1:]
+        for (oh, ow) in ((fh, fw), (fh - 3, fw - 5), (fh + 4, fw + 37)):
+            canvas = np.zeros((N, oh, ow), bool)
+            canvas[:, :min(oh, fh), :min(ow, fw)] = want[:, :min(oh, fh), :min(ow, fw)]
+            a = ops.mask_resize_threshold(pos, up, (oh, ow), 0.4, legacy_interp=legacy).cpu().numpy().astype(bool)
+            b = ops.unpack_mask_bits(ops.mask_resize_threshold_pack(pos, up, (oh, ow), 0.4, legacy_interp=legacy), ow).cpu().numpy().astype(bool)
+            c = ops.unpack_mask_bits(ops.mask_assemble_pack(protos.cuda(), cofs.cuda(), boxes.cuda(), 0.5, (oh, ow), 0.4,
+                                                            layout='chw', up=up, legacy_interp=legacy), ow).cpu().numpy().astype(bool)
+            c16 = ops.unpack_mask_bits(ops.mask_assemble_pack(protos.half().permute(1, 2, 0).contiguous().cuda(), cofs.cuda(),
+                                                              boxes.cuda(), 0.5, (oh, ow), 0.4, layout='hwc', up=up,
+                                                              legacy_interp=legacy), ow).cpu().numpy().astype(bool)
+            assert _iou(a, canvas).min() >= 0.999, (legacy, oh, ow)
+            assert (a != canvas).mean() < 2e-5                      # only pixels whose value sits on the threshold may flip
+            assert (a == b).all()                                   # byte and bit-packed outputs are the same kernel math
+            assert (c != b).mean() < 1e-5                           # fused == two-step
+            assert (c16 != canvas).mean() < 2e-3                    # fp16 prototypes (engine storage type)

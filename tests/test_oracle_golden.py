@@ -26,16 +26,24 @@ def test_nms_mm_fixtures(golden_dir):
     assert O.nms(g['mm4_dets'], 0.7, cmp_ge=True).tolist() == [0, 2, 3]
 
 
-def test_nms_bm_known_answers():
-    """BM/tests/test_nms.py:16-58: 5 boxes (xywh->xyxy with TO_REMOVE=1), thresholds -> kept sets.
-    BM's nms has no +1 in... it uses the same legacy +1 kernel (BM/fcos_core/csrc/cpu/nms_cpu.cpp)."""
-    boxes = np.array([[0, 0, 100, 100], [2, 2, 98, 98], [50, 50, 100, 100], [0, 0, 50, 50]], np.float32)
-    scores = np.array([0.1, 0.9, 0.2, 0.95], np.float32)
-    dets = np.concatenate([boxes, scores[:, None]], 1)
-    # hand-derived with the +1 convention: box1 suppresses box0 (IoU .92), boxes 2/3 overlap others < .5
-    keep = O.nms(dets, 0.5).tolist()
-    assert keep == [1, 2, 3]
-    assert O.nms(dets, 0.95).tolist() == [0, 1, 2, 3]
+def _bm_boxlist(rows):
+    """BM/tests/test_nms.py builds BoxList(..., mode='xywh').convert('xyxy'): x2 = x + w - 1 (TO_REMOVE = 1)."""
+    b = np.asarray(rows, np.float32)
+    return np.stack([b[:, 0], b[:, 1], b[:, 0] + b[:, 2] - 1, b[:, 1] + b[:, 3] - 1], 1)
+
+
+def test_nms_bm_known_answers(golden_dir):
+    """SipMask-benchmark/tests/test_nms.py:16-58 (5 boxes, five thresholds -> kept sets) and :60- (53 boxes ->
+    gt_indices); the vectors are stored as data in nms_known_answers.npz by tests/golden/gen_golden.py."""
+    g = _load(golden_dir, 'nms_known_answers.npz')
+    dets5 = np.concatenate([g['bm5_boxes_xyxy'], g['bm5_scores'][:, None]], 1).astype(np.float32)
+    for thr, want in zip(g['bm5_thrs'], g['bm5_keeps']):
+        want = [int(i) for i in want if i >= 0]
+        for cmp_ge in (False, True):
+            assert sorted(O.nms(dets5, float(thr), cmp_ge=cmp_ge).tolist()) == sorted(want), (thr, cmp_ge)
+    dets53 = np.concatenate([g['bm53_boxes_xyxy'], g['bm53_scores'][:, None]], 1).astype(np.float32)
+    keep = O.nms(dets53, float(g['bm53_thr']), cmp_ge=True)
+    assert sorted(keep.tolist()) == sorted(g['bm53_gt_indices'].tolist())
 
 
 def test_nms_matches_reference_cpp():
@@ -80,8 +88,11 @@ def test_c_oracle_matches_numpy():
 
 
 # ---- reference python fixtures
-@pytest.mark.parametrize('name,cmp_ge', [('ref_head_gn4.npz', True), ('ref_head_ssd2.npz', True)])
+@pytest.mark.parametrize('name,cmp_ge', [('ref_head_gn4.npz', True), ('ref_head_ssd2.npz', True),
+                                         ('ref_head_gn4_sf.npz', True), ('ref_head_ssd2_sf.npz', True)])
 def test_head_and_postproc_match_reference(golden_dir, name, cmp_ge):
+    """The *_sf fixtures were produced with scale_factor != 1 and ori_shape != img_shape (rescale=True): boxes / scale_factor,
+    masks interpolated by 2 / scale_factor (per axis on the SSD path) and pasted into the ori_shape canvas."""
     g = _load(golden_dir, name)
     stacked, gn, ssd = int(g['stacked_convs']), bool(g['gn']), bool(g['ssd_flag'])
     head = M.SipMaskHead(stacked_convs=stacked, gn=gn, ssd_flag=ssd)
@@ -110,7 +121,7 @@ def test_head_and_postproc_match_reference(golden_dir, name, cmp_ge):
         [torch.from_numpy(g['ctr%d' % i][0]) for i in range(nl)],
         [torch.from_numpy(g['cof%d' % i][0]) for i in range(nl)],
         torch.from_numpy(g['feat_masks'][0]), (8, 16, 32, 64, 128),
-        tuple(g['img_shape']), tuple(g['img_shape']), sf, cfg, rescale=True, ssd_flag=ssd, cmp_ge=cmp_ge)
+        tuple(g['img_shape']), tuple(g['ori_shape']), sf, cfg, rescale=True, ssd_flag=ssd, cmp_ge=cmp_ge)
     assert res['det_labels'].tolist() == g['det_labels'].tolist()
     np.testing.assert_array_equal(res['det_bboxes'].numpy(), g['det_bboxes'])
     assert res['masks'].shape == g['masks'].shape
@@ -118,6 +129,43 @@ def test_head_and_postproc_match_reference(golden_dir, name, cmp_ge):
     union = np.logical_or(res['masks'], g['masks']).sum((1, 2))
     assert ((inter + 1e-9) / (union + 1e-9)).min() >= 0.999
     assert (res['masks'] == g['masks']).all()
+
+
+def rescore_fixture_inputs(g):
+    """Regenerate the inputs of the compact ref_head_ssd2_rescore fixture (tests/golden/gen_golden.py::gen_head_case):
+    seeded synthetic head weights incl. the rescoring layers, and the five feature maps from torch.Generator(seed + 10)."""
+    seed = int(g['seed'])
+    sd = synth.head_state_dict(seed=seed, prefix='', stacked_convs=int(g['stacked_convs']), gn=bool(g['gn']), cls_bias=-2.0,
+                               rescoring_flag=True)
+    gen = torch.Generator().manual_seed(seed + 10)
+    feats = [torch.randn(1, 256, int(h), int(w), generator=gen) for (h, w) in g['sizes']]
+    return sd, feats
+
+
+def test_rescoring_matches_reference(golden_dir):
+    """SipMask++ mask rescoring (sipmask_head.py:200-219,635-643) - fixture from the reference python run with
+    rescoring_flag=True: the oracle must reproduce detections, masks and mask_scores."""
+    g = _load(golden_dir, 'ref_head_ssd2_rescore.npz')
+    sd, feats = rescore_fixture_inputs(g)
+    head = M.SipMaskHead(stacked_convs=int(g['stacked_convs']), gn=bool(g['gn']), ssd_flag=True, rescoring_flag=True)
+    head.load_state_dict(sd, strict=True)
+    head.eval()
+    with torch.no_grad():
+        cls, box, ctr, cof, fm = head(feats)
+        cfg = dict(nms_pre=int(g['nms_pre']), score_thr=float(g['score_thr']), nms=dict(iou_thr=0.5),
+                   max_per_img=int(g['max_per_img']))
+        res = P.get_bboxes_single([t[0] for t in cls], [t[0] for t in box], [t[0] for t in ctr], [t[0] for t in cof], fm[0],
+                                  (8, 16, 32, 64, 128), tuple(g['img_shape']), tuple(g['ori_shape']), g['scale_factor'], cfg,
+                                  rescale=True, ssd_flag=True, cmp_ge=True, head=head)
+    assert res['det_labels'].tolist() == g['det_labels'].tolist()
+    np.testing.assert_allclose(res['det_bboxes'].numpy(), g['det_bboxes'], rtol=1e-4, atol=1e-3)
+    want = g['mask_scores']
+    assert (want > 0).sum() >= 10                                     # the fixture exercises the non-trivial branch
+    np.testing.assert_allclose(res['mask_scores'].numpy(), want, rtol=2e-3, atol=2e-5)
+    ref_masks = np.unpackbits(g['masks'], axis=-1)[:, :, :int(g['mask_w'])]
+    inter = np.logical_and(res['masks'], ref_masks).sum((1, 2))
+    union = np.logical_or(res['masks'], ref_masks).sum((1, 2))
+    assert ((inter + 1e-9) / (union + 1e-9)).min() >= 0.999
 
 
 def test_backbone_fpn_match_reference(golden_dir):
