@@ -33,13 +33,32 @@ WORKLOADS = {
     'B': dict(name='SipMask R50-FPN SSD-style head (2conv, no GN, fast_nms), 544x544, bs=32 per forward, synthetic images + '
                    'seeded synthetic weights', depth=50, stacked=2, gn=False, ssd=True, H=544, W=544, img_w=544, batch=32,
               score_thr=0.1, in_flight=2),
+    # configs[4]: SipMask-VIS frame path (3-conv towers, 40 classes, tracking branch, fast_nms max 10), 360x640 padded to
+    # 384x640; frames are sharded one per GPU per step, records + 512-d track features are gathered once at the end and the
+    # tracker association runs on the host in frame order (inside the timed region)
+    'C': dict(name='SipMask-VIS R50-FPN-GN 3conv + track branch, 360x640 (padded 384x640), one frame per GPU per step, '
+                   'synthetic frames + seeded synthetic weights', depth=50, stacked=3, gn=True, ssd=False, vis=True, H=384, W=640,
+              img_w=640, img_h=360, batch=1, score_thr=0.03, in_flight=6, nms_pre=200, max_per_img=10, num_classes=41),
 }
 CLS_BIAS = -5.0
 ROLL = 500          # untimed pre/post-roll steps around the timed region while nvidia-smi samples clocks
 
 
 def test_cfg(wl):
-    return dict(nms_pre=1000, score_thr=wl['score_thr'], nms=dict(type='nms', iou_thr=0.5), max_per_img=100)
+    return dict(nms_pre=wl.get('nms_pre', 1000), score_thr=wl['score_thr'], nms=dict(type='nms', iou_thr=0.5),
+                max_per_img=wl.get('max_per_img', 100))
+
+
+def state_dict_for(wl):
+    from sipmask_b200 import synth
+    if wl.get('vis'):
+        sd = {}
+        sd.update(synth.backbone_state_dict(wl['depth'], 1))
+        sd.update(synth.neck_state_dict(2))
+        sd.update(synth.head_state_dict(3, num_classes=wl['num_classes'], stacked_convs=wl['stacked'], gn=True, cls_bias=CLS_BIAS,
+                                        track=True))
+        return sd
+    return synth.detector_state_dict(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], seed=1, cls_bias=CLS_BIAS)
 
 
 def peaks():
@@ -137,8 +156,9 @@ def build_oracle(wl, threads):
     O.USE_TORCHVISION_DCN = True
     O.USE_C_CROP_SPLIT = True
     net = M.SipMaskDetector(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], ssd_flag=wl['ssd'])
-    net.load_state_dict(synth.detector_state_dict(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], seed=1, cls_bias=CLS_BIAS),
-                        strict=True)
+    if wl.get('vis'):
+        net.bbox_head = M.SipMaskVISHead(num_classes=wl['num_classes'], stacked_convs=wl['stacked'])
+    net.load_state_dict(state_dict_for(wl), strict=True)
     net.eval()
     return net
 
@@ -150,6 +170,13 @@ def oracle_step(net, img, wl):
     import torch
     from oracle import cbind, postproc as P
     from oracle import ops as O
+    if wl.get('vis'):
+        with torch.no_grad():
+            outs = net.bbox_head(net.extract_feat(img))
+        shape = (wl['img_h'], wl['img_w'], 3)
+        meta = dict(img_shape=shape, ori_shape=shape, scale_factor=1.0, is_first=False)
+        det, lab, masks, ids = P.vis_get_bboxes(outs, meta, test_cfg(wl), oracle_step.tracker, rescale=True)
+        return dict(det_bboxes=det)
     with torch.no_grad():
         cls, box, ctr, cof, fm = net(img)
     real_nms = O.nms
@@ -165,6 +192,9 @@ def oracle_step(net, img, wl):
 
 
 def cpu_reference(wl, steps, warmup, threads, budget_s=150.0):
+    if wl.get('vis'):
+        from oracle import postproc as P
+        oracle_step.tracker = P.VISTracker()
     """Times WHOLE images only (r1's row-strip extrapolation was refuted by its own numbers).  The first pass is the probe;
     the number of timed images is min(steps, what fits the time budget), at least 1.  Returns (seconds per image,
     detections, images timed, per-image times)."""
@@ -227,12 +257,15 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
 
-    sd = synth.detector_state_dict(wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], seed=1, cls_bias=CLS_BIAS)
+    sd = state_dict_for(wl)
+    vis = bool(wl.get('vis'))
+    IMG_H = wl.get('img_h', H)
     nfl = max(1, args.in_flight if args.in_flight > 0 else wl['in_flight'])
     cfg = test_cfg(wl)
     sf = np.ones(4, dtype=np.float32) if wl['ssd'] else 1.0
     ekw = dict(depth=wl['depth'], stacked_convs=wl['stacked'], gn=wl['gn'], ssd_flag=wl['ssd'], batch=B, test_cfg=cfg,
-               img_shape=(H, IMG_W, 3), scale_factor=sf, use_graph=True, device=dev)
+               img_shape=(IMG_H, IMG_W, 3), scale_factor=sf, use_graph=True, device=dev, vis=vis,
+               num_classes=wl.get('num_classes', 81))
     # nfl forwards in flight per GPU: nfl engines (shared weights, private activations + CUDA graph)
     engs = make_engines(sd, (H, W), in_flight=nfl, **ekw)
     eng = engs[0]
@@ -243,25 +276,36 @@ def run_ours(args):
     pool = EnginePool(engs)
     # the single collective of the path: records are logged locally per image and gathered ONCE at the end
     # of the run, inside the timed region
-    log = sdist.RecordLog(max(args.steps, 1) * B, eng.max_num, dev)
+    log = sdist.RecordLog(max(args.steps, 1) * B, eng.max_num, dev, feat_dim=512 if vis else 0)
     gathered = torch.empty((world,) + tuple(log.buf.shape), dtype=torch.float32, device=dev) if world > 1 else None
+    if vis:
+        from sipmask_b200.tracker import Tracker
+        tracker = Tracker()
 
     def consume(out):
         for b in range(B):
-            log.append(out['det_bboxes'][b], out['det_labels'][b], out['count'][b:b + 1])
+            log.append(out['det_bboxes'][b], out['det_labels'][b], out['count'][b:b + 1],
+                       out['track_feats'][b] if vis else None)
+
+    def finish_records():
+        n_local = min(log.n, log.cap)
+        g = log.gather(out=gathered)           # world == 1: a view, no communication
+        if vis:                                # association in frame order on the gathered records (host, rank-replicated)
+            tracker.reset()
+            sdist.track_gathered(g, n_local * world, tracker)
+        log.reset()
 
     def step():
         pool.step(consume)
 
     def step_finish():
         pool.flush(consume)
-        log.gather(out=gathered)               # world == 1: a view, no communication
-        log.reset()
+        finish_records()
 
     # end-to-end through the public serving API: pinned-host uint8 image in (the decoder's output; resize / normalise / pad /
     # layout run in one kernel on the device), pinned-host record + bit-packed masks out; upload / replay / download of
     # consecutive images overlap on their own streams (sipmask_b200/serving.py)
-    raw = (B == 1)
+    raw = (B == 1 and not vis)
     if raw:
         g = torch.Generator().manual_seed(rank)
         img_u8 = (torch.rand(H, IMG_W, 3, generator=g) * 255.0).to(torch.uint8).pin_memory()
@@ -277,8 +321,7 @@ def run_ours(args):
 
     def e2e_finish():
         runner.flush(consume)                  # the timed region ends when the last result is on the host
-        log.gather(out=gathered)
-        log.reset()
+        finish_records()
 
     def timed(fn, steps, sample_clocks=False, finish=None):
         """K steps between barrier+synchronize, CUDA events, max over ranks.  nvidia-smi samples clocks every 100 ms;

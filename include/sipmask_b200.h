@@ -183,6 +183,13 @@ int smb_gather_det_inputs(const float* cof_src, int cof_pitch, const int* cand_l
                           const int* count_dev, int max_rows, int row_elems, float* det_cofs, float* det_boxes,
                           int64_t* loc_out, int num_levels, const int* host_level_hw, int n_img, int img, smb_stream_t stream);
 
+/* SipMask-VIS `extract_box_feature_center_single` (SipMask-VIS/mmdet/models/anchor_heads/sipmask_head.py:609-613,768-781):
+ * out[i,:] = track[floor((y1+y2)*sy/2/stride), floor((x1+x2)*sx/2/stride), :] for i < *count, zeros after.
+ * track [h,w,C] fp32 channel-last (the `sipmask_track` output), det [max_rows,5], (sx, sy) = scale_factor when the
+ * detections were rescaled (res_det_bboxes = det * scale_factor), feat_stride = 8. */
+int smb_gather_track_feats(const float* track, int h, int w, int C, const float* det, const int* count_dev, int max_rows,
+                           float scale_x, float scale_y, float feat_stride, float* out, smb_stream_t stream);
+
 /* gather rows: dst[i,:] = src[idx[i],:] for i < *count (device count), zero otherwise. */
 int smb_gather_rows_f32(const float* src, int src_pitch, const int64_t* idx, const int* count_dev,
                         int max_rows, int row_elems, float* dst, smb_stream_t stream);

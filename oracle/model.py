@@ -262,3 +262,45 @@ class SipMaskDetector(nn.Module):
 
     def forward(self, img):
         return self.bbox_head(self.extract_feat(img))
+
+
+class SipMaskVISHead(SipMaskHead):
+    """SipMask-VIS head (VIS/mmdet/models/anchor_heads/sipmask_head.py:160-317; paths below relative to
+    /root/reference/SipMask-VIS/mmdet/): the image head plus a tracking branch - `track_convs` (stacked_convs - 1
+    ConvModules, :274-286) applied to levels 0..2, bilinearly upsampled to P3 resolution (:306-309; level 0 is "interpolated"
+    by 1), concatenated and reduced by `sipmask_track` 1x1 768 -> 512 (:287,:310-312).  Every level's reg feature is
+    interpolated for the prototype branch, also level 0 with factor 1 (:301-303).  forward(feats, feats_x, flag_train) returns
+    the 7-tuple of :315-317; at test time track_feats_ref is track_feats."""
+
+    def __init__(self, num_classes=41, in_channels=256, feat_channels=256, stacked_convs=3, strides=(8, 16, 32, 64, 128), gn=True):
+        super().__init__(num_classes=num_classes, in_channels=in_channels, feat_channels=feat_channels,
+                         stacked_convs=stacked_convs, strides=strides, ssd_flag=False, rescoring_flag=False, gn=gn)
+        self.track_convs = nn.ModuleList([ConvModule(in_channels if i == 0 else feat_channels, feat_channels, gn=gn)
+                                          for i in range(stacked_convs - 1)])
+        self.sipmask_track = nn.Conv2d(feat_channels * 3, 512, 1, padding=0)
+
+    def forward(self, feats, feats_x=None, flag_train=False):
+        cls_scores, bbox_preds, centernesses, cof_preds, feat_masks, track_feats = [], [], [], [], [], []
+        for count, (x, scale, stride) in enumerate(zip(feats, self.scales, self.strides)):
+            cls_feat = reg_feat = track_feat = x
+            for l in self.cls_convs:
+                cls_feat = l(cls_feat)
+            for l in self.reg_convs:
+                reg_feat = l(reg_feat)
+            if count < 3:
+                for l in self.track_convs:
+                    track_feat = l(track_feat)
+                track_feats.append(F.interpolate(track_feat, scale_factor=(2 ** count), mode='bilinear', align_corners=False))
+            bbox_pred = scale(self.fcos_reg(reg_feat))
+            cls_feat = self.feat_align(cls_feat, bbox_pred)
+            cls_scores.append(self.fcos_cls(cls_feat))
+            centernesses.append(self.fcos_centerness(reg_feat))
+            bbox_preds.append(bbox_pred.float() * stride)
+            cof_preds.append(self.sip_cof(cls_feat))
+            if count < 3:
+                feat_masks.append(F.interpolate(reg_feat, scale_factor=(2 ** count), mode='bilinear', align_corners=False))
+        fm = torch.cat(feat_masks, dim=1)
+        fm = F.relu(self.sip_mask_lat(F.relu(self.sip_mask_lat0(fm))))
+        fm = F.interpolate(fm, scale_factor=4, mode='bilinear', align_corners=False)
+        tf = self.sipmask_track(torch.cat(track_feats, dim=1))
+        return cls_scores, bbox_preds, centernesses, cof_preds, fm, tf, tf

@@ -48,8 +48,10 @@ __global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C
     for (int j = 0; j < 8; ++j) {
       const int c = v * 8 + j;
       const int g = c / cpg;
-      const float s = (float)((double)stats[((size_t)img * G + g) * 2] * (1.0 / kGnSumScale));
-      const float ss = (float)((double)stats[((size_t)img * G + g) * 2 + 1] * (1.0 / kGnSqScale));
+      // int64 -> fp32 with ONE rounding; the 2^-20 / 2^-16 scales are exact, so this equals the former double-precision
+      // product bit for bit without FP64 instructions (B200 issues those at a small fraction of the fp32 rate)
+      const float s = __ll2float_rn(stats[((size_t)img * G + g) * 2]) * (1.0f / kGnSumScale);
+      const float ss = __ll2float_rn(stats[((size_t)img * G + g) * 2 + 1]) * (1.0f / kGnSqScale);
       const float mean = s * inv_cnt;
       const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
       const float rstd = rsqrtf(var + eps);
@@ -324,8 +326,9 @@ __global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, 
     const int g = (v * 8) / cpg;
     const long long* st = reinterpret_cast<const long long*>(d.b[l]) + ((size_t)img * 32 + g) * 2;
     const float inv_cnt = 1.0f / ((float)hw * (float)cpg);
-    const float mean = (float)((double)st[0] * (1.0 / kGnSumScale)) * inv_cnt;
-    const float ex2 = (float)((double)st[1] * (1.0 / kGnSqScale)) * inv_cnt;
+    // int64 -> fp32 with one rounding, exact power-of-two scales: same bits as the double-precision product, no FP64 issue
+    const float mean = __ll2float_rn(st[0]) * (1.0f / kGnSumScale) * inv_cnt;
+    const float ex2 = __ll2float_rn(st[1]) * (1.0f / kGnSqScale) * inv_cnt;
     const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + eps);
     uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.c[l]) + row * pitch + v * 8);
     float f[8];

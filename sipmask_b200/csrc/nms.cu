@@ -765,6 +765,32 @@ __global__ void gather_det_inputs_kernel(const float* __restrict__ cof_src, int 
   }
 }
 
+// SipMask-VIS: the 512-d tracking feature of every kept detection, taken at the box centre of res_det = det * scale_factor
+// on the stride-8 track map: floor((x1 + x2) / 2 / 8) (VIS/mmdet/models/anchor_heads/sipmask_head.py:609-613,768-781).
+// track [h,w,C] fp32 channel-last; out [max_rows,C], zeros after *count.  Indices are clamped into the map (the reference
+// indexes unclamped and would raise on an out-of-range centre).
+__global__ void gather_track_feats_kernel(const float* __restrict__ track, int h, int w, int C, const float* __restrict__ det,
+                                          const int* __restrict__ count, int max_rows, float sx, float sy, float stride,
+                                          float* __restrict__ out) {
+  pdl_wait();
+  const int total = max_rows * C;
+  const int cnt = *count;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int r = t / C, e = t - r * C;
+    float v = 0.f;
+    if (r < cnt) {
+      const float x1 = __fmul_rn(det[r * 5 + 0], sx), y1 = __fmul_rn(det[r * 5 + 1], sy);
+      const float x2 = __fmul_rn(det[r * 5 + 2], sx), y2 = __fmul_rn(det[r * 5 + 3], sy);
+      int cx = (int)floorf(__fdiv_rn(__fdiv_rn(__fadd_rn(x2, x1), 2.0f), stride));
+      int cy = (int)floorf(__fdiv_rn(__fdiv_rn(__fadd_rn(y2, y1), 2.0f), stride));
+      cx = min(max(cx, 0), w - 1);
+      cy = min(max(cy, 0), h - 1);
+      v = track[((size_t)cy * w + cx) * C + e];
+    }
+    out[t] = v;
+  }
+}
+
 static int fill_levels(Levels* L, int num_levels, const smb_level_t* host_levels, int nms_pre) {
   if (num_levels < 1 || num_levels > MAXLVL) return -1;
   L->num = num_levels;
@@ -965,6 +991,17 @@ extern "C" int smb_gather_det_inputs(const float* cof_src, int cof_pitch, const 
                          cof_src, cof_pitch, cand_loc, (const long long*)idx, det, count_dev, max_rows, row_elems, det_cofs,
                          det_boxes, (long long*)loc_out, lm));
   SMB_LAUNCH_OK("gather_det_inputs_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_gather_track_feats(const float* track, int h, int w, int C, const float* det, const int* count_dev,
+                                      int max_rows, float scale_x, float scale_y, float feat_stride, float* out,
+                                      smb_stream_t stream) {
+  SMB_CHECK_ARG(track && det && count_dev && out && h > 0 && w > 0 && C > 0 && max_rows > 0 && feat_stride > 0.f,
+                "smb_gather_track_feats: bad argument");
+  SMB_CUDA_OK(launch_pdl(gather_track_feats_kernel, dim3(cdiv(max_rows * C, 256)), dim3(256), 0, (cudaStream_t)stream, track, h, w,
+                         C, det, count_dev, max_rows, scale_x, scale_y, feat_stride, out));
+  SMB_LAUNCH_OK("gather_track_feats_kernel");
   return SMB_OK;
 }
 

@@ -27,7 +27,7 @@ class SipMaskEngine(object):
                  strides=(8, 16, 32, 64, 128), test_cfg=None, img_shape=None, scale_factor=1.0, device='cuda',
                  mask_thr=0.4, use_graph=True, pos_dtype=torch.float32, head_only=False, feat_sizes=None, in_channels=256,
                  fcos=False, prefix_head='bbox_head.', build_postproc=True, two_streams=True, share_weights=None,
-                 max_ctas=None, head_max_ctas=None, backbone_dcn=False, ori_shape=None, legacy_interp=False):
+                 max_ctas=None, head_max_ctas=None, backbone_dcn=False, ori_shape=None, legacy_interp=False, vis=False):
         self.dev = torch.device(device)
         if self.dev.index is None:
             self.dev = torch.device('cuda', torch.cuda.current_device())
@@ -43,6 +43,9 @@ class SipMaskEngine(object):
         # get_bboxes loops over images, sipmask_head.py:517-540; BASELINE config 4 is a bs=32 throughput mode)
         assert head_only or (self.H % 32 == 0 and self.W % 32 == 0), 'images are padded to a multiple of 32 (Pad size_divisor=32)'
         self.depth, self.stacked, self.gn, self.ssd = depth, stacked_convs, gn, ssd_flag
+        # SipMask-VIS head (SipMask-VIS/mmdet/models/anchor_heads/sipmask_head.py): tracking branch, fast_nms with
+        # cfg.score_thr / cfg.max_per_img, masks > 0.5, per-detection 512-d box-centre features in the result record
+        self.vis = vis
         self.backbone_dcn = backbone_dcn           # SipMask++: DeformConvPack (dg=1) as conv2 of every 3rd block of stages 2-4
         self.ncls = num_classes - 1
         self.strides = tuple(strides)
@@ -55,7 +58,7 @@ class SipMaskEngine(object):
         # pasted into the ori_shape canvas (sipmask_head.py:587-588,629-633,648-654)
         self.ori_shape = tuple(ori_shape) if ori_shape is not None else self.img_shape
         self.legacy_interp = legacy_interp
-        self.mask_thr = mask_thr
+        self.mask_thr = 0.5 if (vis and mask_thr == 0.4) else mask_thr      # VIS thresholds at 0.5 (VIS/...:764), MM at 0.4
         self.pos_dtype = pos_dtype
         self.sd = {k: v for k, v in state_dict.items()}
         self.ops = []            # list of zero-argument callables = the launch sequence
@@ -279,7 +282,7 @@ class SipMaskEngine(object):
         self.level_sizes = sizes
         tot = sum(h * w for h, w in sizes)
         nl = len(feats)
-        n_tower = (self.stacked - 1) + self.stacked + 1
+        n_tower = (self.stacked - 1) + self.stacked + 1 + ((self.stacked - 1) if self.vis else 0)
         # one int64 fixed-point statistics arena for every (conv, level) GroupNorm, zeroed once per forward
         self.gn_arena = self._t(n_tower, nl, N, 32, 2, dtype=torch.int64, zero=True)
         self._add(lambda: self.gn_arena.zero_(), 0, name='memset')
@@ -369,6 +372,19 @@ class SipMaskEngine(object):
         if two:
             self._marker('join')
         self._tag = 0
+        if self.vis:
+            # tracking branch (VIS/...:274-287,296-312): track_convs on levels 0..2 -> bilinear x1 / x2 / x4 to P3 resolution ->
+            # concat 768 -> sipmask_track 1x1 -> 512, fp32 (the features enter dot products of the association)
+            tfe = list(feats[:3])
+            for i in range(self.stacked - 1):
+                tfe = self._tower_conv(tfe, hp + 'track_convs.%d.conv.weight' % i, hp + 'track_convs.%d.gn' % i,
+                                       hp + 'track_convs.%d.conv.bias' % i, [self.gn_arena[si + 1 + i, l] for l in range(3)])
+            cat_t = self._t(N, h3, w3, 768)
+            for l in range(3):
+                self._add(lambda l=l, tfe=tfe, cat_t=cat_t: C.upsample_bilinear(tfe[l], 2 ** l, out=cat_t, out_choff=256 * l),
+                          name='upsample')
+            self.track_feats = self._conv(cat_t, hp + 'sipmask_track.weight', 1, bias_key=hp + 'sipmask_track.bias',
+                                          out_dtype=torch.float32)
         self._max_ctas = self.max_ctas
         if self.build_post:
             self._build_postproc()
@@ -427,7 +443,8 @@ class SipMaskEngine(object):
         CCp = self.clscof.shape[-1]
         ncls = self.ncls
         nms_pre = int(cfg['nms_pre'])
-        self.max_num = 100 if self.ssd else int(cfg['max_per_img'])
+        self.max_num = 100 if self.ssd else int(cfg['max_per_img'])      # MM's fast_nms hard-codes 100 (sipmask_head.py:903)
+        fast = self.ssd or self.vis                                         # VIS: fast_nms with cfg.max_per_img (VIS/...:986)
         ncand = sum(min(h * w, nms_pre) if nms_pre > 0 else h * w for h, w in self.level_sizes)
         self.ncand = ncand
         lib = L.lib()
@@ -453,6 +470,7 @@ class SipMaskEngine(object):
         self.loc_kept = self._t(N, self.max_num, dtype=torch.long)
         self.det_cofs = self._t(N, self.max_num, 128, dtype=torch.float32)
         self.det_boxes4 = self._t(N, self.max_num, 4, dtype=torch.float32)
+        self.det_track = self._t(N, self.max_num, 512, dtype=torch.float32) if self.vis else None
         level_hw = (ctypes.c_int * nl)(*[h * w for h, w in self.level_sizes])
         self._keep.append(level_hw)
         # the per-image decode -> NMS -> gather -> mask chains are independent (get_bboxes loops over images,
@@ -479,7 +497,7 @@ class SipMaskEngine(object):
                         'smb_decode_topk')
             self._add(decode, 3, name='decode_topk')
             iou_thr = float(cfg['nms']['iou_thr'])
-            if not self.ssd:
+            if not fast:
                 nws_bytes = lib.smb_multiclass_nms_workspace_bytes(ncand, ncls)
                 nws = self._t(nws_bytes, dtype=torch.uint8)
 
@@ -499,7 +517,7 @@ class SipMaskEngine(object):
                                              L.ptr(self.det[n]), L.ptr(self.labels[n]), L.ptr(self.idx[n]),
                                              L.ptr(self.count[n:n + 1]), L.ptr(nws), ctypes.c_size_t(nws_bytes), L.stream_ptr()),
                             'smb_fast_nms')
-            self._add(nms, 4 if not self.ssd else 2, name='nms')
+            self._add(nms, 4 if not fast else 2, name='nms')
             cof_src = self.clscof[:, ncls:ncls + 128]                          # coefficient columns, row pitch CCp
 
             def gather(n=n, cof_src=cof_src):
@@ -518,6 +536,15 @@ class SipMaskEngine(object):
                                                    ctypes.c_float(ry), ctypes.c_float(rx), oh, ow,
                                                    ctypes.c_float(self.mask_thr), L.stream_ptr()), 'smb_mask_assemble_pack')
             self._add(masks, 2, name='mask_fused')
+            if self.vis:
+                th, tw = self.track_feats.shape[1], self.track_feats.shape[2]
+
+                def track(n=n, th=th, tw=tw):
+                    L.check(lib.smb_gather_track_feats(L.ptr(self.track_feats[n]), th, tw, 512, L.ptr(self.det[n]),
+                                                       L.ptr(self.count[n:n + 1]), self.max_num, ctypes.c_float(float(s4[0])),
+                                                       ctypes.c_float(float(s4[1])), ctypes.c_float(8.0),
+                                                       L.ptr(self.det_track[n]), L.stream_ptr()), 'smb_gather_track_feats')
+                self._add(track, 1, name='gather_track')
         if pp_streams:
             self._marker('join')
         self._tag = 0
@@ -577,8 +604,13 @@ class SipMaskEngine(object):
             self.graph.replay()
         else:
             self._run_ops()
-        return dict(det_bboxes=self.det, det_labels=self.labels, count=self.count, mask_bits=self.mask_bits,
-                    idxs_keep=self.idx)
+        return self._result()
+
+    def _result(self):
+        r = dict(det_bboxes=self.det, det_labels=self.labels, count=self.count, mask_bits=self.mask_bits, idxs_keep=self.idx)
+        if self.vis:
+            r['track_feats'] = self.det_track          # [N,max,512] box-centre tracking features (zeros after count)
+        return r
 
     def forward_raw(self, img_u8, mean=(102.9801, 115.9465, 122.7717)):
         """img_u8: uint8 BGR HWC CUDA image straight from the decoder.  Resize (keep ratio, mmcv.imrescale rule towards this
@@ -602,8 +634,7 @@ class SipMaskEngine(object):
             self.graph_raw.replay()
         else:
             self._run_ops(only=set(self.op_names) - {'image_to_nhwc8', 'fork', 'join'})
-        return dict(det_bboxes=self.det, det_labels=self.labels, count=self.count, mask_bits=self.mask_bits,
-                    idxs_keep=self.idx)
+        return self._result()
 
     # head outputs in the reference's layout (for parity tests / the drop-in head)
     def head_outputs(self):
@@ -615,4 +646,6 @@ class SipMaskEngine(object):
             outs['bbox'].append((rc[..., :4] * self.scales[l]).permute(0, 3, 1, 2) * self.strides[l])
             outs['ctr'].append(rc[..., 4:5].permute(0, 3, 1, 2))
         outs['feat_masks'] = self.protos.permute(0, 3, 1, 2)
+        if self.vis:
+            outs['track_feats'] = self.track_feats.permute(0, 3, 1, 2)
         return outs

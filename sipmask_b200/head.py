@@ -74,7 +74,8 @@ class _HeadBase(nn.Module):
                                 gn=self.norm_cfg is not None, ssd_flag=getattr(self, 'ssd_flag', False),
                                 num_classes=self.num_classes, strides=self.strides, device=dev,
                                 use_graph=False, head_only=True, feat_sizes=sizes, in_channels=self.in_channels,
-                                fcos=self.fcos, prefix_head='', build_postproc=False, share_weights=self._wcache)
+                                fcos=self.fcos, prefix_head='', build_postproc=False, share_weights=self._wcache,
+                                vis=getattr(self, 'vis', False))
             self._engines[key] = eng
             while len(self._engines) > self.MAX_ENGINES:
                 self._engines.popitem(last=False)
@@ -216,6 +217,79 @@ class SipMaskHead(_HeadBase):
             return None
         return dict(conv_w=[m.conv.weight for m in self.convs_scoring], conv_b=[m.conv.bias for m in self.convs_scoring],
                     w1x1=self.mask_scoring.weight, b1x1=self.mask_scoring.bias)
+
+
+class SipMaskVISHead(SipMaskHead):
+    """Drop-in for the SipMask-VIS head (SipMask-VIS/mmdet/models/anchor_heads/sipmask_head.py:131-317,565-682; registered
+    there under the same name `SipMaskHead`): tracking branch parameters `track_convs.{i}.conv/gn`, `sipmask_track`,
+    `forward(feats, feats_x, flag_train)` -> 7-tuple, `get_bboxes(..., track_feats, track_feats_ref, img_metas, cfg, rescale)`
+    -> [det_bboxes, det_labels, obj_segms {obj_id: RLE}, det_obj_ids] with the tracker state (`prev_*`) kept in the module
+    like the reference keeps it.  Inference only (flag_train=True raises)."""
+    vis = True
+
+    def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
+                 regress_ranges=((-1, 64), (64, 128), (128, 256), (256, 512), (512, INF)), center_sampling=False,
+                 center_sample_radius=1.5, loss_cls=None, loss_bbox=None, loss_centerness=None, conv_cfg=None,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True)):
+        super().__init__(num_classes, in_channels, feat_channels=feat_channels, stacked_convs=stacked_convs, strides=strides,
+                         regress_ranges=regress_ranges, center_sampling=center_sampling, center_sample_radius=center_sample_radius,
+                         conv_cfg=conv_cfg, norm_cfg=norm_cfg)
+        gn = norm_cfg is not None
+        self.track_convs = nn.ModuleList([_ConvModule(in_channels if i == 0 else feat_channels, feat_channels, gn=gn)
+                                          for i in range(stacked_convs - 1)])
+        self.sipmask_track = nn.Conv2d(feat_channels * 3, 512, 1, padding=0)
+        self.match_coeff = [1.0, 2.0, 10]
+        for m in self.track_convs:
+            nn.init.normal_(m.conv.weight, 0, 0.01)
+        from .tracker import Tracker
+        self.tracker = Tracker(self.match_coeff)
+
+    @torch.no_grad()
+    def forward(self, feats, feats_x=None, flag_train=False):
+        if flag_train:
+            raise NotImplementedError('sipmask_b200 heads are inference-only (flag_train=False, single_stage.py:71)')
+
+        def collect(eng):
+            o = eng.head_outputs()
+            return o['cls'], o['bbox'], o['ctr'], o['cof'], o['feat_masks'], o['track_feats']
+        out = self._run_images(feats, collect)
+        return tuple(out) + (out[5],)                       # track_feats_ref is track_feats at test time (VIS/...:317)
+
+    @torch.no_grad()
+    def get_bboxes(self, cls_scores, bbox_preds, centernesses, cof_preds, feat_masks, track_feats, track_feats_ref, img_metas,
+                   cfg, rescale=None):
+        results = []
+        for i in range(len(img_metas)):
+            meta = img_metas[i]
+            res = postproc.get_bboxes_single(
+                [t[i] for t in cls_scores], [t[i] for t in bbox_preds], [t[i] for t in centernesses],
+                [t[i] for t in cof_preds], feat_masks[i], self.strides, meta['img_shape'], meta['ori_shape'],
+                meta['scale_factor'], cfg, rescale=bool(rescale), pack=True, vis=True, mask_thr=0.5, track_feats=track_feats[i])
+            k = int(res['count'])
+            det_bboxes, det_labels = res['det_bboxes'][:k], res['det_labels'][:k]
+            if k == 0:                                       # VIS/...:605-608
+                results.append([det_bboxes, det_labels, [[] for _ in range(self.num_classes - 1)], []])
+                return results
+            ids = self.tracker.step(det_bboxes.cpu().numpy(), det_labels.cpu().numpy(), res['track_feats'][:k].cpu().numpy(),
+                                    bool(meta['is_first']))
+            # the VIS reference always pastes into the ori_shape canvas (:669-674), also without rescale
+            oh, ow = int(meta['ori_shape'][0]), int(meta['ori_shape'][1])
+            mh, mw = res['mask_hw']
+            rles = ops.masks_to_rle(res['mask_bits'], min(oh, mh), min(ow, mw), k) if (oh, ow) == (mh, mw) else \
+                [rle.encode(_paste(ops.unpack_mask_bits(res['mask_bits'][j:j + 1], mw)[0].cpu().numpy(), oh, ow)) for j in range(k)]
+            obj_segms = {}
+            for j in range(k):
+                if ids[j] >= 0:
+                    obj_segms[int(ids[j])] = rles[j]
+            results.append([det_bboxes, det_labels, obj_segms, ids])
+        return results
+
+
+def _paste(mask, oh, ow):
+    im = np.zeros((oh, ow), np.uint8)
+    hh, ww = min(mask.shape[0], oh), min(mask.shape[1], ow)
+    im[:hh, :ww] = mask[:hh, :ww]
+    return im
 
 
 class FCOSHead(_HeadBase):

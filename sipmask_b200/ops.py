@@ -203,6 +203,26 @@ def gather_rows(src, idx, count, max_rows):
     return dst
 
 
+@L.device_guard
+def gather_track_feats(track_feats, det, count, scale_factor=1.0, feat_stride=8.0):
+    """SipMask-VIS `extract_box_feature_center_single`: track_feats [512,h,w] (reference layout) or [h,w,512] channel-last
+    fp32, det [max,5], count device int -> [max,512] features at floor((x1+x2) * sf / 2 / 8) (zeros after count)."""
+    _need_cuda(track_feats, det, count)
+    t = track_feats.float()
+    if t.shape[0] == 512 and t.shape[-1] != 512:
+        t = t.permute(1, 2, 0)
+    t = t.contiguous()
+    h, w, C = t.shape
+    a = np.atleast_1d(np.asarray(scale_factor, dtype=np.float32))
+    sx, sy = float(a[0]), float(a[1] if a.size >= 2 else a[0])
+    det = det.float().contiguous()
+    out = torch.empty((det.shape[0], C), dtype=torch.float32, device=det.device)
+    L.check(L.lib().smb_gather_track_feats(L.ptr(t), h, w, C, L.ptr(det), L.ptr(count.to(torch.int32)), det.shape[0],
+                                           ctypes.c_float(sx), ctypes.c_float(sy), ctypes.c_float(feat_stride), L.ptr(out),
+                                           L.stream_ptr()), 'smb_gather_track_feats')
+    return out
+
+
 # -------------------------------------------------------------------------------------- mask assembly
 @L.device_guard
 def mask_assemble(protos, cofs, boxes, box_scale, layout='chw', out_dtype=torch.float32, out=None):

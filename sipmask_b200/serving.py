@@ -84,7 +84,7 @@ class EnginePool(object):
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(self.ev_done[k])
         eng = self.engs[k]
-        r = fn(dict(det_bboxes=eng.det, det_labels=eng.labels, count=eng.count, mask_bits=eng.mask_bits))
+        r = fn(eng._result())
         self.ev_consumed[k].record(cur)
         return r
 
@@ -134,6 +134,9 @@ class PipelinedRunner(object):
             self.in_dev = [torch.empty_like(engine.img) for _ in range(ns)]
         self.out_dev = [dict(det=torch.empty_like(engine.det), lab=torch.empty_like(engine.labels),
                              cnt=torch.empty_like(engine.count), bits=torch.empty_like(engine.mask_bits)) for _ in range(ns)]
+        if engine.vis:                            # SipMask-VIS: the 512-d tracking features travel with the record
+            for o in self.out_dev:
+                o['trk'] = torch.empty_like(engine.det_track)
         self.out_host = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in o.items()} for o in self.out_dev]
         self.ev_in_ready = [torch.cuda.Event() for _ in range(ns)]      # H2D of slot finished
         self.ev_in_free = [torch.cuda.Event() for _ in range(ns)]       # compute consumed the slot's input
@@ -194,10 +197,12 @@ class PipelinedRunner(object):
             o['lab'].copy_(eng.labels, non_blocking=True)
             o['cnt'].copy_(eng.count, non_blocking=True)
             o['bits'].copy_(eng.mask_bits, non_blocking=True)
+            if 'trk' in o:
+                o['trk'].copy_(eng.det_track, non_blocking=True)
             self.ev_out_ready[k].record(cs)
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(self.ev_out_ready[k])
-            for name in ('det', 'lab', 'cnt', 'bits'):
+            for name in o:
                 self.out_host[k][name].copy_(o[name], non_blocking=True)
             self.ev_out_free[k].record(self.s_d2h)
         self.i += 1
@@ -209,7 +214,10 @@ class PipelinedRunner(object):
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(self.ev_out_ready[slot])
         o = self.out_dev[slot]
-        r = fn(dict(det_bboxes=o['det'], det_labels=o['lab'], count=o['cnt'], mask_bits=o['bits']))
+        rec = dict(det_bboxes=o['det'], det_labels=o['lab'], count=o['cnt'], mask_bits=o['bits'])
+        if 'trk' in o:
+            rec['track_feats'] = o['trk']
+        r = fn(rec)
         if self.ev_hold[slot] is None:
             self.ev_hold[slot] = torch.cuda.Event()
         self.ev_hold[slot].record(cur)

@@ -70,7 +70,7 @@ def neck_state_dict(seed=2, prefix='neck.', in_channels=(512, 1024, 2048), out_c
 
 
 def head_state_dict(seed=3, prefix='bbox_head.', num_classes=81, feat=256, stacked_convs=4, gn=True,
-                    rescoring_flag=False, cls_bias=-3.0, num_levels=5):
+                    rescoring_flag=False, cls_bias=-3.0, num_levels=5, track=False):
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -112,6 +112,11 @@ def head_state_dict(seed=3, prefix='bbox_head.', num_classes=81, feat=256, stack
             sd['%sconvs_scoring.%d.conv.bias' % (prefix, i)] = 0.05 * torch.randn(ch[i + 1], generator=g)
         sd[prefix + 'mask_scoring.weight'] = _kaiming(g, ncls, 128, 1)
         sd[prefix + 'mask_scoring.bias'] = 0.1 * torch.randn(ncls, generator=g)
+    if track:                      # SipMask-VIS tracking branch (VIS/.../sipmask_head.py:274-287), drawn last: older seeds keep their values
+        for i in range(stacked_convs - 1):
+            convmod('%strack_convs.%d' % (prefix, i), feat, feat)
+        sd[prefix + 'sipmask_track.weight'] = _kaiming(g, 512, 3 * feat, 1, gain=1.0)
+        sd[prefix + 'sipmask_track.bias'] = 0.1 * torch.randn(512, generator=g)
     return sd
 
 

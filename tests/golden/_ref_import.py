@@ -24,8 +24,8 @@ import torch.nn as nn
 
 REF_MM = '/root/reference/SipMask-mmdetection'
 
-_MOCK_ROOTS = ('pycocotools', 'terminaltables', 'matplotlib', 'six')
-_COMPILED = ('deform_conv_cuda', 'deform_pool_cuda', 'nms_cpu', 'nms_cuda',
+_MOCK_ROOTS = ('pycocotools', 'terminaltables', 'matplotlib', 'six', 'imagecorruptions', 'albumentations')
+_COMPILED = ('deform_conv_cuda', 'deform_pool_cuda', 'nms_cpu', 'nms_cuda', 'soft_nms_cpu',
              'crop_split_cuda', 'crop_split_gt_cuda', 'roi_align_cuda',
              'roi_pool_cuda', 'sigmoid_focal_loss_cuda', 'masked_conv2d_cuda',
              'carafe_cuda', 'carafe_naive_cuda', 'grid_sampler_cuda',
@@ -126,6 +126,12 @@ def _make_fake_mmcv():
     for n in ('OptimizerHook', 'Hook', 'DistSamplerSeedHook', 'Runner'):
         setattr(runner, n, type(n, (_Dummy,), {}))
 
+    runner.__path__ = []
+    ru = types.ModuleType('mmcv.runner.utils')          # VIS tree: `from mmcv.runner.utils import get_dist_info`
+    ru.get_dist_info = runner.get_dist_info
+    runner.utils = ru
+    sys.modules['mmcv.runner.utils'] = ru
+
     parallel = types.ModuleType('mmcv.parallel')
     for n in ('MMDataParallel', 'MMDistributedDataParallel', 'DataContainer'):
         setattr(parallel, n, type(n, (_Dummy,), {}))
@@ -140,12 +146,13 @@ def _make_fake_mmcv():
 _installed = False
 
 
-def install():
-    """Make `import mmdet` resolve to the unmodified reference tree."""
+def install(ref=REF_MM):
+    """Make `import mmdet` resolve to the unmodified reference tree (`ref`: SipMask-mmdetection by default, or
+    /root/reference/SipMask-VIS for the video head; one tree per process)."""
     global _installed
     if _installed:
         return
     _make_fake_mmcv()
     sys.meta_path.insert(0, _MockFinder())
-    sys.path.insert(0, REF_MM)
+    sys.path.insert(0, ref)
     _installed = True
