@@ -49,6 +49,11 @@ def test_cfg(wl):
                 max_per_img=wl.get('max_per_img', 100))
 
 
+# workload A's constants under their round-1 names (tools/*.py import them)
+H, W, IMG_W = WORKLOADS['A']['H'], WORKLOADS['A']['W'], WORKLOADS['A']['img_w']
+TEST_CFG = test_cfg(WORKLOADS['A'])
+
+
 def state_dict_for(wl):
     from sipmask_b200 import synth
     if wl.get('vis'):

@@ -14,7 +14,8 @@
 namespace smb {
 
 constexpr int NT = 1024;          // threads per CTA for all kernels in this file
-constexpr int MAXN = 4096;        // max candidates per class list held in shared memory
+constexpr int MAXN = 5120;        // max candidates per class list held in shared memory (>= 5 levels x nms_pre = 1000)
+constexpr int NMS1 = 8192;        // max boxes of the single-list operator smb_nms
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float iou_ref(const float4 a, const float4 b, const float one) {
@@ -146,13 +147,13 @@ __device__ __forceinline__ void greedy_sweep(const float4* sb, int m, float thr,
 // Single-class NMS operator: dets [n,5]; keep ascending original indices.
 // ---------------------------------------------------------------------------------------------
 struct NmsSmem {
-  unsigned long long keys[2 * MAXN];
-  float4 sb[2 * MAXN];
-  unsigned long long rem[2 * MAXN / 64];
+  unsigned long long keys[NMS1];
+  float4 sb[NMS1];
+  unsigned long long rem[NMS1 / 64];
   unsigned long long diag[64];
   unsigned long long keepbits;
   int warp[33];
-  unsigned char kept[2 * MAXN];
+  unsigned char kept[NMS1];
 };
 
 __global__ void __launch_bounds__(NT) nms_single_kernel(const float* __restrict__ dets, int n, float thr, int cmp_ge,
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NT) nms_single_kernel(const float* __restrict_
     S.sb[r] = make_float4(dets[i * 5], dets[i * 5 + 1], dets[i * 5 + 2], dets[i * 5 + 3]);
   }
   __syncthreads();
-  greedy_sweep_n(S.sb, n, thr, cmp_ge, one, S.rem, 2 * MAXN / 64, S.diag, &S.keepbits);
+  greedy_sweep_n(S.sb, n, thr, cmp_ge, one, S.rem, NMS1 / 64, S.diag, &S.keepbits);
   for (int i = threadIdx.x; i < n; i += NT) S.kept[i] = 0;
   __syncthreads();
   for (int r = threadIdx.x; r < n; r += NT)
@@ -812,7 +813,7 @@ using namespace smb;
 
 extern "C" int smb_nms(const float* dets, int n, float iou_thr, int cmp_ge, int plus_one, int64_t* keep_out,
                        int* n_keep_out, smb_stream_t stream) {
-  SMB_CHECK_ARG(n >= 0 && n <= 2 * MAXN, "smb_nms: n=%d outside [0,%d]", n, 2 * MAXN);
+  SMB_CHECK_ARG(n >= 0 && n <= NMS1, "smb_nms: n=%d outside [0,%d]", n, NMS1);
   SMB_CHECK_ARG(keep_out && n_keep_out && (dets || n == 0), "smb_nms: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {

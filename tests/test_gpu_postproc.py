@@ -58,7 +58,7 @@ def test_nms_ties_are_stable():
 
 
 @pytest.mark.parametrize('seed,n,C,thr,max_num', [(0, 3350, 80, 0.05, 100), (1, 500, 80, 0.05, 100), (2, 200, 5, 0.3, 1000),
-                                                  (3, 64, 80, 0.9999, 100), (4, 4096, 3, 0.05, 10)])
+                                                  (3, 64, 80, 0.9999, 100), (4, 4096, 3, 0.05, 10), (5, 5000, 6, 0.05, 100)])
 def test_multiclass_nms_matches_oracle(seed, n, C, thr, max_num):
     from sipmask_b200 import ops
     O, P, cbind = _oracle()
