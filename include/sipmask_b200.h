@@ -115,6 +115,14 @@ int smb_mask_assemble_pack(const void* protos, int protos_dtype, int layout_hwc,
 int smb_crop_split_forward(const void* data, const void* rois, void* out, int dtype,
                            int H, int W, int c, int N, smb_stream_t stream);
 
+/* Training-side companions.  smb_crop_split_backward replaces crop_split_cuda_backward
+ * (ops/crop/src/crop_split_cuda_kernel.cu:90-163): top_grad [H,W,N] -> bottom_grad [c*c,H,W,N], every element written
+ * (the reference zero-initialises and atomically adds).  smb_crop_split_gt replaces crop_split_gt_cuda_forward AND
+ * _backward (ops/crop/src/crop_split_gt_cuda_kernel.cu:19-49,76-104): out[h,w,n] = data[h,w,n] inside roi n, else 0. */
+int smb_crop_split_backward(const void* top_grad, const void* rois, void* bottom_grad, int dtype, int H, int W, int c, int N,
+                            smb_stream_t stream);
+int smb_crop_split_gt(const void* data, const void* rois, void* out, int dtype, int H, int W, int N, smb_stream_t stream);
+
 /* ------------------------------------------------------------------ NMS (operator API)
  * Replaces nms_cuda.nms(dets, thr) (ops/nms/src/nms_kernel.cu:71-138) without the D2H bitmask copy
  * and host sweep.  dets [n,5] fp32; keep_out [n] int64 receives ORIGINAL indices ascending;

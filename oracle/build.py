@@ -61,6 +61,7 @@ def build_ref_cuda():
     dst = os.path.join(OUT, 'libsipmask_ref_cuda.so')
     wrap = os.path.join(HERE, 'ref_cuda')
     units = [('ref_crop.cu', os.path.join(REF_OPS, 'crop', 'src', 'crop_split_cuda_kernel.cu')),
+             ('ref_crop_gt.cu', os.path.join(REF_OPS, 'crop', 'src', 'crop_split_gt_cuda_kernel.cu')),
              ('ref_dcn.cu', os.path.join(REF_OPS, 'dcn', 'src', 'deform_conv_cuda_kernel.cu'))]
     if not all(os.path.exists(r) for _, r in units):
         return dst if os.path.exists(dst) else None

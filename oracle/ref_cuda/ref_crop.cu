@@ -10,3 +10,9 @@ extern "C" int ref_crop_split_forward(const float* data, const float* rois, floa
   CropSplitForward(at::Tensor(data), at::Tensor(rois), at::Tensor(out), H, W, c, N);
   return (int)cudaDeviceSynchronize();
 }
+
+extern "C" int ref_crop_split_backward(const float* top_grad, const float* rois, float* bottom_grad, int H, int W, int c, int N) {
+  // the caller zero-initialises `bottom_grad` like CropSplitFunction.backward does (ops/crop/crop_split.py:35)
+  CropSplitBack(at::Tensor(top_grad), at::Tensor(rois), at::Tensor(bottom_grad), H, W, c, N);
+  return (int)cudaDeviceSynchronize();
+}

@@ -49,7 +49,9 @@ def build(verbose=False, force=False):
         if rc != 0:
             raise RuntimeError('nvcc failed on %s' % src)
     if rebuilt or not os.path.exists(LIB):
-        subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+        tmp = LIB + '.tmp.so'                      # link next to the target, then rename: the library is never half-written
+        subprocess.check_call([NVCC, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -16,10 +16,8 @@ struct __align__(16) BoxP {
   float x1, y1, x2, y2, roi_w, roi_h, pad0, pad1;
 };
 
-constexpr int MA_THREADS = 128;
 constexpr int MA_TW = 64;   // tile width  (16 threads x 4 pixels)
 constexpr int MA_TH = 8;    // tile height
-constexpr int MA_NB = 64;   // detections per shared-memory chunk
 
 template <typename PT>
 __device__ __forceinline__ float to_f(PT v);
@@ -59,83 +57,103 @@ __device__ __forceinline__ void store1<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void store1<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
-// grid: (ceil(W/64), ceil(H/8)), block 128.  The output has been zero-filled by a memset node (the bulk of the
-// 107 MB pos_masks tensor is zeros and a memset runs at store bandwidth); this kernel only touches pixels inside boxes:
-// a CTA first lists the detections whose roi intersects its 8 x 64 tile, then evaluates, per listed detection and
-// in-box pixel, the ONE 32-term dot product selected by the CropSplit cell.
+// grid: (ceil(W/64), ceil(H/8)), block 256 (warp = tile row, lane = columns lane and lane + 32).  The output has been
+// zero-filled by a memset node (the bulk of the 107 MB pos_masks tensor is zeros and a memset runs at store bandwidth); this
+// kernel only touches pixels inside boxes: a CTA stages its 8 x 64 prototype pixels in shared memory ONCE (16-byte-chunk
+// XOR swizzle: conflict-free LDS.128), lists the detections whose roi intersects the tile, then evaluates, per listed
+// detection and in-box pixel, the ONE 32-term dot product selected by the CropSplit cell (coefficients: warp-uniform L1 reads).
 constexpr int MA_LIST = 128;   // detections listed per pass
+constexpr int MA_THREADS2 = 256;
+
+template <typename PT> struct FusedCfg;
+template <> struct FusedCfg<__half> { static constexpr int kChunks = 4; };   // 64 B / pixel
+template <> struct FusedCfg<float> { static constexpr int kChunks = 8; };    // 128 B / pixel
+
+template <typename PT>
+__device__ __forceinline__ int swz(int p, int k);
+template <>
+__device__ __forceinline__ int swz<__half>(int p, int k) { return k ^ ((p >> 1) & 3); }
+template <>
+__device__ __forceinline__ int swz<float>(int p, int k) { return k ^ (p & 7); }
+
+// 32-term dot product of shared-memory pixel p (swizzled 16-byte chunks) with cof[0..31]: sequential fmaf over channels,
+// the same summation order in the dense and the fused kernel, so both give bit-identical mask values.
+template <typename PT>
+__device__ __forceinline__ float dot32_swz(const unsigned char* s_p, int p, const float* __restrict__ cof);
+template <>
+__device__ __forceinline__ float dot32_swz<__half>(const unsigned char* s_p, int p, const float* __restrict__ cof) {
+  float acc = 0.f;
+  const uint4* q = reinterpret_cast<const uint4*>(s_p + (size_t)p * 64);
+  const float4* c4 = reinterpret_cast<const float4*>(cof);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint4 u = q[swz<__half>(p, v)];
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+    const float4 ca = __ldg(c4 + 2 * v), cb = __ldg(c4 + 2 * v + 1);
+    const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]), f3 = __half22float2(hh[3]);
+    acc = fmaf(f0.x, ca.x, acc); acc = fmaf(f0.y, ca.y, acc); acc = fmaf(f1.x, ca.z, acc); acc = fmaf(f1.y, ca.w, acc);
+    acc = fmaf(f2.x, cb.x, acc); acc = fmaf(f2.y, cb.y, acc); acc = fmaf(f3.x, cb.z, acc); acc = fmaf(f3.y, cb.w, acc);
+  }
+  return acc;
+}
+template <>
+__device__ __forceinline__ float dot32_swz<float>(const unsigned char* s_p, int p, const float* __restrict__ cof) {
+  float acc = 0.f;
+  const float4* q = reinterpret_cast<const float4*>(s_p + (size_t)p * 128);
+  const float4* c4 = reinterpret_cast<const float4*>(cof);
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const float4 a = q[swz<float>(p, v)], c = __ldg(c4 + v);
+    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+  }
+  return acc;
+}
+
+// stage an SRa x SCa window of prototype pixels (top-left source pixel (ys0, xs0)) into swizzled shared memory
+template <typename PT, bool HWC>
+__device__ __forceinline__ void stage_window(const PT* __restrict__ protos, unsigned char* s_p, int H, int W, int ys0, int xs0,
+                                             int SRa, int SCa, int nthreads) {
+  constexpr int CH = FusedCfg<PT>::kChunks, PX_BYTES = CH * 16;
+  const int npx = SRa * SCa;
+  if (HWC) {
+    for (int i = threadIdx.x; i < npx * CH; i += nthreads) {
+      const int p = i / CH, k = i - p * CH;
+      const int r = p / SCa, c = p - r * SCa;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(protos + ((size_t)(ys0 + r) * W + xs0 + c) * 32) + k);
+      *reinterpret_cast<uint4*>(s_p + (size_t)p * PX_BYTES + swz<PT>(p, k) * 16) = v;
+    }
+  } else {
+    for (int i = threadIdx.x; i < npx * 32; i += nthreads) {
+      const int ch = i / npx, p = i - ch * npx;
+      const int r = p / SCa, c = p - r * SCa;
+      const PT v = protos[((size_t)ch * H + ys0 + r) * W + xs0 + c];
+      constexpr int EPC = 16 / (int)sizeof(PT);                              // elements per 16-byte chunk
+      reinterpret_cast<PT*>(s_p + (size_t)p * PX_BYTES + swz<PT>(p, ch / EPC) * 16)[ch % EPC] = v;
+    }
+  }
+}
+
 template <typename PT, bool HWC, typename OT>
-__global__ void __launch_bounds__(MA_THREADS) mask_assemble_kernel(
+__global__ void __launch_bounds__(MA_THREADS2) mask_assemble_kernel(
     const PT* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes,
     float sx1, float sy1, float sx2, float sy2, OT* __restrict__ out, int H, int W, int N) {
+  extern __shared__ __align__(16) unsigned char s_p[];        // [MA_TH * MA_TW] swizzled pixels (32 KB fp16 / 64 KB fp32)
   __shared__ BoxP s_box[MA_LIST];
   __shared__ int s_det[MA_LIST];
   __shared__ int s_cnt;
 
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int h = blockIdx.y * MA_TH + ty;
-  const int w0 = blockIdx.x * MA_TW + tx * 4;
-  const bool row_ok = h < H;
-  const int nvalid = row_ok ? max(0, min(4, W - w0)) : 0;
-  const bool vec_ok = (nvalid == 4) && ((W & 3) == 0);
-  const float tile_x0 = (float)(blockIdx.x * MA_TW), tile_x1 = (float)min(blockIdx.x * MA_TW + MA_TW - 1, W - 1);
-  const float tile_y0 = (float)(blockIdx.y * MA_TH), tile_y1 = (float)min(blockIdx.y * MA_TH + MA_TH - 1, H - 1);
-
-  // ---- prototype pixels -> registers (fp32), read exactly once
-  float P[4][32];
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int k = 0; k < 32; ++k) P[p][k] = 0.f;
-  if (nvalid > 0) {
-    if (HWC) {
-      const PT* base = protos + ((size_t)h * W + w0) * 32;
-      if (sizeof(PT) == 2) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          if (p < nvalid) {
-            const uint4* q = reinterpret_cast<const uint4*>(base + p * 32);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 u = __ldg(q + v);
-              const __half2* hh = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(hh[e]);
-                P[p][v * 8 + e * 2] = f.x;
-                P[p][v * 8 + e * 2 + 1] = f.y;
-              }
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          if (p < nvalid) {
-            const float4* q = reinterpret_cast<const float4*>(base + p * 32);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              float4 f = __ldg(q + v);
-              P[p][v * 4] = f.x; P[p][v * 4 + 1] = f.y; P[p][v * 4 + 2] = f.z; P[p][v * 4 + 3] = f.w;
-            }
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const PT* q = protos + ((size_t)k * H + h) * W + w0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-          if (p < nvalid) P[p][k] = to_f<PT>(q[p]);
-      }
-    }
-  }
-
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int y0t = blockIdx.y * MA_TH, x0t = blockIdx.x * MA_TW;
+  const int SRa = min(MA_TH, H - y0t), SCa = min(MA_TW, W - x0t);
+  stage_window<PT, HWC>(protos, s_p, H, W, y0t, x0t, SRa, SCa, MA_THREADS2);
+  const int h = y0t + warp;
+  const bool row_ok = warp < SRa;
   const float hf = (float)h;
+  const float tile_x0 = (float)x0t, tile_x1 = (float)(x0t + SCa - 1), tile_y0 = (float)y0t, tile_y1 = (float)(y0t + SRa - 1);
+
   for (int n0 = 0; n0 < N; n0 += MA_LIST) {
     const int nb = min(MA_LIST, N - n0);
-    __syncthreads();
+    __syncthreads();                                   // window staged / previous pass done with the list
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     if (threadIdx.x < nb) {
@@ -156,44 +174,23 @@ __global__ void __launch_bounds__(MA_THREADS) mask_assemble_kernel(
     }
     __syncthreads();
     const int cnt = s_cnt;
-    if (nvalid == 0) continue;
+    if (!row_ok) continue;
     for (int j = 0; j < cnt; ++j) {
       const BoxP b = s_box[j];
-      if (!((hf >= b.y1) & (hf < b.y2))) continue;
+      if (!((hf >= b.y1) & (hf < b.y2))) continue;     // warp-uniform: this tile row is outside the roi
       const int n = s_det[j];
-      const float* cof = cofs + (size_t)n * 128;          // 512 B per detection, warp-uniform (broadcast) L1 reads
+      const float* cof = cofs + (size_t)n * 128;
       const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h);
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
-      int inmask = 0;
+      OT* dst = out + ((size_t)n * H + h) * W + x0t;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float wf = (float)(w0 + p);
-        if ((p < nvalid) & (wf >= b.x1) & (wf < b.x2)) {
+      for (int q = 0; q < MA_TW / 32; ++q) {
+        const int c = lane + q * 32;
+        const float wf = (float)(x0t + c);
+        if ((c < SCa) & (wf >= b.x1) & (wf < b.x2)) {
           const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
-          int cell = idx_h * 2 + idx_w;
-          cell = min(max(cell, 0), 3);
-          const float4* c4 = reinterpret_cast<const float4*>(cof + cell * 32);
-          float acc = 0.f;
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const float4 c = __ldg(c4 + v);
-            acc = fmaf(P[p][v * 4], c.x, acc);
-            acc = fmaf(P[p][v * 4 + 1], c.y, acc);
-            acc = fmaf(P[p][v * 4 + 2], c.z, acc);
-            acc = fmaf(P[p][v * 4 + 3], c.w, acc);
-          }
-          o[p] = sigmoidf_(acc);
-          inmask |= 1 << p;
+          const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
+          store1<OT>(dst + c, sigmoidf_(dot32_swz<PT>(s_p, warp * SCa + c, cof + cell * 32)));
         }
-      }
-      if (inmask == 0) continue;
-      OT* dst = out + ((size_t)n * H + h) * W + w0;
-      if (inmask == 15 && vec_ok) {
-        store4<OT>(dst, o, true, 4);
-      } else {
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-          if (inmask & (1 << p)) store1<OT>(dst + p, o[p]);
       }
     }
   }
@@ -297,63 +294,26 @@ __global__ void __launch_bounds__(256) resize_thresh_pack_kernel(const PT* __res
 //   phase 1: one sigmoid-dot per source pixel (cell selected by CropSplit, 0 outside the box) -> s_val (fp32 tile),
 //   phase 2: one lane per output pixel: 4-tap bilinear from s_val, `> thr`, __ballot_sync -> one 32-bit word per warp.
 // (The previous kernel re-evaluated the dot product for up to four output pixels per source pixel: 2.8 % of HBM peak.)
-constexpr int MF_THREADS = 256, MF_SR = 10, MF_LIST = 128;
-template <typename PT> struct FusedCfg;
-template <> struct FusedCfg<__half> { static constexpr int kScCap = 132, kChunks = 4; };   // 64 B / pixel
-template <> struct FusedCfg<float> { static constexpr int kScCap = 68, kChunks = 8; };     // 128 B / pixel
-
-template <typename PT>
-__device__ __forceinline__ int swz(int p, int k);
-template <>
-__device__ __forceinline__ int swz<__half>(int p, int k) { return k ^ ((p >> 1) & 3); }
-template <>
-__device__ __forceinline__ int swz<float>(int p, int k) { return k ^ (p & 7); }
-
-// 32-term dot product of shared-memory pixel p (swizzled 16-byte chunks) with cof[0..31]; same summation order as the
-// dense kernel (sequential fmaf over channels), so both paths give bit-identical mask values.
-template <typename PT>
-__device__ __forceinline__ float dot32_swz(const unsigned char* s_p, int p, const float* __restrict__ cof);
-template <>
-__device__ __forceinline__ float dot32_swz<__half>(const unsigned char* s_p, int p, const float* __restrict__ cof) {
-  float acc = 0.f;
-  const uint4* q = reinterpret_cast<const uint4*>(s_p + (size_t)p * 64);
-  const float4* c4 = reinterpret_cast<const float4*>(cof);
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const uint4 u = q[swz<__half>(p, v)];
-    const __half2* hh = reinterpret_cast<const __half2*>(&u);
-    const float4 ca = __ldg(c4 + 2 * v), cb = __ldg(c4 + 2 * v + 1);
-    const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]), f3 = __half22float2(hh[3]);
-    acc = fmaf(f0.x, ca.x, acc); acc = fmaf(f0.y, ca.y, acc); acc = fmaf(f1.x, ca.z, acc); acc = fmaf(f1.y, ca.w, acc);
-    acc = fmaf(f2.x, cb.x, acc); acc = fmaf(f2.y, cb.y, acc); acc = fmaf(f3.x, cb.z, acc); acc = fmaf(f3.y, cb.w, acc);
-  }
-  return acc;
-}
-template <>
-__device__ __forceinline__ float dot32_swz<float>(const unsigned char* s_p, int p, const float* __restrict__ cof) {
-  float acc = 0.f;
-  const float4* q = reinterpret_cast<const float4*>(s_p + (size_t)p * 128);
-  const float4* c4 = reinterpret_cast<const float4*>(cof);
-#pragma unroll
-  for (int v = 0; v < 8; ++v) {
-    const float4 a = q[swz<float>(p, v)], c = __ldg(c4 + v);
-    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
-  }
-  return acc;
-}
+constexpr int MF_THREADS = 256, MF_LIST = 128, MF_TY_MAX = 16;
+struct RowC {
+  int o0, o1;       // offsets of the two source rows inside the window (row * SCa)
+  int y0, y1;       // the source rows themselves
+  float ly;
+  int pad_[3];
+};
 
 template <typename PT, bool HWC>
-__global__ void __launch_bounds__(MF_THREADS, 2) mask_fused_pack_kernel(
+__global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_kernel(
     const PT* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes, float sx1, float sy1,
     float sx2, float sy2, uint32_t* __restrict__ out, int H, int W, int N, int out_h, int out_w, int words, Resize rs,
-    int TY, int TW, float thr) {
-  constexpr int SC_CAP = FusedCfg<PT>::kScCap, CH = FusedCfg<PT>::kChunks;
-  constexpr int PX_BYTES = CH * 16;
+    int TY, int TW, int win_cap, float thr) {
+  constexpr int PX_BYTES = FusedCfg<PT>::kChunks * 16;
   extern __shared__ __align__(16) unsigned char mf_smem[];
-  unsigned char* s_p = mf_smem;                                                        // [MF_SR * SC_CAP] swizzled pixels
-  float* s_val = reinterpret_cast<float*>(mf_smem + (size_t)MF_SR * SC_CAP * PX_BYTES);   // [2][MF_SR * SC_CAP]
-  BoxP* s_box = reinterpret_cast<BoxP*>(s_val + 2 * MF_SR * SC_CAP);                   // [MF_LIST]
-  int* s_det = reinterpret_cast<int*>(s_box + MF_LIST);                                // [MF_LIST]
+  unsigned char* s_p = mf_smem;                                                        // [win_cap] swizzled pixels
+  float* s_val = reinterpret_cast<float*>(mf_smem + (size_t)win_cap * PX_BYTES);        // [2][win_cap]
+  BoxP* s_box = reinterpret_cast<BoxP*>(s_val + 2 * win_cap);                          // [MF_LIST]
+  RowC* s_row = reinterpret_cast<RowC*>(s_box + MF_LIST);                              // [MF_TY_MAX]
+  int* s_det = reinterpret_cast<int*>(s_row + MF_TY_MAX);                              // [MF_LIST]
   int* s_cnt = s_det + MF_LIST;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -369,25 +329,16 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mask_fused_pack_kernel(
   src_index(rs.ry, y_last, H, t0, ys1, tl);
   src_index(rs.rx, x_first, W, xs0, t1, tl);
   src_index(rs.rx, x_last, W, t0, xs1, tl);
-  const int SRa = ys1 - ys0 + 1, SCa = xs1 - xs0 + 1;                    // <= MF_SR, SC_CAP (tile sizes chosen by the host)
-  const int npx = SRa * SCa;
+  const int SRa = ys1 - ys0 + 1, SCa = xs1 - xs0 + 1;                    // SRa * SCa <= win_cap (tile sizes chosen by the host)
 
-  // ---- prototype window -> shared memory, read exactly once per CTA
-  if (HWC) {
-    for (int i = threadIdx.x; i < npx * CH; i += MF_THREADS) {
-      const int p = i / CH, k = i - p * CH;
-      const int r = p / SCa, c = p - r * SCa;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(protos + ((size_t)(ys0 + r) * W + xs0 + c) * 32) + k);
-      *reinterpret_cast<uint4*>(s_p + (size_t)p * PX_BYTES + swz<PT>(p, k) * 16) = v;
-    }
-  } else {
-    for (int i = threadIdx.x; i < npx * 32; i += MF_THREADS) {
-      const int ch = i / npx, p = i - ch * npx;
-      const int r = p / SCa, c = p - r * SCa;
-      const PT v = protos[((size_t)ch * H + ys0 + r) * W + xs0 + c];
-      constexpr int EPC = 16 / (int)sizeof(PT);                              // elements per 16-byte chunk
-      reinterpret_cast<PT*>(s_p + (size_t)p * PX_BYTES + swz<PT>(p, ch / EPC) * 16)[ch % EPC] = v;
-    }
+  // ---- prototype window -> shared memory, read exactly once per CTA; per-row interpolation constants
+  stage_window<PT, HWC>(protos, s_p, H, W, ys0, xs0, SRa, SCa, MF_THREADS);
+  if (threadIdx.x <= y_last - y_first) {
+    RowC rc;
+    src_index(rs.ry, y_first + threadIdx.x, H, rc.y0, rc.y1, rc.ly);
+    rc.o0 = (rc.y0 - ys0) * SCa;
+    rc.o1 = (rc.y1 - ys0) * SCa;
+    s_row[threadIdx.x] = rc;
   }
 
   // ---- per-lane column constants of phase 2 (warp -> one word column, rows strided by the warps sharing the column)
@@ -402,11 +353,15 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mask_fused_pack_kernel(
   }
   const float hx = 1.f - lx;
   const bool x_ok = x <= x_last;
+  const bool word_ok = x_first + wcol * 32 <= x_last;                    // warp-uniform
+  // source columns read by this warp's word (lane 0 .. last valid lane)
+  const float wsrc_lo = (float)(xs0 + __shfl_sync(0xffffffffu, cx0, 0));
+  const float wsrc_hi = (float)(xs0 + __shfl_sync(0xffffffffu, cx1, min(31, x_last - (x_first + wcol * 32))));
   const float win_x0 = (float)xs0, win_x1 = (float)xs1, win_y0 = (float)ys0, win_y1 = (float)ys1;
 
   for (int n0 = 0; n0 < N; n0 += MF_LIST) {
     const int nb = min(MF_LIST, N - n0);
-    __syncthreads();                                   // prototype window staged / previous pass done with s_box, s_val
+    __syncthreads();                                   // window / row table staged; previous pass done with s_box, s_val
     if (threadIdx.x == 0) *s_cnt = 0;
     __syncthreads();
     if (threadIdx.x < nb) {
@@ -429,33 +384,39 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mask_fused_pack_kernel(
     for (int j = 0; j < cnt; ++j) {
       const BoxP b = s_box[j];
       const int n = s_det[j];
-      float* val = s_val + (j & 1) * (MF_SR * SC_CAP);
+      float* val = s_val + (j & 1) * win_cap;
       const float* cof = cofs + (size_t)n * 128;
-      // ---- phase 1: one sigmoid-dot per source pixel of the window
-      for (int p = threadIdx.x; p < npx; p += MF_THREADS) {
-        const int r = p / SCa, c = p - r * SCa;
-        const float hf = (float)(ys0 + r), wf = (float)(xs0 + c);
-        float v = 0.f;
-        if ((hf >= b.y1) & (hf < b.y2) & (wf >= b.x1) & (wf < b.x2)) {
-          const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h), idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
-          const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
-          v = sigmoidf_(dot32_swz<PT>(s_p, p, cof + cell * 32));
+      // ---- phase 1: one sigmoid-dot per source pixel of the window (warp = window row, lanes = columns); 0 outside the roi
+      for (int r = warp; r < SRa; r += MF_THREADS / 32) {
+        const float hf = (float)(ys0 + r);
+        const bool row_in = (hf >= b.y1) & (hf < b.y2);
+        const int idx_h = row_in ? (int)__fdiv_rn(hf - b.y1, b.roi_h) : 0;
+        for (int c = lane; c < SCa; c += 32) {
+          const float wf = (float)(xs0 + c);
+          float v = 0.f;
+          if (row_in & (wf >= b.x1) & (wf < b.x2)) {
+            const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
+            const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
+            v = sigmoidf_(dot32_swz<PT>(s_p, r * SCa + c, cof + cell * 32));
+          }
+          val[r * SCa + c] = v;
         }
-        val[p] = v;
       }
       __syncthreads();        // the only barrier per detection: s_val is double-buffered, see below
-      // ---- phase 2: lane = output pixel of one word; rows of this warp's word column
-      uint32_t* o = out + (size_t)n * out_h * words + wq_first + wcol;
-      for (int y = y_first + rfirst; y <= y_last; y += rstep) {
-        int y0, y1;
-        float ly;
-        src_index(rs.ry, y, H, y0, y1, ly);
-        const float hy = 1.f - ly;
-        const float* r0 = val + (y0 - ys0) * SCa;
-        const float* r1 = val + (y1 - ys0) * SCa;
-        const float v = hy * (hx * r0[cx0] + lx * r0[cx1]) + ly * (hx * r1[cx0] + lx * r1[cx1]);
-        const uint32_t bits = __ballot_sync(0xffffffffu, x_ok && v > thr);
-        if (lane == 0 && bits) o[(size_t)y * words] = bits;
+      // ---- phase 2: lane = output pixel of one word; rows of this warp's word column.  Words whose source columns, and
+      // rows whose source rows, lie outside the roi are all-zero: skipped (the memset wrote them)
+      if (word_ok && wsrc_hi >= b.x1 && wsrc_lo < b.x2) {
+        uint32_t* o = out + (size_t)n * out_h * words + wq_first + wcol;
+        for (int y = y_first + rfirst; y <= y_last; y += rstep) {
+          const RowC rc = s_row[y - y_first];
+          if ((float)rc.y1 < b.y1 || (float)rc.y0 >= b.y2) continue;
+          const float hy = 1.f - rc.ly;
+          const float* r0 = val + rc.o0;
+          const float* r1 = val + rc.o1;
+          const float v = hy * (hx * r0[cx0] + lx * r0[cx1]) + rc.ly * (hx * r1[cx0] + lx * r1[cx1]);
+          const uint32_t bits = __ballot_sync(0xffffffffu, x_ok && v > thr);
+          if (lane == 0 && bits) o[(size_t)y * words] = bits;
+        }
       }
       // no barrier here: phase 1 of detection j+1 writes the OTHER s_val buffer; buffer (j & 1) is rewritten by detection
       // j+2, whose phase 1 every warp enters only after the barrier of detection j+1, i.e. after all warps left this loop
@@ -487,6 +448,46 @@ __global__ void crop_split_kernel(const T* __restrict__ data, const T* __restric
   }
 }
 
+// CropSplit backward (crop_split_cuda_kernel.cu:90-127): grad_in[cell(h,w,n), h, w, n] = grad_out[h,w,n] inside the roi, 0
+// everywhere else.  Every (cell, index) target is written exactly once, so no atomics and no zero-init are needed.
+template <typename T>
+__global__ void crop_split_backward_kernel(const T* __restrict__ top, const T* __restrict__ rois, T* __restrict__ bottom,
+                                           long long count, int H, int W, int N) {
+  for (long long index = blockIdx.x * (long long)blockDim.x + threadIdx.x; index < count;
+       index += (long long)blockDim.x * gridDim.x) {
+    const int n = (int)(index % N);
+    const int pw = (int)((index / N) % W);
+    const int ph = (int)(index / N / W);
+    const float x1 = to_f<T>(rois[n * 4 + 0]), y1 = to_f<T>(rois[n * 4 + 1]);
+    const float x2 = to_f<T>(rois[n * 4 + 2]), y2 = to_f<T>(rois[n * 4 + 3]);
+    int cell = -1;
+    if (((float)pw >= x1) & ((float)ph >= y1) & ((float)pw < x2) & ((float)ph < y2)) {
+      const float roi_w = (float)(((double)(x2 - x1) + 0.1) / 2);
+      const float roi_h = (float)(((double)(y2 - y1) + 0.1) / 2);
+      cell = min(max((int)__fdiv_rn((float)ph - y1, roi_h) * 2 + (int)__fdiv_rn((float)pw - x1, roi_w), 0), 3);
+    }
+    const T g = top[index];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bottom[(long long)k * count + index] = (k == cell) ? g : T(0.f);
+  }
+}
+
+// CropSplitGt forward and backward (crop_split_gt_cuda_kernel.cu:19-49,76-104): out = data inside the roi, 0 outside.
+template <typename T>
+__global__ void crop_mask_kernel(const T* __restrict__ data, const T* __restrict__ rois, T* __restrict__ out, long long count,
+                                 int H, int W, int N) {
+  for (long long index = blockIdx.x * (long long)blockDim.x + threadIdx.x; index < count;
+       index += (long long)blockDim.x * gridDim.x) {
+    const int n = (int)(index % N);
+    const int pw = (int)((index / N) % W);
+    const int ph = (int)(index / N / W);
+    const float x1 = to_f<T>(rois[n * 4 + 0]), y1 = to_f<T>(rois[n * 4 + 1]);
+    const float x2 = to_f<T>(rois[n * 4 + 2]), y2 = to_f<T>(rois[n * 4 + 3]);
+    const bool in = ((float)pw >= x1) & ((float)ph >= y1) & ((float)pw < x2) & ((float)ph < y2);
+    out[index] = in ? data[index] : T(0.f);
+  }
+}
+
 }  // namespace smb
 
 using namespace smb;
@@ -499,14 +500,23 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
   SMB_CHECK_ARG((protos_dtype == SMB_F32 || protos_dtype == SMB_F16) && (out_dtype == SMB_F32 || out_dtype == SMB_F16),
                 "smb_mask_assemble: bad dtype");
   if (N == 0) return SMB_OK;
-  dim3 grid(cdiv(W, MA_TW), cdiv(H, MA_TH)), block(MA_THREADS);
+  dim3 grid(cdiv(W, MA_TW), cdiv(H, MA_TH)), block(MA_THREADS2);
   const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
   cudaStream_t st = (cudaStream_t)stream;
   // zero background first (a memset node: runs at store bandwidth), then the in-box pixels only
   SMB_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * H * W * (out_dtype == SMB_F32 ? 4 : 2), st));
-#define MA_LAUNCH(PT, HWC, OT)                                                                             \
-  mask_assemble_kernel<PT, HWC, OT><<<grid, block, 0, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, \
-                                                            (OT*)out, H, W, N)
+  const size_t ma_smem = (size_t)MA_TH * MA_TW * (protos_dtype == SMB_F16 ? 64 : 128);
+  static DeviceOnce ma_once;
+  if (ma_once.first()) {
+#define MA_ATTR(PT, HWC, OT) \
+  SMB_CUDA_OK(cudaFuncSetAttribute(mask_assemble_kernel<PT, HWC, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))
+    MA_ATTR(float, false, float); MA_ATTR(float, false, __half); MA_ATTR(float, true, float); MA_ATTR(float, true, __half);
+    MA_ATTR(__half, false, float); MA_ATTR(__half, false, __half); MA_ATTR(__half, true, float); MA_ATTR(__half, true, __half);
+#undef MA_ATTR
+  }
+#define MA_LAUNCH(PT, HWC, OT)                                                                                   \
+  mask_assemble_kernel<PT, HWC, OT><<<grid, block, ma_smem, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, \
+                                                                  (OT*)out, H, W, N)
   const int key = (protos_dtype << 2) | ((layout_hwc ? 1 : 0) << 1) | out_dtype;
   switch (key) {
     case 0: MA_LAUNCH(float, false, float); break;
@@ -599,27 +609,30 @@ extern "C" int smb_mask_assemble_pack(const void* protos, int protos_dtype, int 
   SMB_CUDA_OK(cudaMemsetAsync(out_bits, 0, (size_t)N * out_h * words * 4, st));      // zero background (memset node)
   const int vh = out_h < full_h ? out_h : full_h, vw = out_w < full_w ? out_w : full_w;
   // output tile (TY rows x TW words) whose source window fits the shared-memory caps: rows/cols <= ceil((n-1) * r) + 2
-  const int sc_cap = protos_dtype == SMB_F16 ? FusedCfg<__half>::kScCap : FusedCfg<float>::kScCap;
-  int TW = 8, TY = 16;
-  while (TW > 1 && (int)ceilf((float)(TW * 32 - 1) * rs.rx) + 2 > sc_cap) TW >>= 1;
-  while (TY > 1 && (int)ceilf((float)(TY - 1) * rs.ry) + 2 > MF_SR) TY >>= 1;
-  SMB_CHECK_ARG((int)ceilf((float)(TW * 32 - 1) * rs.rx) + 2 <= sc_cap && (int)ceilf((float)(TY - 1) * rs.ry) + 2 <= MF_SR,
-                "smb_mask_assemble_pack: resize factor %dx%d -> %dx%d (shrinks by more than 4x) is not supported", H, W,
-                full_h, full_w);
+  // window budget in source pixels: ~48 KB of prototypes per CTA (4 CTAs / SM), e.g. 16 rows x 4 words at x2 = 10 x 66 px
+  const size_t px_bytes = protos_dtype == SMB_F16 ? 64 : 128;
+  const int px_budget = (int)((48 * 1024) / px_bytes);
+  auto win_rows = [&](int ty) { return (int)ceilf((float)(ty - 1) * rs.ry) + 2; };
+  auto win_cols = [&](int tw) { return (int)ceilf((float)(tw * 32 - 1) * rs.rx) + 2; };
+  int TW = 4, TY = MF_TY_MAX;
+  while (TW > 1 && win_rows(TY) * win_cols(TW) > px_budget) TW >>= 1;
+  while (TY > 1 && win_rows(TY) * win_cols(TW) > px_budget) TY >>= 1;
+  const int win_cap = win_rows(TY) * win_cols(TW);
+  SMB_CHECK_ARG(win_cap <= px_budget, "smb_mask_assemble_pack: resize %dx%d -> %dx%d shrinks too much for one tile (%d source "
+                "pixels per 32-pixel word)", H, W, full_h, full_w, win_cap);
   dim3 grid(cdiv(cdiv(vw, 32), TW), cdiv(vh, TY)), block(MF_THREADS);
   const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
-  const size_t px_bytes = protos_dtype == SMB_F16 ? 64 : 128;
-  const size_t smem = (size_t)MF_SR * sc_cap * (px_bytes + 8) + MF_LIST * (sizeof(BoxP) + sizeof(int)) + 16;
+  const size_t smem = (size_t)win_cap * (px_bytes + 8) + MF_LIST * (sizeof(BoxP) + sizeof(int)) + MF_TY_MAX * sizeof(RowC) + 16;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
 #define MF_LAUNCH(PT, HWC)                                                                                          \
   mask_fused_pack_kernel<PT, HWC><<<grid, block, smem, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, out_bits, H, W, \
-                                                           N, out_h, out_w, words, rs, TY, TW, thr)
+                                                           N, out_h, out_w, words, rs, TY, TW, win_cap, thr)
   if (protos_dtype == SMB_F16) {
     if (layout_hwc) MF_LAUNCH(__half, true); else MF_LAUNCH(__half, false);
   } else {
@@ -646,5 +659,42 @@ extern "C" int smb_crop_split_forward(const void* data, const void* rois, void* 
   else
     SMB_CHECK_ARG(false, "smb_crop_split_forward: bad dtype %d", dtype);
   SMB_LAUNCH_OK("crop_split_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_crop_split_backward(const void* top_grad, const void* rois, void* bottom_grad, int dtype, int H, int W, int c,
+                                       int N, smb_stream_t stream) {
+  SMB_CHECK_ARG(top_grad && rois && bottom_grad, "smb_crop_split_backward: null pointer");
+  SMB_CHECK_ARG(c == 2, "smb_crop_split_backward: only c == 2 is used by SipMask (got %d)", c);
+  SMB_CHECK_ARG(H > 0 && W > 0 && N >= 0, "smb_crop_split_backward: bad shape");
+  const long long count = (long long)H * W * N;
+  if (count == 0) return SMB_OK;
+  const int blocks = (int)min((long long)148 * 16, (count + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMB_F32)
+    crop_split_backward_kernel<float><<<blocks, 256, 0, st>>>((const float*)top_grad, (const float*)rois, (float*)bottom_grad, count, H, W, N);
+  else if (dtype == SMB_F16)
+    crop_split_backward_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)top_grad, (const __half*)rois, (__half*)bottom_grad, count, H, W, N);
+  else
+    SMB_CHECK_ARG(false, "smb_crop_split_backward: bad dtype %d", dtype);
+  SMB_LAUNCH_OK("crop_split_backward_kernel");
+  return SMB_OK;
+}
+
+extern "C" int smb_crop_split_gt(const void* data, const void* rois, void* out, int dtype, int H, int W, int N,
+                                 smb_stream_t stream) {
+  SMB_CHECK_ARG(data && rois && out, "smb_crop_split_gt: null pointer");
+  SMB_CHECK_ARG(H > 0 && W > 0 && N >= 0, "smb_crop_split_gt: bad shape");
+  const long long count = (long long)H * W * N;
+  if (count == 0) return SMB_OK;
+  const int blocks = (int)min((long long)148 * 16, (count + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SMB_F32)
+    crop_mask_kernel<float><<<blocks, 256, 0, st>>>((const float*)data, (const float*)rois, (float*)out, count, H, W, N);
+  else if (dtype == SMB_F16)
+    crop_mask_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)data, (const __half*)rois, (__half*)out, count, H, W, N);
+  else
+    SMB_CHECK_ARG(false, "smb_crop_split_gt: bad dtype %d", dtype);
+  SMB_LAUNCH_OK("crop_mask_kernel");
   return SMB_OK;
 }

@@ -46,13 +46,83 @@ def crop_split(data, rois, c=2):
     return out
 
 
+@L.device_guard
+def crop_split_backward(grad_output, rois, c=2):
+    """grad_output [H,W,N], rois [N,4] -> grad_input [c*c,H,W,N] (ops/crop/crop_split.py:27-38)."""
+    _need_cuda(grad_output, rois)
+    g = grad_output.contiguous()
+    H, W, N = g.shape
+    rois = rois.to(g.dtype).contiguous()
+    out = torch.empty((c * c, H, W, N), dtype=g.dtype, device=g.device)
+    L.check(L.lib().smb_crop_split_backward(L.ptr(g), L.ptr(rois), L.ptr(out), _dt(g), H, W, int(c), N, L.stream_ptr()),
+            'smb_crop_split_backward')
+    return out
+
+
+@L.device_guard
+def crop_split_gt(data, rois, c=2):
+    """data [H,W,N], rois [N,4] -> data inside roi n, 0 outside (ops/crop/crop_split_gt.py:9-25); also its own backward."""
+    _need_cuda(data, rois)
+    if not data.is_contiguous():
+        raise L.SmbError('input must be contiguous')
+    H, W, N = data.shape
+    rois = rois.to(data.dtype).contiguous()
+    out = torch.empty_like(data)
+    L.check(L.lib().smb_crop_split_gt(L.ptr(data), L.ptr(rois), L.ptr(out), _dt(data), H, W, N, L.stream_ptr()),
+            'smb_crop_split_gt')
+    return out
+
+
+class _CropSplitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, rois, c):
+        ctx.c = c
+        ctx.save_for_backward(rois)
+        return crop_split(data, rois, c)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (rois,) = ctx.saved_tensors
+        return crop_split_backward(grad_output, rois, ctx.c), None, None
+
+
+class _CropSplitGtFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data, rois, c):
+        ctx.c = c
+        ctx.save_for_backward(rois)
+        return crop_split_gt(data, rois, c)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (rois,) = ctx.saved_tensors
+        return crop_split_gt(grad_output.contiguous(), rois, ctx.c), None, None
+
+
 class CropSplit(nn.Module):
+    """mmdet.ops.CropSplit (ops/crop/crop_split.py:42-49), differentiable w.r.t. `data` like the reference."""
+
     def __init__(self, c=2):
         super().__init__()
         self.c = c
 
     def forward(self, data, rois):
+        if data.requires_grad and torch.is_grad_enabled():
+            return _CropSplitFn.apply(data, rois, self.c)
         return crop_split(data, rois, self.c)
+
+
+class CropSplitGt(nn.Module):
+    """mmdet.ops.CropSplitGt (ops/crop/crop_split_gt.py:29-36)."""
+
+    def __init__(self, c=2):
+        super().__init__()
+        self.c = c
+
+    def forward(self, data, rois):
+        if data.requires_grad and torch.is_grad_enabled():
+            return _CropSplitGtFn.apply(data, rois, self.c)
+        return crop_split_gt(data, rois, self.c)
 
 
 # ------------------------------------------------------------------------------------------------ nms

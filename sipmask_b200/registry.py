@@ -21,12 +21,13 @@ def register_ops(force=True):
     import mmdet.ops as mmops
     from . import ops
     mmops.CropSplit = ops.CropSplit
+    mmops.CropSplitGt = ops.CropSplitGt
     mmops.DeformConv = ops.DeformConv
     mmops.nms = ops.nms
     for sub in ('crop', 'dcn', 'nms'):          # `from mmdet.ops.dcn import DeformConv` style imports
         m = getattr(mmops, sub, None)
         if m is not None:
-            for name in ('CropSplit', 'DeformConv', 'nms'):
+            for name in ('CropSplit', 'CropSplitGt', 'DeformConv', 'nms'):
                 if hasattr(m, name):
                     setattr(m, name, getattr(ops, name))
     return mmops

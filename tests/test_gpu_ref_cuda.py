@@ -139,3 +139,35 @@ def test_deform_conv_operator_vs_reference_im2col_gemm():
     assert got.shape == (B, Cout, H, W) and got.dtype == x.dtype
     err = (got.double() - want).abs().max().item()
     assert err <= 4e-3 * (want.abs().max().item() + 1.0), err      # fp16 column + fp16 output storage, fp32 accumulate
+
+
+@pytest.mark.parametrize('H,W,N', [(40, 56, 16), (100, 168, 37)])
+def test_crop_split_backward_and_gt_vs_reference_kernels(H, W, N):
+    """Training-side companions: CropSplit backward and CropSplitGt forward / backward against the reference's
+    own kernels (crop_split_cuda_kernel.cu:90-163, crop_split_gt_cuda_kernel.cu:19-140), bit for bit, incl. autograd."""
+    from sipmask_b200 import ops
+    lib = _ref()
+    g = torch.Generator().manual_seed(H + N)
+    rois = _rois(N, H, W, g).cuda()
+    top = (torch.rand(H, W, N, generator=g) + 0.01).cuda()
+    want = torch.zeros((4, H, W, N), dtype=torch.float32, device='cuda')              # crop_split.py:35 zero-initialises
+    torch.cuda.synchronize()
+    assert lib.ref_crop_split_backward(_p(top), _p(rois), _p(want), H, W, 2, N) == 0
+    got = ops.crop_split_backward(top, rois)
+    assert torch.equal(got, want)
+    data = (torch.rand(4, H, W, N, generator=g) + 0.01).cuda().requires_grad_(True)
+    out = ops.CropSplit(2)(data, rois)
+    out.backward(top)
+    assert torch.equal(data.grad, want)
+    # CropSplitGt
+    d = (torch.rand(H, W, N, generator=g) + 0.01).cuda()
+    want_f = torch.zeros_like(d)
+    torch.cuda.synchronize()
+    assert lib.ref_crop_split_gt_forward(_p(d), _p(rois), _p(want_f), H, W, 2, N) == 0
+    assert torch.equal(ops.CropSplitGt(2)(d, rois), want_f)
+    want_b = torch.zeros_like(d)
+    torch.cuda.synchronize()
+    assert lib.ref_crop_split_gt_backward(_p(top), _p(rois), _p(want_b), H, W, 2, N) == 0
+    dg = d.clone().requires_grad_(True)
+    ops.CropSplitGt(2)(dg, rois).backward(top)
+    assert torch.equal(dg.grad, want_b)
