@@ -308,6 +308,14 @@ int smb_preprocess_u8(const uint8_t* src, int src_h, int src_w, int src_pitch_by
 /* Stem 7x7/2 conv (3->64) + folded BN + ReLU on the padded NHWC8 image (backbones/resnet.py:448-460). */
 int smb_stem_plan_create(int N, int H, int W, const void* img_nhwc8, const void* weight448, void* out,
                          smb_conv_plan_t** plan_out);
+/* Space-to-depth form of the same stem (K = 256 instead of 448): the image is stored as [N, H/2+3, W/2+4, 16] fp16 with
+ * element (Y, X, (dy*2+dx)*4 + c) = padded pixel (2Y+dy, 2X+dx) channel c (smb_image_to_s2d16 / smb_preprocess_u8_s2d), the
+ * weights as [64, 4*64] with K = a*64 + b*16 + (dy*2+dx)*4 + c for filter tap (r, s) = (2a+dy, 2b+dx). */
+int smb_stem_plan_create_s2d(int N, int H, int W, const void* img_s2d16, const void* weight256, void* out,
+                             smb_conv_plan_t** plan_out);
+int smb_image_to_s2d16(const float* img_nchw_f32, void* out_s2d16, int N, int H, int W, smb_stream_t stream);
+int smb_preprocess_u8_s2d(const uint8_t* src, int src_h, int src_w, int src_pitch_bytes, int dst_h, int dst_w,
+                          const float* host_mean3, void* out_s2d16, int H, int W, smb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -288,6 +288,33 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, __half* __r
   }
 }
 
+// img [N,3,H,W] fp32 -> out [N, H/2+3, W/2+4, 16] fp16: the stem's space-to-depth layout, element (Y, X, (dy*2+dx)*4 + c) =
+// image pixel (2Y+dy-3, 2X+dx-3), channel c; zeros outside the image and in c == 3.
+__global__ void image_to_s2d16_kernel(const float* __restrict__ img, __half* __restrict__ out, int N, int H, int W) {
+  pdl_wait();
+  const int Hq = H / 2 + 3, Wq = W / 2 + 4;
+  const long long total = (long long)N * Hq * Wq;
+  const size_t plane = (size_t)H * W;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+    const int X = (int)(t % Wq);
+    const int Y = (int)((t / Wq) % Hq);
+    const int n = (int)(t / ((long long)Wq * Hq));
+    float f[16];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int x = 2 * X + (d & 1) - 3, y = 2 * Y + (d >> 1) - 3;
+      f[4 * d] = f[4 * d + 1] = f[4 * d + 2] = f[4 * d + 3] = 0.f;
+      if (x >= 0 && x < W && y >= 0 && y < H) {
+        const float* p = img + (size_t)n * 3 * plane + (size_t)y * W + x;
+        f[4 * d] = p[0]; f[4 * d + 1] = p[plane]; f[4 * d + 2] = p[2 * plane];
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + t * 16);
+    o[0] = pack8(f);
+    o[1] = pack8(f + 8);
+  }
+}
+
 // ------------------------------------------------------------------------------- multi-level (batched) variants
 // The FCOS towers run on five pyramid levels with shared weights; these kernels process all levels in one launch.
 constexpr int kMaxLv = 5;
@@ -525,6 +552,14 @@ static int fill_multi(MultiDesc* d, int num, const int* Hs, const int* Ws, long 
     d->start[l + 1] = d->start[l] + (long long)n_img * Hs[l] * Ws[l] * items_per_pixel;
   }
   return 0;
+}
+
+extern "C" int smb_image_to_s2d16(const float* img, void* out, int N, int H, int W, smb_stream_t stream) {
+  SMB_CHECK_ARG(img && out && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "smb_image_to_s2d16: bad argument");
+  const long long total = (long long)N * (H / 2 + 3) * (W / 2 + 4);
+  SMB_CUDA_OK(launch_pdl(image_to_s2d16_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, img, (__half*)out, N, H, W));
+  SMB_LAUNCH_OK("image_to_s2d16_kernel");
+  return SMB_OK;
 }
 
 extern "C" int smb_groupnorm_relu_apply_multi(int num_levels, void* const* xs, const void* const* stats, const int* Hs,

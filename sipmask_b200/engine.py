@@ -151,18 +151,27 @@ class SipMaskEngine(object):
             return
         self.img = self._t(N, 3, H, W, dtype=torch.float32)
         # ---- stem
-        img8 = self._t(N, H + 6, W + 8, 8)
+        # stem input: space-to-depth [N,H/2+3,W/2+4,16] (K = 256) by default, the 8-pixel-window NHWC8 form (K = 448) with
+        # SMB_STEM_S2D=0 (kept for A/B timing); the op keeps its round-1 name 'image_to_nhwc8' either way
+        s2d = os.environ.get('SMB_STEM_S2D', '1') != '0'
+        img8 = self._t(N, H // 2 + 3, W // 2 + 4, 16) if s2d else self._t(N, H + 6, W + 8, 8)
         self.img8 = img8
-        self._add(lambda: C.image_to_nhwc8(self.img, img8), name='image_to_nhwc8')
-        wk, b = self._once('stem', lambda: C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'),
-                                                              device=self.dev))
+        if s2d:
+            self._add(lambda: C.image_to_s2d16(self.img, img8), name='image_to_nhwc8')
+            wk, b = self._once('stem_s2d', lambda: C.pack_stem_weight_s2d(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'),
+                                                                          device=self.dev))
+        else:
+            self._add(lambda: C.image_to_nhwc8(self.img, img8), name='image_to_nhwc8')
+            wk, b = self._once('stem', lambda: C.pack_stem_weight(self._w('backbone.conv1.weight'), self._bn('backbone.bn1'),
+                                                                  device=self.dev))
         s1 = self._t(N, H // 2, W // 2, 64)
-        stem = C.StemPlan(img8, wk, b, s1, N, H, W)
+        stem = C.StemPlan(img8, wk, b, s1, N, H, W, s2d=s2d)
         self._keep += [stem, wk, b]
         self.conv_plans.append(stem)
-        fl = 2.0 * N * (H // 2) * (W // 2) * 64 * 147                                 # algorithmic 7x7x3 (executed K is 448)
+        fl = 2.0 * N * (H // 2) * (W // 2) * 64 * 147                                 # algorithmic 7x7x3 (executed K is 256 / 448)
         self.conv_flops += fl
-        self.conv_meta.append(dict(name='stem', M=N * (H // 2) * (W // 2), N=64, K=448, k=7, stride=2, flops=fl, res=False, gn=False))
+        self.conv_meta.append(dict(name='stem', M=N * (H // 2) * (W // 2), N=64, K=256 if s2d else 448, k=7, stride=2, flops=fl,
+                                   res=False, gn=False))
         self._add(stem.run, name='conv')
         x = self._t(N, H // 4, W // 4, 64)
         self._add(lambda s1=s1, x=x: C.maxpool3x3s2(s1, x), name='maxpool')

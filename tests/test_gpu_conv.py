@@ -150,6 +150,17 @@ def test_stem_matches_reference(H, W):
     wq = (w.cuda() * s.view(-1, 1, 1, 1)).half().double()
     y = F.conv2d(img.half().double(), wq, stride=2, padding=3) + bias.double().view(1, -1, 1, 1)
     _check(out, y.clamp(min=0).permute(0, 2, 3, 1))
+    # space-to-depth form (K = 256): same convolution, same fp16 weights, different summation grouping only
+    wk2, bias2 = conv.pack_stem_weight_s2d(w, bn, device='cuda')
+    q = conv.image_to_s2d16(img)
+    assert q.shape == (2, H // 2 + 3, W // 2 + 4, 16)
+    p8 = img8.float()                                           # [2, H+6, W+8, 8]: padded pixels, channels 0..2 real
+    want_q = p8.view(2, H // 2 + 3, 2, W // 2 + 4, 2, 8)[..., :4].permute(0, 1, 3, 2, 4, 5).reshape(2, H // 2 + 3, W // 2 + 4, 16)
+    assert torch.equal(q.float(), want_q)                       # q(Y, X, (dy*2+dx)*4 + c) = padded pixel (2Y+dy, 2X+dx, c)
+    out2 = torch.empty_like(out)
+    conv.StemPlan(q, wk2, bias2, out2, 2, H, W, s2d=True).run()
+    torch.cuda.synchronize()
+    _check(out2, y.clamp(min=0).permute(0, 2, 3, 1))
     # max pool 3x3/2 pad 1 (resnet.py:460)
     mp = conv.maxpool3x3s2(out)
     ref = F.max_pool2d(out.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)

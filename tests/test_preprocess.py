@@ -49,6 +49,10 @@ def test_device_preprocess_bit_exact(h, w):
     want = torch.empty_like(out)
     C.image_to_nhwc8(torch.from_numpy(x).cuda(), want)                          # the fp32 path of the engine
     assert torch.equal(out, want)
+    # space-to-depth layout of the stem (engine default)
+    out2 = torch.full((1, H // 2 + 3, W // 2 + 4, 16), 7.0, dtype=torch.float16, device='cuda')
+    C.preprocess_u8(torch.from_numpy(img).cuda(), (nh, nw), out2, P.MEAN_BGR)
+    assert torch.equal(out2, C.image_to_s2d16(torch.from_numpy(x).cuda()))
 
 
 @pytest.mark.gpu
