@@ -37,11 +37,11 @@ __global__ void gn_apply_kernel(__half* __restrict__ x, int n_img, int hw, int C
   const long long total = (long long)n_img * hw * vecs;
   const int G = 32, cpg = C / G;
   const float inv_cnt = 1.0f / ((float)hw * (float)cpg);
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int v = (int)(t % vecs);
-    const long long row = t / vecs;
+    const unsigned row = t / (unsigned)vecs;
     const int img = (int)(row / hw);
-    uint4* p = reinterpret_cast<uint4*>(x + row * pitch + v * 8);
+    uint4* p = reinterpret_cast<uint4*>(x + (size_t)row * pitch + v * 8);
     float f[8];
     unpack8(*p, f);
 #pragma unroll
@@ -107,10 +107,10 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int hw, int C, int
 __global__ void offset_conv_kernel(const float* __restrict__ bbox, int bbox_pitch, float scale, const float* __restrict__ w,
                                    int n_off, float* __restrict__ off, long long npix) {
   const long long total = npix * n_off;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int o = (int)(t % n_off);
-    const long long pix = t / n_off;
-    const float* b = bbox + pix * bbox_pitch;
+    const unsigned pix = t / (unsigned)n_off;
+    const float* b = bbox + (size_t)pix * bbox_pitch;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc = fmaf(__fmul_rn(b[k], scale), w[o * 4 + k], acc);
@@ -184,9 +184,9 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ x, __half* __rest
   pdl_wait();
   const int vecs = C >> 3;
   const long long total = (long long)N * Ho * Wo * vecs;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int v = (int)(t % vecs);
-    long long q = t / vecs;
+    unsigned q = t / (unsigned)vecs;
     const int ox = (int)(q % Wo); q /= Wo;
     const int oy = (int)(q % Ho);
     const int n = (int)(q / Ho);
@@ -221,9 +221,9 @@ __global__ void upsample_bilinear_kernel(const __half* __restrict__ x, int in_pi
   const int Ho = H * factor, Wo = W * factor;
   const float rs = 1.0f / (float)factor;
   const long long total = (long long)N * Ho * Wo * vecs;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int v = (int)(t % vecs);
-    long long q = t / vecs;
+    unsigned q = t / (unsigned)vecs;
     const int ox = (int)(q % Wo); q /= Wo;
     const int oy = (int)(q % Ho);
     const int n = (int)(q / Ho);
@@ -253,17 +253,17 @@ __global__ void copy_channels_kernel(const __half* __restrict__ x, int in_pitch,
   pdl_wait();
   const int vecs = C >> 3;
   const long long total = npix * vecs;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int v = (int)(t % vecs);
-    const long long pix = t / vecs;
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(x + pix * in_pitch + v * 8));
+    const unsigned pix = t / (unsigned)vecs;
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (size_t)pix * in_pitch + v * 8));
     if (relu) {
       __half2* h = reinterpret_cast<__half2*>(&u);
       const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
     }
-    *reinterpret_cast<uint4*>(y + pix * out_pitch + out_choff + v * 8) = u;
+    *reinterpret_cast<uint4*>(y + (size_t)pix * out_pitch + out_choff + v * 8) = u;
   }
 }
 
@@ -273,7 +273,7 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, __half* __r
   pdl_wait();
   const int Hp = H + 6, Wp = W + 8;
   const long long total = (long long)N * Hp * Wp;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int xp = (int)(t % Wp);
     const int yp = (int)((t / Wp) % Hp);
     const int n = (int)(t / ((long long)Wp * Hp));
@@ -284,7 +284,7 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, __half* __r
       const float* p = img + (size_t)n * 3 * plane + (size_t)y * W + x;
       f[0] = p[0]; f[1] = p[plane]; f[2] = p[2 * plane];
     }
-    *reinterpret_cast<uint4*>(out + t * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(out + (size_t)t * 8) = pack8(f);
   }
 }
 
@@ -295,7 +295,7 @@ __global__ void image_to_s2d16_kernel(const float* __restrict__ img, __half* __r
   const int Hq = H / 2 + 3, Wq = W / 2 + 4;
   const long long total = (long long)N * Hq * Wq;
   const size_t plane = (size_t)H * W;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int X = (int)(t % Wq);
     const int Y = (int)((t / Wq) % Hq);
     const int n = (int)(t / ((long long)Wq * Hq));
@@ -309,7 +309,7 @@ __global__ void image_to_s2d16_kernel(const float* __restrict__ img, __half* __r
         f[4 * d] = p[0]; f[4 * d + 1] = p[plane]; f[4 * d + 2] = p[2 * plane];
       }
     }
-    uint4* o = reinterpret_cast<uint4*>(out + t * 16);
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)t * 16);
     o[0] = pack8(f);
     o[1] = pack8(f + 8);
   }
@@ -343,12 +343,12 @@ __global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, 
   const int vecs = C >> 3;
   const int cpg = C / 32;
   const long long total = d.start[d.num];
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int l = find_level(d, t);
-    const long long q = t - d.start[l];
+    const unsigned q = t - (unsigned)d.start[l];
     const int hw = d.H[l] * d.W[l];
     const int v = (int)(q % vecs);
-    const long long row = q / vecs;
+    const unsigned row = q / (unsigned)vecs;
     const int img = (int)(row / hw);
     const int g = (v * 8) / cpg;
     const long long* st = reinterpret_cast<const long long*>(d.b[l]) + ((size_t)img * 32 + g) * 2;
@@ -357,7 +357,7 @@ __global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, 
     const float mean = __ll2float_rn(st[0]) * (1.0f / kGnSumScale) * inv_cnt;
     const float ex2 = __ll2float_rn(st[1]) * (1.0f / kGnSqScale) * inv_cnt;
     const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + eps);
-    uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.c[l]) + row * pitch + v * 8);
+    uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.c[l]) + (size_t)row * pitch + v * 8);
     float f[8];
     unpack8(*p, f);
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
@@ -377,12 +377,12 @@ __global__ void gn_apply_multi_kernel(MultiDesc d, int n_img, int C, int pitch, 
 __global__ void offset_conv_multi_kernel(MultiDesc d, int bbox_pitch, const float* __restrict__ w, int n_off) {
   pdl_wait();
   const long long total = d.start[d.num];
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)blockDim.x * gridDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < (unsigned)total; t += blockDim.x * gridDim.x) {   // 32-bit index math: 64-bit div/mod costs ~100 instructions each
     const int l = find_level(d, t);
-    const long long q = t - d.start[l];
+    const unsigned q = t - (unsigned)d.start[l];
     const int o = (int)(q % n_off);
-    const long long pix = q / n_off;
-    const float* b = reinterpret_cast<const float*>(d.a[l]) + pix * bbox_pitch;
+    const unsigned pix = q / (unsigned)n_off;
+    const float* b = reinterpret_cast<const float*>(d.a[l]) + (size_t)pix * bbox_pitch;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc = fmaf(__fmul_rn(b[k], d.scale[l]), w[o * 4 + k], acc);
@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(256) deform_im2col_multi_kernel(MultiDesc d, i
 }
 
 static inline int grid_for(long long total, int block) {
+  // the grid-stride kernels index their work items with 32 bits (64-bit div / mod costs ~100 instructions each on the GPU);
+  // 2^31 items = 16 GB of fp16 vectors, far beyond any tensor on this path
+  if (total >= (1LL << 31)) { fprintf(stderr, "sipmask_b200: %lld work items exceed the 32-bit index range\n", total); abort(); }
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 32;
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
