@@ -10,7 +10,7 @@ import sys
 COLS = [('gpu__time_duration.sum', 'time'), ('dram__bytes_read.sum', 'dram_rd'), ('dram__bytes_write.sum', 'dram_wr'),
         ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram%'), ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l2%'),
         ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm%'),
-        ('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'tensor%'),
+        ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor%'),
         ('sm__inst_executed_pipe_tensor.sum', 'tensor_inst'),
         ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ%'), ('launch__registers_per_thread', 'regs'),
@@ -50,13 +50,13 @@ def main():
                     except ValueError:
                         d[name] = r[idx[col]]
         out.append(d)
-    print('%-52s %9s %9s %9s %8s %6s %6s %6s %6s %5s %6s' % ('kernel', 'time_us', 'rd_MB', 'wr_MB', 'GB/s', 'dram%', 'l2%', 'sm%',
+    print('%-52s %9s %9s %9s %8s %6s %6s %6s %6s %5s %6s' % ('kernel', 'time_us', 'rd_MB', 'wr_MB', 'GB/s', 'tens%', 'l2%', 'sm%',
                                                               'issue%', 'regs', 'grid'))
     for d in out:
         tot = d.get('dram_rd', 0) + d.get('dram_wr', 0)
         print('%-52s %9.2f %9.2f %9.2f %8.0f %6.1f %6.1f %6.1f %6.1f %5d %6d' % (
             d['kernel'][:52], d.get('time', 0), d.get('dram_rd', 0) / 1e6, d.get('dram_wr', 0) / 1e6,
-            tot / max(d.get('time', 1e-9), 1e-9) / 1e3, d.get('dram%', 0), d.get('l2%', 0), d.get('sm%', 0), d.get('issue%', 0),
+            tot / max(d.get('time', 1e-9), 1e-9) / 1e3, d.get('tensor%', 0), d.get('l2%', 0), d.get('sm%', 0), d.get('issue%', 0),
             int(d.get('regs', 0)), int(d.get('grid', 0))))
     if '--json' in sys.argv:
         jpath = sys.argv[sys.argv.index('--json') + 1]
