@@ -617,8 +617,10 @@ extern "C" int smb_mask_assemble_pack(const void* protos, int protos_dtype, int 
   int TW = 4, TY = MF_TY_MAX;
   while (TW > 1 && win_rows(TY) * win_cols(TW) > px_budget) TW >>= 1;
   while (TY > 1 && win_rows(TY) * win_cols(TW) > px_budget) TY >>= 1;
-  const int win_cap = win_rows(TY) * win_cols(TW);
-  SMB_CHECK_ARG(win_cap <= px_budget, "smb_mask_assemble_pack: resize %dx%d -> %dx%d shrinks too much for one tile (%d source "
+  // rounded up to a multiple of 4 pixels: the arrays carved out of shared memory after the window (s_val, s_box, ...) are
+  // read with 16-byte vector loads
+  const int win_cap = (win_rows(TY) * win_cols(TW) + 3) & ~3;
+  SMB_CHECK_ARG(win_cap <= px_budget + 3, "smb_mask_assemble_pack: resize %dx%d -> %dx%d shrinks too much for one tile (%d source "
                 "pixels per 32-pixel word)", H, W, full_h, full_w, win_cap);
   dim3 grid(cdiv(cdiv(vw, 32), TW), cdiv(vh, TY)), block(MF_THREADS);
   const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];

@@ -67,16 +67,20 @@ def main():
             js = {}
         agg = {}
         for d in out:
-            a = agg.setdefault(d['kernel'], dict(n=0, bytes=0.0, time=0.0))
+            a = agg.setdefault(d['kernel'], dict(n=0, bytes=0.0, rd=0.0, wr=0.0, time=0.0))
             a['n'] += 1
             a['bytes'] += d.get('dram_rd', 0) + d.get('dram_wr', 0)
+            a['rd'] += d.get('dram_rd', 0)
+            a['wr'] += d.get('dram_wr', 0)
             a['time'] += d.get('time', 0)
         for k, a in agg.items():
             key = ('conv_gemm_kernel' if 'conv_gemm_kernel' in k else 'mask_fused_kernel' if 'mask_fused_pack' in k else
                    'mask_assemble_kernel' if 'mask_assemble_kernel' in k else k)
-            e = js.setdefault(key, dict(launches=0, dram_bytes=0.0, time_us=0.0))
+            e = js.setdefault(key, dict(launches=0, dram_bytes=0.0, dram_read_bytes=0.0, dram_write_bytes=0.0, time_us=0.0))
             e['launches'] += a['n']
             e['dram_bytes'] += a['bytes']
+            e['dram_read_bytes'] += a['rd']
+            e['dram_write_bytes'] += a['wr']
             e['time_us'] += a['time']
             e['source'] = 'ncu --set full, %s' % path.split('/')[-1]
         for key, e in js.items():
