@@ -259,6 +259,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback for the product path)'
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
 

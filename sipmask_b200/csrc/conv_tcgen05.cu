@@ -28,10 +28,10 @@ namespace smb {
 constexpr int kMaxTaps = 9;
 constexpr int kMaxMaps = 8;
 constexpr int kMaxLevels = 5;
-constexpr int kThreads = 352;          // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue (2 per TMEM lane quadrant),
-                                       // warp 10 = staging ring: TMA stores of finished chunks + residual prefetch
-constexpr int kStoreWarp = 10;
-constexpr int kEpiThreads = 256;
+constexpr int kThreads = 608;          // warp 0 = TMA, warp 1 = MMA, warps 2..17 = epilogue (4 per TMEM lane quadrant),
+                                       // warp 18 = staging ring: TMA stores of finished chunks + residual prefetch
+constexpr int kStoreWarp = 18;
+constexpr int kEpiThreads = 512;
 constexpr int kABytes = 128 * 64 * 2;   // one A stage: 128 pixels x 64 channels fp16
 
 // One pyramid level (or the only tensor) of a launch.  Convolutions whose weights are shared by several feature-pyramid
@@ -372,14 +372,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tma_prefetch_desc(&p.bmap);
     if (kPair) {
       // full: leader's expect_tx arrive + peer's remote arrive; empty / tfull: one multicast tcgen05.commit;
-      // tempty (used in the leader): 8 local + 8 remote epilogue warps
+      // tempty (used in the leader): 16 local + 16 remote epilogue warps
       for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 32); }
     } else {
       for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
     }
-    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&sfull_bar[i], 8); mbar_init(&sfree_bar[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&sfull_bar[i], 16); mbar_init(&sfree_bar[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -558,16 +558,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       __syncwarp();
     }
   } else {
-    // ===================== epilogue warps (2..9) =====================
-    // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); the pair splits the tile's
-    // columns, which doubles the loads/stores in flight of this latency-bound phase.
+    // ===================== epilogue warps (2..17) =====================
+    // Four warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); each takes a quarter of the tile's
+    // columns.  The epilogue is a long dependent instruction stream per thread (TMEM load -> convert / bias / residual ->
+    // pack -> staging store): with two warps per scheduler (r1) the issue slots were 23 % busy and a 64-channel chunk cost
+    // 1.1-1.4 k cycles whatever else ran on the GPU (profiles/r02_conv_mix_hbm_vs_tensor.txt); four warps per scheduler hide
+    // the fixed-latency dependencies of each other.
     const int lane_grp = warp & 3;
-    const int col_half = (warp - 2) >> 2;
+    const int col_q = (warp - 2) >> 2;               // 0..3: which 16 columns of every 64-column chunk
     const int row = lane_grp * 32 + lane;
-    const int et = threadIdx.x - 64;                 // 0..255 within the epilogue group
-    int split = ((p.n_tile / 2 + 31) / 32) * 32;
-    if (split > p.n_tile) split = p.n_tile;
-    const int c_begin = col_half ? split : 0, c_end = col_half ? p.n_tile : split;
+    const int et = threadIdx.x - 64;                 // 0..511 within the epilogue group
     uint32_t lt = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
@@ -607,16 +607,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           res_row = L.residual + (((size_t)tc.img * L.res_h + sy) * L.res_w + sx) * p.res_pitch;
         }
       }
-      // residual prefetch (one 32-channel chunk ahead of the accumulator drain)
-      uint4 rcur[4], rnext[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { rcur[j] = make_uint4(0u, 0u, 0u, 0u); rnext[j] = make_uint4(0u, 0u, 0u, 0u); }
-      if (res_row && c_begin < c_end && !p.out_tma) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (n0 + c_begin + j * 8 + 8 <= p.Cout && c_begin + j * 8 < c_end)
-            rcur[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c_begin + j * 8));
-      }
       TS2(17);
       // stage this tile's bias slice in shared memory (double-buffered; one named barrier per tile).  With a single N
       // tile the slice never changes: staged once, before the first tile.
@@ -625,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (p.bias) {
           for (int c = et; c < p.n_tile; c += kEpiThreads) sb[c] = (n0 + c < p.Cout) ? __ldg(p.bias + n0 + c) : 0.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
       TS2(18);
       mbar_wait(&tfull_bar[acc], acc_ph);
@@ -635,171 +625,157 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
       if (p.out_tma) {
         // ---------- staged epilogue: TMEM -> registers -> swizzled smem tile (128 px x 64 ch) -> TMA store ----------
-        // All 8 warps work on the same 64-channel chunk (warp pair = two 32-channel halves of a lane quadrant); the
+        // All 16 warps work on the same 64-channel chunk (the four warps of a lane quadrant take 16 channels each); the
         // scattered per-thread 16-byte global stores of the direct path become one coalesced, bounds-clipped TMA store.
         const int nch = p.n_tile >> 6;
-        uint4 rc[4], rn[4];
+        uint4 rc[2], rn[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { rc[j] = make_uint4(0u, 0u, 0u, 0u); rn[j] = make_uint4(0u, 0u, 0u, 0u); }
+        for (int j = 0; j < 2; ++j) { rc[j] = make_uint4(0u, 0u, 0u, 0u); rn[j] = make_uint4(0u, 0u, 0u, 0u); }
         const bool res_smem = p.res_tma && tc.active;
         if (res_row && !res_smem) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + col_half * 32 + j * 8));
+          for (int j = 0; j < 2; ++j) rc[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + col_q * 16 + j * 8));
         }
-        // Half-chunk software pipeline: while 16 accumulator columns are being turned into fp16, the tcgen05.ld of the next
-        // 16 is in flight (same register budget as one 32-column load).
-        uint32_t va[16], vb[16];
-        tmem_ld16(t_base + (uint32_t)(col_half * 32), va);
-        // The chunk loop is rolled (the body is ~400 SASS instructions instead of ~3000 straight-line ones per tile, and
-        // the GroupNorm partials need no dynamically indexed array).  NOTE: rolling it did NOT change the measured
-        // epilogue time (profiles/r01_conv_concurrency_h.txt, run 45); why a chunk still costs ~1.1-1.4k cycles with all
-        // of its work disabled (profiles/r01_epilogue_ablation_debug_bits.txt) is not yet attributed - see DESIGN.md 7.
+        // software pipeline over chunks: the tcgen05.ld of the next chunk's 16 columns is in flight while this chunk's are
+        // converted (the accumulator registers are copied out before the next load is issued)
+        uint32_t v[16];
+        tmem_ld16(t_base + (uint32_t)(col_q * 16), v);
 #pragma unroll 1
         for (int c64 = 0; c64 < nch; ++c64) {
-          {
-            const int cc = c64 * 64 + col_half * 32;     // first of this thread's 32 columns inside the tile
-            float gv[8];                                   // GroupNorm partials of this chunk: [group of 8 ch][sum, sumsq]
+          const int cc = c64 * 64 + col_q * 16;          // first of this thread's 16 columns inside the tile
+          if (res_row && !res_smem && c64 + 1 < nch) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = 0.f;
-            if (res_row && !res_smem && c64 + 1 < nch) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
-            }
-            const uint32_t srow = stage_a + (uint32_t)slot * 16384u + (uint32_t)row * 128u;   // this thread's staging row
-            if (o_flags & 4) {
-              // the slot's previous store has been read out AND this chunk's residual has landed in it (inactive tiles:
-              // the store warp arrives without a load)
-              mbar_wait_a(rfull_a + (uint32_t)slot * 8u, slot_ph);
-              if (res_smem) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rc[j] = lds128(srow + (uint32_t)(((col_half * 4 + j) ^ (row & 7)) * 16));
-              }
-            } else {
-              mbar_wait_a(sfree_a + (uint32_t)slot * 8u, slot_ph ^ 1);       // the slot's previous TMA store has been read out
-            }
-            TS3(20 + 4 * c64);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t* v = h ? vb : va;
-              if (!(o_dbg & 128)) {
-                tmem_ld_wait16(v);
-                if (h == 0) tmem_ld16(t_base + (uint32_t)(cc + 16), vb);
-                else if (c64 + 1 < nch) tmem_ld16(t_base + (uint32_t)(cc + 64), va);
-              }
-              if (h == 0) TS3(21 + 4 * c64);
-              float f[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-              if ((o_flags & 1) && !(o_dbg & 64)) {
-                const uint32_t ba = bias_a + (uint32_t)((single_n ? 0 : (int)(lt & 1) * 256) + cc + h * 16) * 4u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 b = lds128(ba + (uint32_t)j * 16u);
-                  f[4 * j] += __uint_as_float(b.x); f[4 * j + 1] += __uint_as_float(b.y);
-                  f[4 * j + 2] += __uint_as_float(b.z); f[4 * j + 3] += __uint_as_float(b.w);
-                }
-              }
-              if (o_flags & 16) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] *= o_alpha;
-              }
-              if ((res_row || res_smem) && !(o_dbg & 64)) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const __half2* hh = reinterpret_cast<const __half2*>(&rc[h * 2 + j]);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 a = __half22float2(hh[e]);
-                    f[j * 8 + 2 * e] += a.x; f[j * 8 + 2 * e + 1] += a.y;
-                  }
-                }
-              }
-              if ((o_flags & 8) && valid && !(o_dbg & 4)) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                  float sg = 0.f, qg = 0.f;
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) { sg += f[g * 8 + e]; qg += f[g * 8 + e] * f[g * 8 + e]; }
-                  gv[(h * 2 + g) * 2] = sg;
-                  gv[(h * 2 + g) * 2 + 1] = qg;
-                }
-              }
-              // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7); ReLU on the packed halves
-              // (max(round(x), 0) == round(max(x, 0)): rounding is monotonic and 0 is exact)
-              const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 o;
-                __half2* ho = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __half2 hv = __floats2half2_rn(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
-                  ho[e] = (o_flags & 2) ? __hmax2(hv, zero2) : hv;
-                }
-                const int chunk = (col_half * 4 + h * 2 + j) ^ (row & 7);
-                if (!(o_dbg & 32)) sts128(srow + (uint32_t)(chunk * 16), o);
-              }
-            }
-            if ((o_flags & 8) && !(o_dbg & 4)) {
-              // 32 lanes x 8 partials -> lane j (j < 8) ends up with the warp total of partial j (recursive halving over
-              // lane bits 2..0, then two full exchanges over bits 3, 4: 9 shuffles), then ONE 64-bit fixed-point atomic
-              // per partial (integer adds are associative: bit-reproducible statistics).
-#pragma unroll
-              for (int off = 4; off >= 1; off >>= 1) {
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < off; ++i) {
-                  const float send = up ? gv[i] : gv[i + off];
-                  const float keep = up ? gv[i + off] : gv[i];
-                  gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-              }
-              gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 8);
-              gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 16);
-              if (lane < 8 && tc.active) {
-                const int g = lane >> 1, kind = lane & 1;
-                const int grp = ((n0 + cc) >> 3) + g;
-                const int ngroups = p.Cout / p.gn_group;
-                unsigned long long* st = reinterpret_cast<unsigned long long*>(L.gn_stats) + ((size_t)tc.img * ngroups + grp) * 2 + kind;
-                atomicAdd(st, (unsigned long long)__float2ll_rn(gv[0] * (kind ? kGnSqScale : kGnSumScale)));
-              }
-            }
-            TS3(41);
-            if (!(o_dbg & 16)) fence_async_smem();         // generic-proxy writes -> visible to the TMA store
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(sfull_a + (uint32_t)slot * 8u);  // 8 warps -> the store warp ships the slot
-            TS3(22 + 4 * c64);
-            if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rc[j] = rn[j];
+            for (int j = 0; j < 2; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cc + 64 + j * 8));
           }
-        }
-      } else
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        if (res_row && c0 + 32 < c_end) {
+          const uint32_t srow = stage_a + (uint32_t)slot * 16384u + (uint32_t)row * 128u;   // this thread's staging row
+          if (o_flags & 4) {
+            // the slot's previous store has been read out AND this chunk's residual has landed in it (inactive tiles:
+            // the store warp arrives without a load)
+            mbar_wait_a(rfull_a + (uint32_t)slot * 8u, slot_ph);
+            if (res_smem) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (n0 + c0 + 32 + j * 8 + 8 <= p.Cout && c0 + 32 + j * 8 < c_end)
-              rnext[j] = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + c0 + 32 + j * 8));
+              for (int j = 0; j < 2; ++j) rc[j] = lds128(srow + (uint32_t)(((col_q * 2 + j) ^ (row & 7)) * 16));
+            }
+          } else {
+            mbar_wait_a(sfree_a + (uint32_t)slot * 8u, slot_ph ^ 1);       // the slot's previous TMA store has been read out
+          }
+          TS3(20 + 4 * c64);
+          float f[16];
+          if (!(o_dbg & 128)) {
+            tmem_ld_wait16(v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (c64 + 1 < nch) tmem_ld16(t_base + (uint32_t)(cc + 64), v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = 0.f;
+          }
+          TS3(21 + 4 * c64);
+          if ((o_flags & 1) && !(o_dbg & 64)) {
+            const uint32_t ba = bias_a + (uint32_t)((single_n ? 0 : (int)(lt & 1) * 256) + cc) * 4u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 b = lds128(ba + (uint32_t)j * 16u);
+              f[4 * j] += __uint_as_float(b.x); f[4 * j + 1] += __uint_as_float(b.y);
+              f[4 * j + 2] += __uint_as_float(b.z); f[4 * j + 3] += __uint_as_float(b.w);
+            }
+          }
+          if (o_flags & 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] *= o_alpha;
+          }
+          if ((res_row || res_smem) && !(o_dbg & 64)) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const __half2* hh = reinterpret_cast<const __half2*>(&rc[j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 a = __half22float2(hh[e]);
+                f[j * 8 + 2 * e] += a.x; f[j * 8 + 2 * e + 1] += a.y;
+              }
+            }
+          }
+          float gv[4] = {0.f, 0.f, 0.f, 0.f};            // GroupNorm partials of this chunk: [group of 8 ch][sum, sumsq]
+          if ((o_flags & 8) && valid && !(o_dbg & 4)) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float sg = 0.f, qg = 0.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { sg += f[g * 8 + e]; qg += f[g * 8 + e] * f[g * 8 + e]; }
+              gv[g * 2] = sg;
+              gv[g * 2 + 1] = qg;
+            }
+          }
+          // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7); ReLU on the packed halves
+          // (max(round(x), 0) == round(max(x, 0)): rounding is monotonic and 0 is exact)
+          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 o;
+            __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 hv = __floats2half2_rn(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
+              ho[e] = (o_flags & 2) ? __hmax2(hv, zero2) : hv;
+            }
+            const int chunk = (col_q * 2 + j) ^ (row & 7);
+            if (!(o_dbg & 32)) sts128(srow + (uint32_t)(chunk * 16), o);
+          }
+          if ((o_flags & 8) && !(o_dbg & 4)) {
+            // 32 lanes x 4 partials -> lane j (j < 4) ends up with the warp total of partial j (recursive halving over lane
+            // bits 1..0, then three full exchanges over bits 2..4: 6 shuffles), then ONE 64-bit fixed-point atomic per
+            // partial (integer adds are associative: bit-reproducible statistics).
+#pragma unroll
+            for (int off = 2; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send = up ? gv[i] : gv[i + off];
+                const float keep = up ? gv[i + off] : gv[i];
+                gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 4);
+            gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 8);
+            gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 16);
+            if (lane < 4 && tc.active) {
+              const int g = lane >> 1, kind = lane & 1;
+              const int grp = ((n0 + cc) >> 3) + g;
+              const int ngroups = p.Cout / p.gn_group;
+              unsigned long long* st = reinterpret_cast<unsigned long long*>(L.gn_stats) + ((size_t)tc.img * ngroups + grp) * 2 + kind;
+              atomicAdd(st, (unsigned long long)__float2ll_rn(gv[0] * (kind ? kGnSqScale : kGnSumScale)));
+            }
+          }
+          TS3(41);
+          if (!(o_dbg & 16)) fence_async_smem();         // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(sfull_a + (uint32_t)slot * 8u);  // 16 warps -> the store warp ships the slot
+          TS3(22 + 4 * c64);
+          if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) rc[j] = rn[j];
         }
-        uint32_t v[32];
-        if (c0 + 32 <= c_end) {
-          tmem_ld32(t_base + (uint32_t)c0, v);
-        } else {                                     // 16-column tail
+      } else {
+        // ---------- direct epilogue (fp32 head outputs, Cout not a multiple of 64): 16 columns per step ----------
+        const int units16 = (p.n_tile + 15) >> 4;
+        const int u_begin = (units16 * col_q) >> 2, u_end = (units16 * (col_q + 1)) >> 2;
+        for (int u = u_begin; u < u_end; ++u) {
+          const int c0 = u * 16;
+          const int ch0 = n0 + c0;
+          if (ch0 >= p.Cout) break;                    // warp-uniform
+          uint32_t v[16];
           tmem_ld16(t_base + (uint32_t)c0, v);
-#pragma unroll
-          for (int j = 16; j < 32; ++j) v[j] = 0u;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {                // two 16-channel halves
-          const int ch0 = n0 + c0 + h * 16;
-          if (c0 + h * 16 >= c_end || ch0 >= p.Cout) continue;     // warp-uniform
+          uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = make_uint4(0u, 0u, 0u, 0u);
+          if (res_row) {
+            r0 = __ldg(reinterpret_cast<const uint4*>(res_row + ch0));
+            r1 = __ldg(reinterpret_cast<const uint4*>(res_row + ch0 + 8));
+          }
+          tmem_ld_wait16(v);
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(sb + c0 + h * 16);
+            const float4* b4 = reinterpret_cast<const float4*>(sb + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b = b4[j];
@@ -811,8 +787,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int j = 0; j < 16; ++j) f[j] *= p.alpha;
           }
           if (res_row) {
-            const __half2* ha = reinterpret_cast<const __half2*>(&rcur[2 * h]);
-            const __half2* hb = reinterpret_cast<const __half2*>(&rcur[2 * h + 1]);
+            const __half2* ha = reinterpret_cast<const __half2*>(&r0);
+            const __half2* hb = reinterpret_cast<const __half2*>(&r1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 a = __half22float2(ha[j]), b = __half22float2(hb[j]);
@@ -878,8 +854,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
       }
       if (lt == 0 && warp == 2 && lane == 0) TS(10);
       TS2(36);
