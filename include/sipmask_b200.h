@@ -198,6 +198,14 @@ int smb_gather_det_inputs(const float* cof_src, int cof_pitch, const int* cand_l
 int smb_gather_track_feats(const float* track, int h, int w, int C, const float* det, const int* count_dev, int max_rows,
                            float scale_x, float scale_y, float feat_stride, float* out, smb_stream_t stream);
 
+/* HOST helper (plain C++, no CUDA): one frame of the SipMask-VIS tracker association (SipMask-VIS/mmdet/models/anchor_heads/
+ * sipmask_head.py:544-562,612-667) on host arrays.  State = the tracked objects' boxes [capacity,5], labels [capacity],
+ * features [capacity,feat_dim], of which the first n_prev are valid; updated in place.  host_ids_out [n] receives the object
+ * ids (-1: lost the claim).  Returns the new number of tracked objects, or a negative SMB_E* code. */
+int smb_track_step(const float* host_det, const int64_t* host_labels, const float* host_feats, int n, int feat_dim,
+                   float* host_prev_det, int64_t* host_prev_labels, float* host_prev_feats, int n_prev, int capacity,
+                   const float* host_match_coeff3, int32_t* host_ids_out);
+
 /* gather rows: dst[i,:] = src[idx[i],:] for i < *count (device count), zero otherwise. */
 int smb_gather_rows_f32(const float* src, int src_pitch, const int64_t* idx, const int* count_dev,
                         int max_rows, int row_elems, float* dst, smb_stream_t stream);

@@ -32,18 +32,62 @@ def log_softmax(x):
 
 
 class Tracker(object):
-    def __init__(self, match_coeff=(1.0, 2.0, 10.0)):
+    """native=True (default when the library is present): the per-frame step runs in C (`smb_track_step`, ~2 us instead of
+    ~150 us of numpy calls - at 8 GPUs the python version was the bottleneck of a clip); the numpy implementation below is the
+    same algorithm and is what `native=False` runs."""
+
+    def __init__(self, match_coeff=(1.0, 2.0, 10.0), native=True, capacity=4096, feat_dim=512):
         self.match_coeff = tuple(np.float32(c) for c in match_coeff)
         self.prev_roi_feats = self.prev_bboxes = self.prev_det_labels = None
+        self.native = native
+        self.capacity, self.feat_dim = capacity, feat_dim
+        if native:
+            import ctypes
+            from . import _lib as L
+            self._L, self._ct = L, ctypes
+            self._coef = np.asarray(self.match_coeff, np.float32)
+            self._pd = np.zeros((capacity, 5), np.float32)
+            self._pl = np.zeros((capacity,), np.int64)
+            self._pf = np.zeros((capacity, feat_dim), np.float32)
+            self._np = -1                                   # -1: no state yet (first frame of a video)
+            self._fn = L.lib().smb_track_step
+            self._state_ptrs = [ctypes.c_void_p(a.ctypes.data) for a in (self._pd, self._pl, self._pf, self._coef)]
 
     def reset(self):
         self.prev_roi_feats = self.prev_bboxes = self.prev_det_labels = None
+        if self.native:
+            self._np = -1
+
+    @property
+    def num_objects(self):
+        return max(self._np, 0) if self.native else (0 if self.prev_bboxes is None else self.prev_bboxes.shape[0])
+
+    def _step_native(self, det, lab, feats, is_first):
+        ct, n = self._ct, det.shape[0]
+        if n == 0:
+            return np.zeros((0,), np.int32)
+        assert feats.shape[1] == self.feat_dim
+        det, lab, feats = np.ascontiguousarray(det), np.ascontiguousarray(lab), np.ascontiguousarray(feats)
+        if is_first or self._np < 0:
+            assert n <= self.capacity
+            self._pd[:n], self._pl[:n], self._pf[:n] = det, lab, feats
+            self._np = n
+            return np.arange(n, dtype=np.int32)
+        ids = np.empty((n,), np.int32)
+        vp = ct.c_void_p
+        r = self._fn(vp(det.ctypes.data), vp(lab.ctypes.data), vp(feats.ctypes.data), n, self.feat_dim, self._state_ptrs[0],
+                     self._state_ptrs[1], self._state_ptrs[2], self._np, self.capacity, self._state_ptrs[3], vp(ids.ctypes.data))
+        self._L.check(r if r < 0 else 0, 'smb_track_step')
+        self._np = r
+        return ids
 
     def step(self, det_bboxes, det_labels, det_roi_feats, is_first):
         """det_bboxes [n,5] f32 (x1,y1,x2,y2,score), det_labels [n] int, det_roi_feats [n,512] f32 -> det_obj_ids [n] int32."""
         det = np.asarray(det_bboxes, np.float32)
         lab = np.asarray(det_labels, np.int64)
         feats = np.asarray(det_roi_feats, np.float32)
+        if self.native:
+            return self._step_native(det, lab, feats, is_first)
         n = det.shape[0]
         if n == 0:
             return np.zeros((0,), np.int32)

@@ -68,7 +68,7 @@ def test_host_tracker_matches_oracle_tracker():
     from oracle import postproc as P
     from sipmask_b200.tracker import Tracker
     rng = np.random.RandomState(0)
-    a, b = P.VISTracker(), Tracker()
+    a, b, c = P.VISTracker(), Tracker(native=False), Tracker(native=True)
     for t in range(12):
         n = int(rng.randint(0, 9))
         xy = rng.rand(n, 2) * 100
@@ -79,4 +79,32 @@ def test_host_tracker_matches_oracle_tracker():
         first = t in (0, 7)
         ia = a.step(torch.from_numpy(det), torch.from_numpy(lab), torch.from_numpy(feats), first)
         ib = b.step(det, lab, feats, first)
-        assert np.asarray(ia).tolist() == np.asarray(ib).tolist(), t
+        ic = c.step(det, lab, feats, first)                  # smb_track_step (host C) - the default of the product
+        assert np.asarray(ia).tolist() == np.asarray(ib).tolist() == np.asarray(ic).tolist(), t
+        assert c.num_objects == b.num_objects == a.prev_bboxes.shape[0]
+
+
+def test_native_tracker_reproduces_reference_clip(golden_dir):
+    """The product's default tracker step (smb_track_step, host C in the ABI library) on the reference clip: oracle head
+    outputs -> oracle post-processing -> native association must give the reference python's object ids."""
+    from oracle import model as M
+    from oracle import postproc as P
+    from sipmask_b200.tracker import Tracker
+    g = dict(np.load(os.path.join(golden_dir, 'ref_vis_clip.npz')))
+    head = M.SipMaskVISHead(num_classes=41, stacked_convs=3)
+    head.load_state_dict(synth.head_state_dict(seed=int(g['seed']), prefix='', num_classes=41, stacked_convs=3, gn=True,
+                                               cls_bias=-2.0, track=True), strict=True)
+    head.eval()
+
+    class Wrap(object):
+        def __init__(self):
+            self.t = Tracker(native=True)
+
+        def step(self, det, lab, feats, first):
+            return self.t.step(det.numpy(), lab.numpy(), feats.numpy(), first)
+    w = Wrap()
+    for t, feats in enumerate(clip_feats(g)):
+        with torch.no_grad():
+            outs = head(feats, feats, False)
+        _, _, _, ids = P.vis_get_bboxes(outs, vis_meta(g, t), vis_cfg(g), w, rescale=True)
+        assert np.asarray(ids).tolist() == g['f%d_ids' % t].tolist(), t
