@@ -521,7 +521,7 @@ def mask_rooflines(line, eng, pk, pk_kind, traffic, H, IMG_W):
     ma_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + N * Hm * Wm * 4
     gbs = ma_bytes / (ma_ms * 1e-3) / 1e9
     tr = traffic.get('mask_assemble', {})
-    line['roofline_mask_assembly'] = dict(bound='hbm', kernel='smb_mask_assemble = memset + mask_assemble_kernel', achieved=gbs,
+    line['roofline_mask_assembly'] = dict(bound='hbm', kernel='mask_assemble_kernel (writes every output element; no memset)', achieved=gbs,
                                           peak=float(pk['hbm_gbs']), unit='GB/s', frac=gbs / float(pk['hbm_gbs']),
                                           traffic=tr.get('dram_bytes_per_launch'), traffic_source=tr.get('source'), ms=ma_ms,
                                           algorithmic_bytes=ma_bytes, peak_source=pk_kind + ' hbm_gbs',

@@ -133,6 +133,18 @@ __device__ __forceinline__ void stage_window(const PT* __restrict__ protos, unsi
   }
 }
 
+template <typename OT>
+__device__ __forceinline__ void store_zero4(OT* p);
+template <>
+__device__ __forceinline__ void store_zero4<float>(float* p) { *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f); }
+template <>
+__device__ __forceinline__ void store_zero4<__half>(__half* p) { *reinterpret_cast<uint2*>(p) = make_uint2(0u, 0u); }
+
+// The kernel writes EVERY output element exactly once (no separate zero-fill pass): for a detection whose roi misses the
+// tile the CTA stores 8 x 256 bytes of zeros (one 16-byte store per thread, 128 threads), for an intersecting one each warp
+// stores its row (value inside the roi, 0 outside; 128 bytes per store instruction).  With seven CTAs per SM the stores of
+// ~100 detections per tile are in flight concurrently - the r1 kernel had the same store pattern but 8 warps per SM and a
+// serial per-thread detection loop.
 template <typename PT, bool HWC, typename OT>
 __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_kernel(
     const PT* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes,
@@ -150,12 +162,17 @@ __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_kernel(
   const bool row_ok = warp < SRa;
   const float hf = (float)h;
   const float tile_x0 = (float)x0t, tile_x1 = (float)(x0t + SCa - 1), tile_y0 = (float)y0t, tile_y1 = (float)(y0t + SRa - 1);
+  // zero-fill role: thread t < 128 owns the 4 pixels (row t / 16, columns 4 * (t % 16) ..) of the tile
+  const int zr = threadIdx.x >> 4, zc = (threadIdx.x & 15) * 4;
+  const bool z_vec = threadIdx.x < 128 && zr < SRa && zc + 3 < SCa && ((W & 3) == 0);
+  const bool z_tail = threadIdx.x < 128 && zr < SRa && !z_vec && zc < SCa;
 
   for (int n0 = 0; n0 < N; n0 += MA_LIST) {
     const int nb = min(MA_LIST, N - n0);
     __syncthreads();                                   // window staged / previous pass done with the list
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
+    bool mine_listed = false;
     if (threadIdx.x < nb) {
       const float* b = boxes + (size_t)(n0 + threadIdx.x) * 4;
       BoxP bp;
@@ -170,26 +187,50 @@ __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_kernel(
         const int pos = atomicAdd(&s_cnt, 1);
         s_box[pos] = bp;
         s_det[pos] = n0 + threadIdx.x;
+        mine_listed = true;
       }
+    }
+    // listed flags of this pass as four 32-bit ballots, broadcast through shared memory
+    __shared__ unsigned s_listed[MA_LIST / 32];
+    {
+      const unsigned bal = __ballot_sync(0xffffffffu, mine_listed);
+      if (lane == 0 && warp < MA_LIST / 32) s_listed[warp] = bal;
     }
     __syncthreads();
     const int cnt = s_cnt;
+    // ---- detections whose roi misses the tile: zeros (16 bytes per thread, 8 rows x 256 B per detection)
+    if (z_vec | z_tail) {
+      for (int j = 0; j < nb; ++j) {
+        if ((s_listed[j >> 5] >> (j & 31)) & 1u) continue;
+        OT* dst = out + ((size_t)(n0 + j) * H + (y0t + zr)) * W + x0t + zc;
+        if (z_vec) {
+          store_zero4<OT>(dst);
+        } else {
+          for (int e = 0; e < 4 && zc + e < SCa; ++e) store1<OT>(dst + e, 0.f);
+        }
+      }
+    }
     if (!row_ok) continue;
+    // ---- listed detections: every pixel of the tile row is written (value inside the roi, 0 outside)
     for (int j = 0; j < cnt; ++j) {
       const BoxP b = s_box[j];
-      if (!((hf >= b.y1) & (hf < b.y2))) continue;     // warp-uniform: this tile row is outside the roi
+      const bool row_in = (hf >= b.y1) & (hf < b.y2);     // warp-uniform
       const int n = s_det[j];
       const float* cof = cofs + (size_t)n * 128;
-      const int idx_h = (int)__fdiv_rn(hf - b.y1, b.roi_h);
+      const int idx_h = row_in ? (int)__fdiv_rn(hf - b.y1, b.roi_h) : 0;
       OT* dst = out + ((size_t)n * H + h) * W + x0t;
 #pragma unroll
       for (int q = 0; q < MA_TW / 32; ++q) {
         const int c = lane + q * 32;
-        const float wf = (float)(x0t + c);
-        if ((c < SCa) & (wf >= b.x1) & (wf < b.x2)) {
-          const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
-          const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
-          store1<OT>(dst + c, sigmoidf_(dot32_swz<PT>(s_p, warp * SCa + c, cof + cell * 32)));
+        if (c < SCa) {
+          const float wf = (float)(x0t + c);
+          float v = 0.f;
+          if (row_in & (wf >= b.x1) & (wf < b.x2)) {
+            const int idx_w = (int)__fdiv_rn(wf - b.x1, b.roi_w);
+            const int cell = min(max(idx_h * 2 + idx_w, 0), 3);
+            v = sigmoidf_(dot32_swz<PT>(s_p, warp * SCa + c, cof + cell * 32));
+          }
+          store1<OT>(dst + c, v);
         }
       }
     }
@@ -503,8 +544,6 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
   dim3 grid(cdiv(W, MA_TW), cdiv(H, MA_TH)), block(MA_THREADS2);
   const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
   cudaStream_t st = (cudaStream_t)stream;
-  // zero background first (a memset node: runs at store bandwidth), then the in-box pixels only
-  SMB_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)N * H * W * (out_dtype == SMB_F32 ? 4 : 2), st));
   const size_t ma_smem = (size_t)MA_TH * MA_TW * (protos_dtype == SMB_F16 ? 64 : 128);
   static DeviceOnce ma_once;
   if (ma_once.first()) {
