@@ -275,6 +275,26 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t* v) {
                : "memory");
 }
 
+// Packed fp32 pair add (FADD2 on sm_100: two independent IEEE adds per instruction) and fp32x2 -> fp16x2 pack with the ReLU
+// folded into the conversion (F2FP.RELU).  The epilogue is issue-bound: ~12 instructions per output element.
+__device__ __forceinline__ void fadd2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long ua, ub;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ua) : "l"(ub));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(ua));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {      // max(round(x), 0) == round(max(x, 0))
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024>>4 |
 //   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
@@ -318,10 +338,23 @@ struct TileCoord {
 
 __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
 
+// n / d and n % d for small non-negative n (< 2^22) without the ~30-instruction integer division: float reciprocal estimate
+// plus one correction step (exact: the estimate is off by at most one).  The tile decode runs once per tile in every
+// epilogue thread, on the critical path of the short-K (epilogue-bound) plans.
+__device__ __forceinline__ int fast_divmod(int n, int d, int& rem) {
+  int q = __float2int_rz(__int2float_rn(n) * __frcp_rn(__int2float_rn(d)));
+  int r = n - q * d;
+  if (r >= d) { ++q; r -= d; }
+  if (r < 0) { --q; r += d; }
+  rem = r;
+  return q;
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int unit, int rank) {
   TileCoord t;
-  const int nt = unit % p.n_tiles_n;
-  int mt = (unit / p.n_tiles_n) * p.cluster + rank;
+  int nt = 0, um = unit;
+  if (p.n_tiles_n > 1) um = fast_divmod(unit, p.n_tiles_n, nt);
+  int mt = um * p.cluster + rank;
   t.active = mt < p.tiles_m;
   if (!t.active) mt = p.tiles_m - 1;
   int l = 0;
@@ -329,11 +362,10 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int unit, 
   for (int i = 1; i < kMaxLevels; ++i)
     if (i < p.num_levels && mt >= p.lv[i].tile_start) l = i;
   mt -= p.lv[l].tile_start;
-  const int tx = mt % p.lv[l].tiles_x;
-  mt /= p.lv[l].tiles_x;
-  const int ty = mt % p.lv[l].tiles_y;
+  int tx, ty;
+  mt = fast_divmod(mt, p.lv[l].tiles_x, tx);
+  t.img = fast_divmod(mt, p.lv[l].tiles_y, ty);
   t.lvl = l;
-  t.img = mt / p.lv[l].tiles_y;
   t.x0 = tx * p.lv[l].BW;
   t.y0 = ty * p.lv[l].BH;
   t.n0 = nt * p.n_tile;
@@ -592,7 +624,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #define TS3(slot) do { } while (0)
 #endif
       TS2(16);
-      const int iy = row / L.BW, ix = row - iy * L.BW;
+      const int bw_shift = 31 - __clz(L.BW);            // BW is a power of two (choose_patch)
+      const int iy = row >> bw_shift, ix = row & (L.BW - 1);
       const int x = tc.x0 + ix, y = tc.y0 + iy, n0 = tc.n0;
       const bool valid = tc.active && (x < L.W_out) && (y < L.H_out);
       const size_t pix = ((size_t)tc.img * L.H_out + y) * L.W_out + x;
@@ -695,8 +728,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const uint4 b = lds128(ba + (uint32_t)j * 16u);
-                  f[4 * j] += __uint_as_float(b.x); f[4 * j + 1] += __uint_as_float(b.y);
-                  f[4 * j + 2] += __uint_as_float(b.z); f[4 * j + 3] += __uint_as_float(b.w);
+                  fadd2(f[4 * j], f[4 * j + 1], __uint_as_float(b.x), __uint_as_float(b.y));
+                  fadd2(f[4 * j + 2], f[4 * j + 3], __uint_as_float(b.z), __uint_as_float(b.w));
                 }
               }
               if (o_flags & 16) {
@@ -710,7 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const float2 a = __half22float2(hh[e]);
-                    f[j * 8 + 2 * e] += a.x; f[j * 8 + 2 * e + 1] += a.y;
+                    fadd2(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1], a.x, a.y);
                   }
                 }
               }
@@ -726,15 +759,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               }
               // swizzled staging write: row = pixel, 16-byte chunk index ^= (row & 7); ReLU on the packed halves
               // (max(round(x), 0) == round(max(x, 0)): rounding is monotonic and 0 is exact)
-              const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 uint4 o;
-                __half2* ho = reinterpret_cast<__half2*>(&o);
+                uint32_t* ho = reinterpret_cast<uint32_t*>(&o);
+                if (o_flags & 2) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __half2 hv = __floats2half2_rn(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
-                  ho[e] = (o_flags & 2) ? __hmax2(hv, zero2) : hv;
+                  for (int e = 0; e < 4; ++e) ho[e] = pack_f16x2_relu(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) ho[e] = pack_f16x2(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
                 }
                 const int chunk = (col_half * 4 + h * 2 + j) ^ (row & 7);
                 if (!(o_dbg & 32)) sts128(srow + (uint32_t)(chunk * 16), o);
