@@ -32,7 +32,7 @@ WORKLOADS = {
     # configs[3]: real-time SSD-style head (2 convs, no GN, fast_nms), 544x544, bs=32 per forward (throughput mode)
     'B': dict(name='SipMask R50-FPN SSD-style head (2conv, no GN, fast_nms), 544x544, bs=32 per forward, synthetic images + '
                    'seeded synthetic weights', depth=50, stacked=2, gn=False, ssd=True, H=544, W=544, img_w=544, batch=32,
-              score_thr=0.1, in_flight=2),
+              score_thr=0.1, in_flight=1),
     # configs[4]: SipMask-VIS frame path (3-conv towers, 40 classes, tracking branch, fast_nms max 10), 360x640 padded to
     # 384x640; frames are sharded one per GPU per step, records + 512-d track features are gathered once at the end and the
     # tracker association runs on the host in frame order (inside the timed region)
