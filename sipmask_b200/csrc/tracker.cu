@@ -19,6 +19,21 @@
 
 #include "common.cuh"
 
+// 512-term dot product; the host compiler emits an AVX2 + FMA clone next to the baseline one and picks at load time
+// (function multi-versioning), so the library still runs on any x86-64 host.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDA_ARCH__)
+__attribute__((target_clones("avx2,fma", "default")))
+#endif
+static float dot_f32(const float* __restrict__ a, const float* __restrict__ b, int n) {
+  float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int k = 0;
+  for (; k + 8 <= n; k += 8)
+    for (int e = 0; e < 8; ++e) a8[e] += a[k + e] * b[k + e];
+  float acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+  for (; k < n; ++k) acc += a[k] * b[k];
+  return acc;
+}
+
 extern "C" int smb_track_step(const float* host_det, const int64_t* host_labels, const float* host_feats, int n, int feat_dim,
                               float* host_prev_det, int64_t* host_prev_labels, float* host_prev_feats, int n_prev, int capacity,
                               const float* host_match_coeff3, int32_t* host_ids_out) {
@@ -40,13 +55,7 @@ extern "C" int smb_track_step(const float* host_det, const int64_t* host_labels,
     float mx = 0.f;
     for (int j = 0; j < m; ++j) {
       const float* pf = host_prev_feats + (size_t)j * feat_dim;
-      // eight independent partial sums: lets the host compiler vectorise the 512-term dot product
-      float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int k = 0;
-      for (; k + 8 <= feat_dim; k += 8)
-        for (int e = 0; e < 8; ++e) a8[e] += f[k + e] * pf[k + e];
-      float acc = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-      for (; k < feat_dim; ++k) acc += f[k] * pf[k];
+      const float acc = dot_f32(f, pf, feat_dim);       // eight independent partial sums (vectorisable)
       row[j + 1] = acc;
       mx = acc > mx ? acc : mx;
     }
