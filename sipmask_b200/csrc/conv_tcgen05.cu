@@ -63,6 +63,7 @@ struct ConvParams {
   int debug_mode;                 // profiling only (SMB_CONV_DEBUG): 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA only)
   int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
   int out_pitch; int out_f32; int out_tma; int res_tma;
+  int store_lag;                  // TMA stores kept in flight before a slot is recycled (1..4, < stage_slots)
   int stage_slots;                // staging ring: n_tile/64 (one tile) or 2*n_tile/64 (two tiles) chunk buffers of 128 px x 64 ch
   const float* bias; float alpha;
   int res_pitch; int res_mode;
@@ -569,7 +570,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           // (a deeper lag - more stores in flight - was measured slower: it delays the residual requests, r01 run 42)
           int h = -1;
           if (nslots == 1) { bulk_wait_read<0>(); h = g; }
-          else if (g >= 1) { bulk_wait_read<1>(); h = g - 1; }
+          else if (g >= p.store_lag) {
+            // keep `store_lag` stores in flight: recycle the slot of chunk g - lag once its store has been read out
+            switch (p.store_lag) {
+              case 1: bulk_wait_read<1>(); break;
+              case 2: bulk_wait_read<2>(); break;
+              case 3: bulk_wait_read<3>(); break;
+              default: bulk_wait_read<4>(); break;
+            }
+            h = g - p.store_lag;
+          }
           if (h >= 0) {
             if (p.res_tma) {
               if (h + nslots < total_chunks) { fence_async_smem(); request_residual(h + nslots); }
@@ -1055,6 +1065,7 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   // without starving the operand pipeline (short-K tiles - the bottleneck output / shortcut 1x1 convs - are epilogue-bound:
   // with two tiles of slots the residual of the next tile lands and the stores of the previous tile drain meanwhile).
   p.stage_slots = n_tile / 64;
+  p.store_lag = 1;
   {
     const int kblocks = Ktotal / 64;
     const char* envs = getenv("SMB_CONV_STAGE_SETS");
@@ -1064,6 +1075,14 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
       p.stage_slots *= 2;
       stage_out *= 2;
     }
+  }
+  {
+    const char* envl = getenv("SMB_CONV_STORE_LAG");
+    int lag = envl ? atoi(envl) : 1;
+    if (lag < 1) lag = 1;
+    if (lag > 4) lag = 4;
+    if (lag > p.stage_slots - 1) lag = p.stage_slots > 1 ? p.stage_slots - 1 : 1;
+    p.store_lag = lag;
   }
   const size_t budget = 194 * 1024 - stage_out;
   int stages = (int)(budget / stage);

@@ -66,7 +66,10 @@ def bench(p):
 
 VARIANTS = [('base', {}), ('no store (DEBUG=8)', {'SMB_CONV_DEBUG': '8'}), ('residual via LDG', {'SMB_CONV_NO_TMA_RES': '1'}),
             ('direct STG epilogue', {'SMB_CONV_NO_TMA_STORE': '1'}), ('one staging set', {'SMB_CONV_STAGE_SETS': '1'}),
-            ('no pair mode', {'SMB_CONV_PAIR': '0'}), ('no store + residual via LDG', {'SMB_CONV_DEBUG': '8', 'SMB_CONV_NO_TMA_RES': '1'})]
+            ('no store + residual via LDG', {'SMB_CONV_DEBUG': '8', 'SMB_CONV_NO_TMA_RES': '1'}),
+            ('store lag 2', {'SMB_CONV_STORE_LAG': '2'}), ('store lag 3', {'SMB_CONV_STORE_LAG': '3'}),
+            ('store lag 4', {'SMB_CONV_STORE_LAG': '4'}), ('store lag 4, no store', {'SMB_CONV_STORE_LAG': '4', 'SMB_CONV_DEBUG': '8'}),
+            ('store lag 3, residual via LDG', {'SMB_CONV_STORE_LAG': '3', 'SMB_CONV_NO_TMA_RES': '1'})]
 for res in (True, False):
     for cap in (48, None):
         print('--- layer1 %s, %s' % ('conv3 (+residual, 77 MB)' if res else 'downsample (no residual, 43 MB)', 'cap %d CTAs' % cap if cap else 'uncapped'))
