@@ -67,6 +67,10 @@ def bench(p):
 VARIANTS = [('base', {}), ('no store (DEBUG=8)', {'SMB_CONV_DEBUG': '8'}), ('residual via LDG', {'SMB_CONV_NO_TMA_RES': '1'}),
             ('direct STG epilogue', {'SMB_CONV_NO_TMA_STORE': '1'}), ('one staging set', {'SMB_CONV_STAGE_SETS': '1'}),
             ('no store + residual via LDG', {'SMB_CONV_DEBUG': '8', 'SMB_CONV_NO_TMA_RES': '1'}),
+            ('no TMEM loads (128)', {'SMB_CONV_DEBUG': '128'}), ('no bias/res math (64)', {'SMB_CONV_DEBUG': '64'}),
+            ('no staging writes (32)', {'SMB_CONV_DEBUG': '32'}), ('no proxy fence (16)', {'SMB_CONV_DEBUG': '16'}),
+            ('no tmem/math/sts/fence (240)', {'SMB_CONV_DEBUG': '240'}), ('no tmem/math/sts/fence/store (248)', {'SMB_CONV_DEBUG': '248'}),
+            ('no MMA (1): TMA + epilogue only', {'SMB_CONV_DEBUG': '1'}),
             ('store lag 2', {'SMB_CONV_STORE_LAG': '2'}), ('store lag 3', {'SMB_CONV_STORE_LAG': '3'}),
             ('store lag 4', {'SMB_CONV_STORE_LAG': '4'}), ('store lag 4, no store', {'SMB_CONV_STORE_LAG': '4', 'SMB_CONV_DEBUG': '8'}),
             ('store lag 3, residual via LDG', {'SMB_CONV_STORE_LAG': '3', 'SMB_CONV_NO_TMA_RES': '1'})]
