@@ -949,6 +949,184 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Short-K 1x1 convolutions (ResNet conv1 / conv3 / shortcut with K <= 256): ONE 128 x 128 tile per CTA, no persistent loop,
+// no staging ring, several CTAs resident per SM.
+//
+// Why a second kernel: for these shapes the persistent kernel above spends ~3.3 us per 128-pixel tile even with its whole
+// epilogue switched off (profiles/r02_conv_diag_short_k.txt: 39.7 -> 35.8 us with TMEM loads, math, staging writes, fence and
+// stores disabled) - the tile time is the latency of the load -> MMA -> commit -> epilogue -> recycle chain of ONE CTA per
+// SM, which a K = 64 tile (one k-block) cannot amortise.  Here the chain is still there, but 2-3 independent CTAs per SM
+// (64-96 KB shared memory, 128 TMEM columns, 160 threads each) overlap each other's latencies.
+//
+//   warp 0      : TMEM alloc, TMA loads (A k-blocks, weight k-blocks, residual tile) and tcgen05.mma issue (one elected lane)
+//   warps 1..4  : epilogue, one TMEM lane quadrant each: tcgen05.ld 32 columns -> +bias (+residual from the staging tile)
+//                 -> ReLU -> fp16 -> back into the swizzled staging tile; then two 64-channel TMA stores.
+constexpr int kSmallThreads = 160;
+constexpr int kSmallN = 128;
+
+__global__ void __launch_bounds__(kSmallThreads) conv1x1_small_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nst = p.stages;                                   // 1 or 2 operand stages
+  uint8_t* sA = smem;                                         // [nst][128 px x 64 ch]
+  uint8_t* sB = smem + (size_t)nst * kABytes;                 // [nst][128 co x 64 k]
+  uint8_t* s_stage = sB + (size_t)nst * kABytes;              // [2][128 px x 64 ch]: residual in, result out
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stage + 2 * 16384);
+  uint64_t* empty_bar = full_bar + 2;
+  uint64_t* tfull_bar = empty_bar + 2;
+  uint64_t* rfull_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.amap[0]);
+      tma_prefetch_desc(&p.bmap);
+      tma_prefetch_desc(&p.omap[0]);
+      for (int i = 0; i < 2; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      mbar_init(tfull_bar, 1);
+      mbar_init(rfull_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, (uint32_t)kSmallN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // tile of this CTA: N tiles of one M tile are adjacent in the grid (they read the same activation patch: L2 reuse)
+  const LevelDesc& L = p.lv[0];
+  int nt;
+  int mt = fast_divmod((int)blockIdx.x, p.n_tiles_n, nt);
+  int tx, ty;
+  mt = fast_divmod(mt, L.tiles_x, tx);
+  const int img = fast_divmod(mt, L.tiles_y, ty);
+  const int x0 = tx * L.BW, y0 = ty * L.BH, n0 = nt * kSmallN;
+  const int kblocks = p.kb_per_tap;                            // one tap (1x1), Cin / 64 k-blocks
+
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(128, kSmallN);
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+    const int ax = x0 + p.tap_dx[0], ay = y0 + p.tap_dy[0];
+    if (elect_one()) {
+      if (p.res_tma) {                                       // residual tile: two 64-channel boxes into the staging tile
+        mbar_expect_tx(rfull_bar, 2 * 16384);
+        tma_load_4d(s_stage, &p.rmap[0], rfull_bar, n0, x0, y0, img);
+        tma_load_4d(s_stage + 16384, &p.rmap[0], rfull_bar, n0 + 64, x0, y0, img);
+      }
+      for (int kb = 0; kb < nst && kb < kblocks; ++kb) {
+        mbar_expect_tx(&full_bar[kb], 2 * kABytes);
+        tma_load_4d(sA + (size_t)kb * kABytes, &p.amap[p.tap_map[0]], &full_bar[kb], kb * 64, ax, ay, img);
+        tma_load_2d(sB + (size_t)kb * kABytes, &p.bmap, &full_bar[kb], kb * 64, n0);
+      }
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_sdesc(sA0 + (uint32_t)s * kABytes);
+        const uint64_t bdesc = make_sdesc(sB0 + (uint32_t)s * kABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+      if (kb + nst < kblocks) {                                // refill this stage with k-block kb + nst once its MMAs retired
+        mbar_wait(&empty_bar[s], ph);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], 2 * kABytes);
+          tma_load_4d(sA + (size_t)s * kABytes, &p.amap[p.tap_map[0]], &full_bar[s], (kb + nst) * 64, ax, ay, img);
+          tma_load_2d(sB + (size_t)s * kABytes, &p.bmap, &full_bar[s], (kb + nst) * 64, n0);
+        }
+        __syncwarp();
+      }
+      if (++s == nst) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(tfull_bar);
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: warps 1..4 <-> TMEM lane quadrants (warp & 3)
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const uint32_t stage_a = smem_u32(s_stage);
+    if (p.res_tma) mbar_wait(rfull_bar, 0);
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < kSmallN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_base + (uint32_t)(c * 32), v);
+      const uint32_t srow = stage_a + (uint32_t)(c >> 1) * 16384u + (uint32_t)row * 128u;
+      uint4 rc[4];
+      if (p.res_tma) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rc[j] = lds128(srow + (uint32_t)((((c & 1) * 4 + j) ^ (row & 7)) * 16));
+      }
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(b4 + j);
+          fadd2(f[4 * j], f[4 * j + 1], b.x, b.y);
+          fadd2(f[4 * j + 2], f[4 * j + 3], b.z, b.w);
+        }
+      }
+      if (p.res_tma) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2* hh = reinterpret_cast<const __half2*>(&rc[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a = __half22float2(hh[e]);
+            fadd2(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1], a.x, a.y);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        uint32_t* ho = reinterpret_cast<uint32_t*>(&o);
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ho[e] = pack_f16x2_relu(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ho[e] = pack_f16x2(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1]);
+        }
+        sts128(srow + (uint32_t)((((c & 1) * 4 + j) ^ (row & 7)) * 16), o);
+      }
+    }
+    fence_async_smem();                                        // generic-proxy writes -> visible to the TMA store
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 1 && elect_one()) {
+      tma_store_4d(&p.omap[0], s_stage, n0, x0, y0, img);
+      tma_store_4d(&p.omap[0], s_stage + 16384, n0 + 64, x0, y0, img);
+      bulk_commit();
+      bulk_wait_read<0>();                                     // the staging tile must outlive the stores' read-out
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)kSmallN);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -997,6 +1175,7 @@ struct smb_conv_plan {
   int omap_ok;                    // output tensor maps encoded (fp16 output, Cout % 64 == 0)
   int rmap_ok;                    // residual tensor maps encoded (same-shape fp16 residual)
   const void* rmap_ptr;           // single-level plans: residual pointer rmap[0] is currently encoded for (lazy, smb_conv_run)
+  int small;                      // 1: conv1x1_small_kernel (one 128 x 128 tile per CTA), else the persistent conv_gemm_kernel
 };
 
 static int g_min_tiles = 48;
@@ -1029,6 +1208,38 @@ static void choose_patch(int H, int W, int* BH, int* BW) {
 
 static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weight) {
   ConvParams& p = pl->p;
+  pl->small = 0;
+  {
+    // short-K 1x1 convolutions (K <= 256, fp16 TMA-storable output, no GroupNorm statistics, same-shape residual or none):
+    // one tile per CTA, several CTAs per SM (conv1x1_small_kernel)
+    const char* envs = getenv("SMB_CONV_SMALL");
+    const int want = envs ? atoi(envs) : 1;
+    const int kb = Ktotal / 64;
+    if (want && p.num_levels == 1 && p.num_taps == 1 && kb >= 1 && kb <= 4 && Cout % kSmallN == 0 && pl->omap_ok && !p.out_f32 &&
+        p.gn_group == 0 && (p.res_mode == 0 || (p.res_mode == 1 && pl->rmap_ok)) && !getenv("SMB_CONV_DEBUG")) {
+      pl->small = 1;
+      p.n_tile = kSmallN;
+      p.n_tiles_n = Cout / kSmallN;
+      p.num_acc = 1;
+      p.tmem_cols = kSmallN;
+      p.pair = 0;
+      p.cluster = 1;
+      p.debug_mode = 0;
+      p.out_tma = 1;
+      p.res_tma = (p.res_mode == 1) ? 1 : 0;
+      p.stage_slots = 2;
+      p.store_lag = 1;
+      p.stages = kb < 2 ? kb : 2;
+      pl->smem_bytes = (size_t)p.stages * 2 * kABytes + 2 * 16384 + 256 + 1024;
+      uint64_t dims[2] = {(uint64_t)Ktotal, (uint64_t)Cout};
+      uint64_t strides[1] = {(uint64_t)Ktotal * 2};
+      uint32_t box[2] = {64, (uint32_t)kSmallN};
+      const int rc = encode_map(&p.bmap, const_cast<void*>(weight), 2, dims, strides, box);
+      if (rc) return rc;
+      pl->grid = p.tiles_m * p.n_tiles_n;
+      return SMB_OK;
+    }
+  }
   // N tile: the largest of {Cout (<=256, rounded to 16) | 256, 128, 64} that still yields >= ~one wave of tiles.
   // Small feature maps (few M tiles) are latency-bound per tile, so they are split along N to occupy more SMs.
   int cand[3], nc = 0;
@@ -1345,6 +1556,7 @@ extern "C" void smb_conv_plan_destroy(smb_conv_plan_t* plan) { delete plan; }
 // can run side by side and fill each other's partial waves.
 extern "C" int smb_conv_plan_set_max_ctas(smb_conv_plan_t* plan, int max_ctas) {
   SMB_CHECK_ARG(plan && max_ctas >= 1, "smb_conv_plan_set_max_ctas: bad argument");
+  if (plan->small) return SMB_OK;                   // one tile per CTA: the grid is the tile count
   const int c = plan->p.cluster;
   int g = (max_ctas / c) * c;
   if (g < c) g = c;
@@ -1383,6 +1595,7 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
     }
   }
   p.alpha = alpha;
+  SMB_CHECK_ARG(!plan->small || alpha == 1.0f, "smb_conv_run: the short-K 1x1 plan does not scale its output (alpha must be 1)");
   {
     const char* ets = getenv("SMB_CONV_TS");      // hex device address of a 16 x int64 buffer (profiling only)
     p.dbg_ts = ets ? (long long*)strtoull(ets, nullptr, 16) : nullptr;
@@ -1391,11 +1604,12 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
   if (attr_once.first()) {
     SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SMB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(conv1x1_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(plan->grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(plan->small ? kSmallThreads : kThreads);
   cfg.dynamicSmemBytes = plan->smem_bytes;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[2];
@@ -1413,7 +1627,9 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
     cfg.numAttrs = 2;
   }
   {
-    cudaError_t e = p.pair ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p) : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, p);
+    cudaError_t e = plan->small ? cudaLaunchKernelEx(&cfg, conv1x1_small_kernel, p)
+                    : p.pair  ? cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, p)
+                              : cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, p);
     if (e != cudaSuccess) {
       set_error("conv_gemm_kernel launch failed: %s (grid=%d cluster=%d pair=%d smem=%zu n_tile=%d stages=%d tiles_m=%d n_tiles_n=%d)",
                 cudaGetErrorString(e), plan->grid, p.cluster, p.pair, plan->smem_bytes, p.n_tile, p.stages, p.tiles_m, p.n_tiles_n);
