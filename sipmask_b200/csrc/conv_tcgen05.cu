@@ -1212,8 +1212,10 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
   {
     // short-K 1x1 convolutions (K <= 256, fp16 TMA-storable output, no GroupNorm statistics, same-shape residual or none):
     // one tile per CTA, several CTAs per SM (conv1x1_small_kernel)
+    // Measured (profiles/r02_conv_times_small1x1_*.txt): not faster than the persistent kernel - layer1.conv3 19.7 us with
+    // either - so it is OFF by default (SMB_CONV_SMALL=1 selects it; tests/test_gpu_conv.py keeps it validated).
     const char* envs = getenv("SMB_CONV_SMALL");
-    const int want = envs ? atoi(envs) : 1;
+    const int want = envs ? atoi(envs) : 0;
     const int kb = Ktotal / 64;
     if (want && p.num_levels == 1 && p.num_taps == 1 && kb >= 1 && kb <= 4 && Cout % kSmallN == 0 && pl->omap_ok && !p.out_f32 &&
         p.gn_group == 0 && (p.res_mode == 0 || (p.res_mode == 1 && pl->rmap_ok)) && !getenv("SMB_CONV_DEBUG")) {

@@ -271,3 +271,27 @@ def test_multi_level_conv_and_helpers_match_single_level():
         assert torch.equal(o1, offs[i]), i
         # the batched kernel evaluates the four bilinear terms in one expression (different FMA contraction): fp16-ulp level
         assert (c1.float() - cols[i].float()).abs().max().item() <= 2e-3 * (c1.float().abs().max().item() + 1), i
+
+
+@pytest.mark.parametrize('H,W,cin,cout,stride,res', [(200, 336, 64, 256, 1, True), (50, 84, 256, 512, 2, False),
+                                                     (13, 21, 256, 2048, 1, True), (8, 160, 128, 256, 1, False)])
+def test_small_1x1_kernel_matches_persistent_kernel(H, W, cin, cout, stride, res, monkeypatch):
+    """conv1x1_small_kernel (one 128 x 128 tile per CTA, 2-3 CTAs per SM; SMB_CONV_SMALL=1) is an alternative execution of the
+    short-K 1x1 convolutions: bit-identical to the persistent kernel (same MMA order over K, same epilogue arithmetic)."""
+    from sipmask_b200 import conv
+    g = torch.Generator().manual_seed(H + cout)
+    x = _nhwc(torch.randn(1, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, 1, 1, generator=g) / (cin ** 0.5)
+    wk, _ = conv.pack_weight(w, device='cuda')
+    bias = torch.randn(cout, generator=g).cuda()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    r = _nhwc(torch.randn(1, cout, Ho, Wo, generator=g)) if res else None
+    outs = []
+    for small in ('0', '1'):
+        monkeypatch.setenv('SMB_CONV_SMALL', small)
+        out = torch.zeros((1, Ho, Wo, cout), dtype=torch.float16, device='cuda')
+        conv.ConvPlan(x, wk, out, 1, stride, relu=True, bias=bias, residual=r).run()
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    _check(outs[1], _ref_conv(x, wk, 1, stride, bias=bias, residual=r, relu=True))
