@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libsipmask_b200.so')
+# SMB_LIB_PATH: an instrumented build of the same sources (tools/build_trace_lib.sh), for profiling tools only
+LIB_PATH = os.environ.get('SMB_LIB_PATH') or os.path.join(HERE, 'lib', 'libsipmask_b200.so')
 
 F32, F16 = 0, 1
 

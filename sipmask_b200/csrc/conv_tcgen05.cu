@@ -60,6 +60,7 @@ struct ConvParams {
   int Cout, n_tile, n_tiles_n, stages, tmem_cols, num_acc;
   int cluster;                    // CTAs per cluster sharing (multicasting) the weight tile: 1, 2 or 4
   long long* dbg_ts;              // profiling only: clock64 stamps of CTA 0 (SMB_CONV_TS buffer), else null
+  int epi_split;                  // 1: the two epilogue warp groups work on different 64-channel chunks (epilogue_split)
   int debug_mode;                 // profiling only (SMB_CONV_DEBUG): 1 = no MMAs (TMA pipeline only), 2 = no TMA (MMA only)
   int pair;                       // 1: tcgen05 cta_group::2 - two CTAs (SMs) compute one 256 x N tile, each holding half of B
   int out_pitch; int out_f32; int out_tma; int res_tma;
@@ -327,6 +328,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_wait32x2(uint32_t* a, uint32_t* b) {
+  // one tcgen05.wait::ld for two prefetched 32-column loads; the "+r" operands pin every consumer of a[] / b[] below it
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]),
+                 "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]),
+                 "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]),
+                 "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]), "+r"(b[16]),
+                 "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]), "+r"(b[24]),
+                 "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+               :
+               : "memory");
+}
+
 
 // work unit -> tile.  A unit is a group of `cluster` consecutive M-tiles that share one N-tile (their CTAs multicast the
 // weight tile to each other); units of the same M-group with different N-tiles are adjacent so concurrently running
@@ -373,6 +392,124 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int unit, 
   return t;
 }
 
+#ifdef SMB_TRACE   // per-role, per-tile clock64 trace of CTA 0 (tools/conv_trace.py; tools/build_trace_lib.sh builds with -DSMB_TRACE)
+#define TR(role, t, e) do { if (p.dbg_ts && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (t) < 16) \
+    p.dbg_ts[64 + (role) * 64 + (int)(t) * 4 + (e)] = clock64(); } while (0)
+#else
+#define TR(role, t, e) do { } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Split-group epilogue (TMA-store plans with bias, no GroupNorm, alpha == 1; residual none or TMA-staged).
+//
+// Measured (profiles/r02_conv_trace_*.txt, tools/conv_trace.py): on the short-K plans the tile period IS the epilogue - the
+// TMA/MMA main loop alone runs at 0.7 us per 128 x 256 tile, the lockstep epilogue at 3.0-3.7 us - and a 64-channel chunk
+// costs ~1300 cycles of which ~470 are the bare slot-wait / arrive skeleton: a serial chain of latencies (wait -> LDS ->
+// tcgen05.wait::ld -> adds -> STS -> MEMBAR -> arrive) that the eight warps execute simultaneously, so nothing overlaps.
+// Here the two warp groups (warps 2-5, 6-9: each covers the four TMEM lane quadrants) take ALTERNATE chunks: a warp drains
+// all 64 channels of its 32 rows, and the chains of chunk g and chunk g+1 run concurrently.  The staging-ring protocol with
+// the store warp is unchanged except that a slot is complete after 4 warp arrivals.
+template <bool kPair, bool kRes, bool kRelu>
+__device__ __forceinline__ void epilogue_split(const ConvParams& p, int cluster_id, int num_clusters, int total_units, int crank,
+                                               uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t stage_a,
+                                               uint32_t rfull_a, uint32_t sfull_a, uint32_t sfree_a, int warp, int lane) {
+  const int lane_grp = warp & 3, grp = (warp - 2) >> 2;
+  const int row = lane_grp * 32 + lane;
+  const int nch = p.n_tile >> 6, nslots = p.stage_slots, n_tile = p.n_tile, n_tiles_n = p.n_tiles_n;
+  const float* __restrict__ bias = p.bias;
+  uint32_t soff[8];                                  // this thread's row, 16-byte pieces in swizzled order
+#pragma unroll
+  for (int q = 0; q < 8; ++q) soff[q] = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) * 16);
+  int acc = 0;
+  uint32_t acc_ph = 0;
+  int g0 = 0;                                        // chunk counter of this CTA at the start of the tile,
+  int slot0 = 0;                                     // its ring slot and the slot's use parity
+  uint32_t ph0 = 0;
+  for (int unit = cluster_id; unit < total_units; unit += num_clusters, g0 += nch) {
+    int nt = 0;
+    if (n_tiles_n > 1) { int um = fast_divmod(unit, n_tiles_n, nt); (void)um; }
+    const float* btile = bias + nt * n_tile;
+    if (warp == 2) TR(2, g0 / nch, 0);
+    mbar_wait(&tfull_bar[acc], acc_ph);
+    if (warp == 2) TR(2, g0 / nch, 1);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * n_tile);
+#pragma unroll 1
+    for (int c64 = (g0 + grp) & 1 ? 1 : 0; c64 < nch; c64 += 2) {
+      // chunks alternate between the groups over the CTA's whole chunk sequence: with an odd nch (1) the tiles alternate
+      int slot = slot0 + c64;                          // nch <= nslots: at most one wrap
+      uint32_t slot_ph = ph0;
+      if (slot >= nslots) { slot -= nslots; slot_ph ^= 1u; }
+      const uint32_t sbase = stage_a + (uint32_t)slot * 16384u;
+      uint32_t va[32], vb[32];
+      tmem_ld32(t_base + (uint32_t)(c64 * 64), va);
+      tmem_ld32(t_base + (uint32_t)(c64 * 64 + 32), vb);
+      const float4* b4 = reinterpret_cast<const float4*>(btile + c64 * 64);
+      float4 bq[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bq[q] = __ldg(b4 + q);
+      uint4 r[8];
+      if (kRes) {
+        mbar_wait_a(rfull_a + (uint32_t)slot * 8u, slot_ph);           // residual landed (and the slot's last store read out)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = lds128(sbase + soff[q]);
+      } else {
+        mbar_wait_a(sfree_a + (uint32_t)slot * 8u, slot_ph ^ 1u);      // the slot's previous TMA store has been read out
+      }
+      tmem_ld_wait32x2(va, vb);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t* v = h ? vb : va;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (h == 1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bq[q] = __ldg(b4 + 8 + q);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          fadd2(f[4 * q], f[4 * q + 1], bq[q].x, bq[q].y);
+          fadd2(f[4 * q + 2], f[4 * q + 3], bq[q].z, bq[q].w);
+        }
+        if (kRes) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __half2* hh = reinterpret_cast<const __half2*>(&r[h * 4 + q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = __half22float2(hh[e]);
+              fadd2(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1], a.x, a.y);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          uint32_t* ho = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            ho[e] = kRelu ? pack_f16x2_relu(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]) : pack_f16x2(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+          sts128(sbase + soff[h * 4 + q], o);
+        }
+      }
+      fence_async_smem();                              // generic-proxy writes -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(sfull_a + (uint32_t)slot * 8u);       // 4 warps -> the store warp ships the slot
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      else mbar_arrive(&tempty_bar[acc]);
+    }
+    if (warp == 2) TR(2, g0 / nch, 2);
+    if (++acc == p.num_acc) { acc = 0; acc_ph ^= 1; }
+    slot0 += nch;
+    if (slot0 >= nslots) { slot0 -= nslots; ph0 ^= 1u; }
+  }
+}
+
 // kPair = true: tcgen05 cta_group::2 instantiation (must be launched with 2-CTA clusters); false: single-CTA MMA.
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
@@ -412,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], (uint32_t)p.cluster); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     }
-    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&sfull_bar[i], 8); mbar_init(&sfree_bar[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&rfull_bar[i], 1); mbar_init(&sfull_bar[i], p.epi_split ? 4 : 8); mbar_init(&sfree_bar[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -447,7 +584,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const int b_part = b_bytes / p.cluster, n_part = p.n_tile / p.cluster;
       const uint32_t lbar0 = kPair ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0u;     // leader's full_bar[0] (pair mode)
       const int nstages = p.stages, kb_per_tap = p.kb_per_tap, num_taps = p.num_taps;
-      for (int unit = cluster_id; unit < total_units; unit += num_clusters) {
+      int plt = 0;
+      for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++plt) {
         const TileCoord tc = decode_tile(p, unit, crank);
         const int map0 = p.lv[tc.lvl].map0;
         for (int t = 0; t < num_taps; ++t) {
@@ -458,6 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if ((p.debug_mode & 3) != 2) {
               if (first) { TS(2); first = false; }
               mbar_wait(&empty_bar[s], ph ^ 1);    // every CTA of the cluster has finished reading stage s
+              if (t == 0 && kc == 0) TR(0, plt, 0);
               if (elect_one()) {
                 if constexpr (kPair) {
                   // each CTA loads its own 128 x 64 activation tile and its half of the weight tile; all bytes are
@@ -480,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
               }
               __syncwarp();
+              if (t == 0 && kc == 0) TR(0, plt, 1);
             }
             if (++s == nstages) { s = 0; ph ^= 1; }
           }
@@ -499,11 +639,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       for (int unit = cluster_id; unit < total_units; unit += num_clusters, ++lt) {
         if (lt == 0) TS(3);
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);
+        TR(1, lt, 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
         for (int kb = 0; kb < kblocks; ++kb) {
           if ((p.debug_mode & 3) != 2) mbar_wait(&full_bar[s], ph);
           if (lt == 0 && kb == 0) TS(4);
+          if (kb == 0) TR(1, lt, 1);
           tc_fence_after();
           if (elect_one()) {
             if ((p.debug_mode & 3) == 1) {
@@ -531,6 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           else umma_commit(&tfull_bar[acc]);                   // accumulator complete
         }
         __syncwarp();
+        TR(1, lt, 2);
         if (++acc == num_acc) { acc = 0; acc_ph ^= 1; }
       }
     }
@@ -539,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (p.out_tma) {
       const int nch = p.n_tile >> 6, nslots = p.stage_slots;
       const int my_tiles = cluster_id < total_units ? (total_units - cluster_id + num_clusters - 1) / num_clusters : 0;
-      const int total_chunks = my_tiles * nch;
+      const int total_chunks = (p.debug_mode & 256) ? 0 : my_tiles * nch;   // 256: epilogue skips the chunk loop
       // residual request for chunk g (tile g / nch of this CTA, 64-channel chunk g % nch) into slot g % nslots
       auto request_residual = [&](int g) {
         const int t = g / nch, c = g - t * nch;
@@ -561,6 +704,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       TileCoord tc = decode_tile(p, cluster_id, crank);
       for (int g = 0; g < total_chunks; ++g) {
         mbar_wait(&sfull_bar[slot], slot_ph);
+        if (c == 0) TR(3, t, 0);
+        if (c == nch - 1) TR(3, t, 2);
         if (elect_one()) {
           if (tc.active && !(p.debug_mode & 8))
             tma_store_4d(&p.omap[tc.lvl], s_stage + (size_t)slot * 16384, tc.n0 + c * 64, tc.x0, tc.y0, tc.img);
@@ -589,6 +734,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
         __syncwarp();
+        if (c == 0) TR(3, t, 1);
+        if (c == nch - 1) TR(3, t, 3);
         if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
         if (++c == nch) {
           c = 0;
@@ -598,6 +745,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
       if (elect_one()) bulk_wait_read<0>();          // staging slots must outlive their TMA stores
       __syncwarp();
+    }
+  } else if (p.epi_split) {
+    // ===================== epilogue warps (2..9), split groups =====================
+    const uint32_t stage_a = smem_u32(s_stage);
+    const uint32_t rfull_a = smem_u32(rfull_bar), sfull_a = smem_u32(sfull_bar), sfree_a = smem_u32(sfree_bar);
+    if (p.res_tma) {
+      if (p.relu) epilogue_split<kPair, true, true>(p, cluster_id, num_clusters, total_units, crank, tmem_base, tfull_bar, tempty_bar,
+                                                    stage_a, rfull_a, sfull_a, sfree_a, warp, lane);
+      else epilogue_split<kPair, true, false>(p, cluster_id, num_clusters, total_units, crank, tmem_base, tfull_bar, tempty_bar,
+                                              stage_a, rfull_a, sfull_a, sfree_a, warp, lane);
+    } else {
+      if (p.relu) epilogue_split<kPair, false, true>(p, cluster_id, num_clusters, total_units, crank, tmem_base, tfull_bar, tempty_bar,
+                                                     stage_a, rfull_a, sfull_a, sfree_a, warp, lane);
+      else epilogue_split<kPair, false, false>(p, cluster_id, num_clusters, total_units, crank, tmem_base, tfull_bar, tempty_bar,
+                                               stage_a, rfull_a, sfull_a, sfree_a, warp, lane);
     }
   } else {
     // ===================== epilogue warps (2..9) =====================
@@ -634,6 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #define TS3(slot) do { } while (0)
 #endif
       TS2(16);
+      if (warp == 2) TR(2, lt, 0);
       const int bw_shift = 31 - __clz(L.BW);            // BW is a power of two (choose_patch)
       const int iy = row >> bw_shift, ix = row & (L.BW - 1);
       const int x = tc.x0 + ix, y = tc.y0 + iy, n0 = tc.n0;
@@ -673,10 +836,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       TS2(18);
       mbar_wait(&tfull_bar[acc], acc_ph);
       TS2(19);
+      if (warp == 2) TR(2, lt, 1);
       if (lt == 0 && warp == 2 && lane == 0) TS(9);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.n_tile);
-      if (p.out_tma) {
+      if (p.out_tma && (o_dbg & 256)) {
+        // profiling: accumulator released untouched (bare main-loop period)
+      } else if (p.out_tma) {
         // ---------- staged epilogue: TMEM -> registers -> swizzled smem tile (128 px x 64 ch) -> TMA store ----------
         // All 8 warps work on the same 64-channel chunk (warp pair = two 32-channel halves of a lane quadrant); the
         // scattered per-thread 16-byte global stores of the direct path become one coalesced, bounds-clipped TMA store.
@@ -721,6 +887,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               mbar_wait_a(sfree_a + (uint32_t)slot * 8u, slot_ph ^ 1);       // the slot's previous TMA store has been read out
             }
             TS3(20 + 4 * c64);
+            if (warp == 2 && lt == 2) TR(4, c64, 0);
+            if (!(o_dbg & 512)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t* v = h ? vb : va;
@@ -730,6 +898,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 else if (c64 + 1 < nch) tmem_ld16(t_base + (uint32_t)(cc + 64), va);
               }
               if (h == 0) TS3(21 + 4 * c64);
+              if (h == 0 && warp == 2 && lt == 2) TR(4, c64, 1);
+              if (h == 1 && warp == 2 && lt == 2) TR(5, c64, 0);
               float f[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -783,6 +953,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const int chunk = (col_half * 4 + h * 2 + j) ^ (row & 7);
                 if (!(o_dbg & 32)) sts128(srow + (uint32_t)(chunk * 16), o);
               }
+              if (h == 0 && warp == 2 && lt == 2) TR(5, c64, 1);
+            }
             }
             if ((o_flags & 8) && !(o_dbg & 4)) {
               // 32 lanes x 8 partials -> lane j (j < 8) ends up with the warp total of partial j (recursive halving over
@@ -809,10 +981,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               }
             }
             TS3(41);
+            if (warp == 2 && lt == 2) TR(4, c64, 2);
             if (!(o_dbg & 16)) fence_async_smem();         // generic-proxy writes -> visible to the TMA store
+            if (warp == 2 && lt == 2) TR(5, c64, 2);
             __syncwarp();
             if (lane == 0) mbar_arrive_a(sfull_a + (uint32_t)slot * 8u);  // 8 warps -> the store warp ships the slot
             TS3(22 + 4 * c64);
+            if (warp == 2 && lt == 2) TR(4, c64, 3);
             if (++slot == nslots) { slot = 0; slot_ph ^= 1; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) rc[j] = rn[j];
@@ -934,6 +1109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
         else mbar_arrive(&tempty_bar[acc]);
       }
+      if (warp == 2) TR(2, lt, 2);
       if (++acc == p.num_acc) { acc = 0; acc_ph ^= 1; }
     }
   }
@@ -1297,6 +1473,14 @@ static int finish_plan(smb_conv_plan* pl, int Cout, int Ktotal, const void* weig
     if (lag > p.stage_slots - 1) lag = p.stage_slots > 1 ? p.stage_slots - 1 : 1;
     p.store_lag = lag;
   }
+  {
+    // split-group epilogue (epilogue_split): TMA-store plans without GroupNorm statistics whose residual, if any, is
+    // TMA-staged; bias and alpha == 1 are checked at run time.  SMB_CONV_EPI_SPLIT=0 keeps the lockstep epilogue.
+    const char* enve = getenv("SMB_CONV_EPI_SPLIT");
+    const int want = enve ? atoi(enve) : 1;
+    p.epi_split = (want && p.out_tma && p.gn_group == 0 && (p.res_mode == 0 || p.res_tma) && Cout % n_tile == 0 &&
+                   p.stage_slots >= 2 && p.stage_slots >= n_tile / 64 && !(p.debug_mode & ~8)) ? 1 : 0;
+  }
   const size_t budget = 194 * 1024 - stage_out;
   int stages = (int)(budget / stage);
   if (stages > 8) stages = 8;
@@ -1597,6 +1781,7 @@ extern "C" int smb_conv_run(const smb_conv_plan_t* plan, const float* bias, cons
     }
   }
   p.alpha = alpha;
+  if (!plan->has_bias || alpha != 1.0f || ((uintptr_t)bias & 15)) p.epi_split = 0;   // epilogue_split: float4 bias reads, no scaling
   SMB_CHECK_ARG(!plan->small || alpha == 1.0f, "smb_conv_run: the short-K 1x1 plan does not scale its output (alpha must be 1)");
   {
     const char* ets = getenv("SMB_CONV_TS");      // hex device address of a 16 x int64 buffer (profiling only)

@@ -64,7 +64,9 @@ def bench(p):
     return best
 
 
-VARIANTS = [('base', {}), ('no store (DEBUG=8)', {'SMB_CONV_DEBUG': '8'}), ('residual via LDG', {'SMB_CONV_NO_TMA_RES': '1'}),
+VARIANTS = [('base', {}), ('epilogue releases the accumulator untouched (256)', {'SMB_CONV_DEBUG': '256'}),
+            ('chunk loop = wait + arrive only (760)', {'SMB_CONV_DEBUG': '760'}),
+            ('pair mode off', {'SMB_CONV_PAIR': '0'}), ('pair off, chunk loop skipped', {'SMB_CONV_PAIR': '0', 'SMB_CONV_DEBUG': '256'}), ('no store (DEBUG=8)', {'SMB_CONV_DEBUG': '8'}), ('residual via LDG', {'SMB_CONV_NO_TMA_RES': '1'}),
             ('direct STG epilogue', {'SMB_CONV_NO_TMA_STORE': '1'}), ('one staging set', {'SMB_CONV_STAGE_SETS': '1'}),
             ('no store + residual via LDG', {'SMB_CONV_DEBUG': '8', 'SMB_CONV_NO_TMA_RES': '1'}),
             ('no TMEM loads (128)', {'SMB_CONV_DEBUG': '128'}), ('no bias/res math (64)', {'SMB_CONV_DEBUG': '64'}),
@@ -74,6 +76,8 @@ VARIANTS = [('base', {}), ('no store (DEBUG=8)', {'SMB_CONV_DEBUG': '8'}), ('res
             ('store lag 2', {'SMB_CONV_STORE_LAG': '2'}), ('store lag 3', {'SMB_CONV_STORE_LAG': '3'}),
             ('store lag 4', {'SMB_CONV_STORE_LAG': '4'}), ('store lag 4, no store', {'SMB_CONV_STORE_LAG': '4', 'SMB_CONV_DEBUG': '8'}),
             ('store lag 3, residual via LDG', {'SMB_CONV_STORE_LAG': '3', 'SMB_CONV_NO_TMA_RES': '1'})]
+if os.environ.get('SMB_DIAG_QUICK'):
+    VARIANTS = [v for v in VARIANTS if v[0] in ('base', 'no tmem/math/sts/fence/store (248)') or '256' in str(v[1]) or '760' in str(v[1]) or 'pair' in v[0]]
 for res in (True, False):
     for cap in (48, None):
         print('--- layer1 %s, %s' % ('conv3 (+residual, 77 MB)' if res else 'downsample (no residual, 43 MB)', 'cap %d CTAs' % cap if cap else 'uncapped'))
