@@ -295,3 +295,30 @@ def test_small_1x1_kernel_matches_persistent_kernel(H, W, cin, cout, stride, res
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
     _check(outs[1], _ref_conv(x, wk, 1, stride, bias=bias, residual=r, relu=True))
+
+
+@pytest.mark.parametrize('H,W,cin,cout,k,stride,res', [(200, 336, 64, 256, 1, 1, True), (100, 168, 256, 64, 1, 1, False),
+                                                       (50, 84, 256, 512, 1, 2, False), (25, 42, 256, 256, 3, 1, False),
+                                                       (13, 21, 512, 2048, 1, 1, True), (37, 53, 128, 128, 3, 1, False)])
+def test_split_epilogue_matches_lockstep_epilogue(H, W, cin, cout, k, stride, res, monkeypatch):
+    """epilogue_split (the two warp groups drain alternate 64-channel chunks) against the lockstep epilogue of the same kernel
+    (SMB_CONV_EPI_SPLIT=0): the per-element arithmetic (acc + bias, + residual, ReLU, round) is the same sequence, so the
+    outputs are bit-identical."""
+    from sipmask_b200 import conv
+    g = torch.Generator().manual_seed(H * 3 + cout + k)
+    x = _nhwc(torch.randn(1, cin, H, W, generator=g))
+    w = torch.randn(cout, cin, k, k, generator=g) / ((cin * k * k) ** 0.5)
+    wk, _ = conv.pack_weight(w, device='cuda')
+    bias = torch.randn(cout, generator=g).cuda()
+    Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+    r = _nhwc(torch.randn(1, cout, Ho, Wo, generator=g)) if res else None
+    outs = []
+    for split in ('0', '1'):
+        monkeypatch.setenv('SMB_CONV_EPI_SPLIT', split)
+        out = torch.zeros((1, Ho, Wo, cout), dtype=torch.float16, device='cuda')
+        conv.ConvPlan(x, wk, out, k, stride, relu=True, bias=bias, residual=r).run()
+        torch.cuda.synchronize()
+        outs.append(out)
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+    _check(outs[0], _ref_conv(x, wk, k, stride, bias=bias, residual=r, relu=True))
