@@ -335,6 +335,20 @@ def run_ours(args):
         the sampler stays on throughout (clocks.window says so)."""
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
         roll = max(1, ROLL // B)
+        if sample_clocks:
+            # nvidia-smi needs ~0.3 s to start and samples every 100 ms: make each roll last >= 0.8 s of the same load
+            # (short steps - workloads B / C - got no sample with a fixed count); every rank uses the same count
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            if finish is not None:
+                finish()
+            torch.cuda.synchronize()
+            per = max(1e-5, (time.perf_counter() - t0) / 3)
+            need = torch.tensor([max(roll, int(0.8 / per) + 1)], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(need, op=dist.ReduceOp.MAX)
+            roll = int(need.item())
         if sampler:
             sampler.start()
         if sample_clocks:
