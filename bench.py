@@ -530,12 +530,21 @@ def mask_rooflines(line, eng, pk, pk_kind, traffic, H, IMG_W):
         return statistics.median(ts[2:])
 
     protos = eng.protos[0]
+    tensor_dot = ops.set_mask_tensor_dot(None)             # the family the engine runs (fp16 prototypes)
+    fam = 'mma.sync dot products' if tensor_dot else 'scalar fmaf dot products'
+    # the other family, same inputs, for the record
+    ops.set_mask_tensor_dot(not tensor_dot)
+    other = dict(kernels='scalar fmaf' if tensor_dot else 'mma.sync',
+                 dense_ms=time_kernel(lambda: ops.mask_assemble(protos, cofs, boxes, 0.5, layout='hwc', out=pos)),
+                 fused_ms=time_kernel(lambda: ops.mask_assemble_pack(protos, cofs, boxes, 0.5, (H, IMG_W), 0.4, layout='hwc', out=bits)))
+    ops.set_mask_tensor_dot(tensor_dot)
     # (a) the reference-shaped output: dense pos_masks [N,Hm,Wm] fp32 (what CropSplit returns, permuted)
     ma_ms = time_kernel(lambda: ops.mask_assemble(protos, cofs, boxes, 0.5, layout='hwc', out=pos))
     ma_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + N * Hm * Wm * 4
     gbs = ma_bytes / (ma_ms * 1e-3) / 1e9
     tr = traffic.get('mask_assemble', {})
-    line['roofline_mask_assembly'] = dict(bound='hbm', kernel='mask_assemble_kernel (writes every output element; no memset)', achieved=gbs,
+    line['roofline_mask_assembly'] = dict(bound='hbm', kernel='mask_assemble%s_kernel, %s (writes every output element; no memset)'
+                                                              % ('_mma' if tensor_dot else '', fam), achieved=gbs,
                                           peak=float(pk['hbm_gbs']), unit='GB/s', frac=gbs / float(pk['hbm_gbs']),
                                           traffic=tr.get('dram_bytes_per_launch'), traffic_source=tr.get('source'), ms=ma_ms,
                                           algorithmic_bytes=ma_bytes, peak_source=pk_kind + ' hbm_gbs',
@@ -545,11 +554,14 @@ def mask_rooflines(line, eng, pk, pk_kind, traffic, H, IMG_W):
     mf_bytes = Hm * Wm * 32 * 2 + N * 128 * 4 + N * 16 + bits.numel() * 4
     mgbs = mf_bytes / (mf_ms * 1e-3) / 1e9
     tr = traffic.get('mask_fused', {})
-    line['roofline_mask_fused'] = dict(bound='hbm', kernel='smb_mask_assemble_pack = memset + mask_fused_pack_kernel', achieved=mgbs,
+    line['roofline_mask_fused'] = dict(bound='hbm', kernel='smb_mask_assemble_pack = memset + mask_fused_pack%s_kernel, %s'
+                                                           % ('_mma' if tensor_dot else '', fam), achieved=mgbs,
                                        peak=float(pk['hbm_gbs']), unit='GB/s', frac=mgbs / float(pk['hbm_gbs']),
                                        traffic=tr.get('dram_bytes_per_launch'), traffic_source=tr.get('source'), ms=mf_ms,
                                        algorithmic_bytes=mf_bytes, peak_source=pk_kind + ' hbm_gbs',
                                        note='protos fp16 read once + bit-packed [100,800,42] int32 masks written')
+    line['roofline_mask_assembly']['other_family'] = dict(kernels=other['kernels'], ms=other['dense_ms'])
+    line['roofline_mask_fused']['other_family'] = dict(kernels=other['kernels'], ms=other['fused_ms'])
 
 
 def dropin_timing(eng, sd, cfg, H, IMG_W):

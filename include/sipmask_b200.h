@@ -108,6 +108,12 @@ int smb_mask_assemble_pack(const void* protos, int protos_dtype, int layout_hwc,
                            const float* host_box_scale4, uint32_t* out_bits, int H, int W, int N, int full_h, int full_w,
                            float ry, float rx, int out_h, int out_w, float thr, smb_stream_t stream);
 
+/* fp16 prototypes run the tensor-core variants of smb_mask_assemble / smb_mask_assemble_pack (mma.sync dot products with
+ * the fp32 coefficients split into fp16 hi + lo; same crop geometry, mask values within ~1e-6 of the scalar kernels).
+ * on = 1 / 0 selects them / the scalar-fmaf kernels for later calls, on < 0 only queries; returns the previous setting
+ * (initial value: environment SMB_MASK_MMA, else the build default). */
+int smb_mask_set_tensor_dot(int on);
+
 /* ------------------------------------------------------------------ CropSplit (operator API)
  * Replaces crop_split_cuda.crop_split_cuda_forward(data, rois, out, H, W, c, n)
  * (ops/crop/src/crop_split_cuda.cpp:14-36).  data [c*c,H,W,N], rois [N,4], out [H,W,N]; c == 2.

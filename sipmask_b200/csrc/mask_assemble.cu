@@ -10,6 +10,10 @@
 // HBM-bound: algorithmic bytes = protos (H*W*32*sizeof) + out (N*H*W*sizeof).
 #include "common.cuh"
 
+#ifndef SMB_MASK_MMA_DEFAULT
+#define SMB_MASK_MMA_DEFAULT 0
+#endif
+
 namespace smb {
 
 struct __align__(16) BoxP {
@@ -465,6 +469,417 @@ __global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core variants of the two kernels above for fp16 prototypes (the engine's storage type).
+//
+// The 32-term dot products are evaluated by mma.sync.m16n8k16 (fp16 x fp16 -> fp32):
+//   A  = 16 staged prototype pixels x 16 channels, read from the swizzled shared-memory window (two k-steps cover the 32
+//        channels); row g / g + 8 of the fragment = pixel g / g + 8 of a 16-pixel run of one window row,
+//   B  = 16 channels x 8 columns; column n = (detection slot n >> 1 of a group of FOUR listed detections, idx_w = n & 1):
+//        the coefficients of CropSplit cell 2 * idx_h + idx_w, where idx_h is the half of the roi the pixel ROW lies in
+//        (uniform along a row, so each B column is chosen per (detection, row) by the lanes that own it),
+//   D  = for every pixel the logits of both idx_w halves of four detections; the epilogue keeps the one the pixel's own
+//        cell selects, applies the sigmoid and the crop.
+// The fp32 coefficients enter as fp16 hi + fp16 lo (c = hi + lo to 22 mantissa bits; two MMAs into one accumulator), the
+// prototypes are fp16 already, products and accumulation are fp32: the logit agrees with the sequential-fmaf kernels to
+// ~1e-6 relative; the geometry (which pixels are inside, which cell) is computed exactly as before.
+// Scalar kernels: ~140 instructions per in-box pixel and detection; here ~75 per 16 pixels x 4 detections.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void mma_f16f32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// A fragments (both k-steps) of window pixels p0 (fragment row g) and p0 + 8 (row g + 8).
+// Register layout of m16n8k16: a0 = (row g, k 2t..2t+1), a1 = (row g+8, same k), a2 = (row g, k 2t+8..2t+9), a3 = (row g+8, ..);
+// channel 16 * ks + 2t lives in 16-byte chunk 2 * ks at byte 4t, channel 16 * ks + 8 + 2t in chunk 2 * ks + 1 at byte 4t.
+// `addr` = shared-window address of pixel p0 plus 4t, `sw` = swizzle key (p0 >> 1) & 3 of stage_window (chunk k sits at
+// position k ^ sw; pixel p0 + 8 has the same key, 512 bytes further on).
+__device__ __forceinline__ void load_a_frag(uint32_t addr, int sw, uint32_t (&a)[2][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint32_t lo = addr + (((2 * ks) ^ sw) << 4), hi = addr + (((2 * ks + 1) ^ sw) << 4);
+    a[ks][0] = lds_u32(lo);
+    a[ks][1] = lds_u32(lo + 512);
+    a[ks][2] = lds_u32(hi);
+    a[ks][3] = lds_u32(hi + 512);
+  }
+}
+
+// B fragments of column n = g: cof32 = the 32 fp32 coefficients of (detection, cell); b0 = (k 2t..2t+1, n), b1 = (k 2t+8..2t+9, n).
+// hi = fp16(c), lo = fp16(c - hi); |c| is clamped to the fp16 range first (a coefficient beyond 6e4 saturates the sigmoid
+// through any non-zero prototype anyway).
+__device__ __forceinline__ void load_b_frag(const float* __restrict__ cof32, int t, bool valid, uint32_t (&bh)[2][2], uint32_t (&bl)[2][2]) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float2 v = make_float2(0.f, 0.f);
+      if (valid) v = __ldg(reinterpret_cast<const float2*>(cof32 + ks * 16 + h * 8 + 2 * t));
+      v.x = fminf(fmaxf(v.x, -65000.f), 65000.f);
+      v.y = fminf(fmaxf(v.y, -65000.f), 65000.f);
+      const __half2 hi = __floats2half2_rn(v.x, v.y);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn(v.x - hf.x, v.y - hf.y);
+      bh[ks][h] = *reinterpret_cast<const uint32_t*>(&hi);
+      bl[ks][h] = *reinterpret_cast<const uint32_t*>(&lo);
+    }
+  }
+}
+
+// sigmoid for the tensor-core kernels: ex2.approx + rcp.approx (4 instructions, |error| < 3e-7; the IEEE division of
+// sigmoidf_ is ~12).  ex2 overflow -> rcp(inf) = 0, underflow -> rcp(1) = 1: the limits are right without special cases.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+
+// (int)(a / b) of crop_split_cuda_kernel.cu:50-51 for a >= 0, b > 0.  IEEE division rounds to nearest; a < b implies
+// a <= pred(b) and pred(b) / b <= 1 - 2^-24, which rounds below 1: the truncated quotient is >= 1 exactly when a >= b
+// (and >= 2 exactly when a >= 2b, 2b being exact).  The kernels below use idx = (a >= b) inline and send a >= 2b - only
+// reachable by rounding, the roi is two cells wide - to the generic path.
+__device__ __forceinline__ int crop_idx(float a, float b) {
+  return a >= b + b ? (int)__fdiv_rn(a, b) : (a >= b ? 1 : 0);
+}
+
+// Generic (cold, out of line) value of window pixel p at image position (wf, hf): the scalar kernel's arithmetic.
+__device__ __noinline__ float pixel_value_cold(const unsigned char* s_p, int p, float wf, float hf, const BoxP* bp,
+                                               const float* __restrict__ cof128) {
+  const BoxP b = *bp;
+  if (!((hf >= b.y1) & (hf < b.y2) & (wf >= b.x1) & (wf < b.x2))) return 0.f;
+  const int cell = min(max(crop_idx(hf - b.y1, b.roi_h) * 2 + crop_idx(wf - b.x1, b.roi_w), 0), 3);
+  return sigmoid_fast(dot32_swz<__half>(s_p, p, cof128 + cell * 32));
+}
+
+// Epilogue of one 16-pixel run for the detection whose accumulators this thread holds: acc[0] / acc[1] = pixel c0 (fragment
+// row g), idx_w 0 / 1; acc[2] / acc[3] = pixel c0 + 8.  Straight-line and predicated; the never-in-practice cases (a
+// quotient of 2) are recomputed out of line.
+struct RowSel {
+  bool row_in;      // row inside [y1, y2) of a valid detection
+  bool rare;        // row_in and idx_h >= 2
+  float x0f;        // image x of window column 0
+};
+__device__ __forceinline__ void run_values(const float (&acc)[4], const BoxP& b, const RowSel& rs, int c0, float& v0, float& v1,
+                                           bool& rare) {
+  const float roi_w2 = b.roi_w + b.roi_w;
+  const float w0 = rs.x0f + (float)c0, w1 = w0 + 8.f;                 // exact: small integers
+  const float a0 = w0 - b.x1, a1 = w1 - b.x1;
+  const bool in0 = rs.row_in & (w0 >= b.x1) & (w0 < b.x2), in1 = rs.row_in & (w1 >= b.x1) & (w1 < b.x2);
+  const float s0 = a0 >= b.roi_w ? acc[1] : acc[0], s1 = a1 >= b.roi_w ? acc[3] : acc[2];
+  v0 = in0 ? sigmoid_fast(s0) : 0.f;
+  v1 = in1 ? sigmoid_fast(s1) : 0.f;
+  rare = rs.rare | (in0 & (a0 >= roi_w2)) | (in1 & (a1 >= roi_w2));
+}
+
+// Dense pos_masks, tensor-core dots.  Same tiling / listing / zero-fill as mask_assemble_kernel; a warp owns one tile row
+// (its A fragments are re-read from shared memory per 16-pixel run and group: 8 LDS.32 against ~70 other instructions;
+// keeping the row's 32 fragment registers live cost a CTA per SM).
+template <bool HWC, typename OT>
+__global__ void __launch_bounds__(MA_THREADS2) mask_assemble_mma_kernel(
+    const __half* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes,
+    float sx1, float sy1, float sx2, float sy2, OT* __restrict__ out, int H, int W, int N) {
+  extern __shared__ __align__(16) unsigned char s_p[];        // [MA_TH * MA_TW] swizzled pixels (32 KB)
+  __shared__ BoxP s_box[MA_LIST];
+  __shared__ int s_det[MA_LIST];
+  __shared__ int s_cnt;
+  __shared__ unsigned s_listed[MA_LIST / 32];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int y0t = blockIdx.y * MA_TH, x0t = blockIdx.x * MA_TW;
+  const int SRa = min(MA_TH, H - y0t), SCa = min(MA_TW, W - x0t);
+  stage_window<__half, HWC>(protos, s_p, H, W, y0t, x0t, SRa, SCa, MA_THREADS2);
+  const int h = y0t + warp;
+  const bool row_ok = warp < SRa;
+  const float hf = (float)h;
+  const float tile_x0 = (float)x0t, tile_x1 = (float)(x0t + SCa - 1), tile_y0 = (float)y0t, tile_y1 = (float)(y0t + SRa - 1);
+  const int zr = threadIdx.x >> 4, zc = (threadIdx.x & 15) * 4;
+  const bool z_vec = threadIdx.x < 128 && zr < SRa && zc + 3 < SCa && ((W & 3) == 0);
+  const bool z_tail = threadIdx.x < 128 && zr < SRa && !z_vec && zc < SCa;
+  const int MT = (SCa + 15) >> 4;                           // 16-pixel runs of a tile row (the last one may be partial:
+                                                            // its surplus rows read the next row's pixels and are discarded)
+  // fragment row g of run 0 of this warp's row: pixel p_row (run m adds 16 pixels = 1024 bytes, same swizzle key)
+  const int p_row = warp * SCa + g;
+  const uint32_t a_row = smem_addr(s_p) + (uint32_t)p_row * 64 + 4 * t;
+  const int a_sw = (p_row >> 1) & 3;
+
+  for (int n0 = 0; n0 < N; n0 += MA_LIST) {
+    const int nb = min(MA_LIST, N - n0);
+    __syncthreads();                                   // window staged / previous pass done with the list
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    bool mine_listed = false;
+    if (threadIdx.x < nb) {
+      const float* b = boxes + (size_t)(n0 + threadIdx.x) * 4;
+      BoxP bp;
+      bp.x1 = b[0] * sx1; bp.y1 = b[1] * sy1; bp.x2 = b[2] * sx2; bp.y2 = b[3] * sy2;
+      if (tile_x1 >= bp.x1 && tile_x0 < bp.x2 && tile_y1 >= bp.y1 && tile_y0 < bp.y2) {
+        bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
+        bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
+        bp.pad0 = bp.pad1 = 0.f;
+        const int pos = atomicAdd(&s_cnt, 1);
+        s_box[pos] = bp;
+        s_det[pos] = n0 + threadIdx.x;
+        mine_listed = true;
+      }
+    }
+    {
+      const unsigned bal = __ballot_sync(0xffffffffu, mine_listed);
+      if (lane == 0 && warp < MA_LIST / 32) s_listed[warp] = bal;
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    // ---- detections whose roi misses the tile: zeros (16 bytes per thread, 8 rows x 256 B per detection)
+    if (z_vec | z_tail) {
+      for (int j = 0; j < nb; ++j) {
+        if ((s_listed[j >> 5] >> (j & 31)) & 1u) continue;
+        OT* dst = out + ((size_t)(n0 + j) * H + (y0t + zr)) * W + x0t + zc;
+        if (z_vec) {
+          store_zero4<OT>(dst);
+        } else {
+          for (int e = 0; e < 4 && zc + e < SCa; ++e) store1<OT>(dst + e, 0.f);
+        }
+      }
+    }
+    if (!row_ok) continue;                               // warp-uniform
+    // ---- listed detections, four at a time: every pixel of the tile row is written (value inside the roi, 0 outside)
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      // B side: this lane feeds column n = g: detection slot g >> 1, idx_w = g & 1, row half of THIS row in that roi
+      uint32_t bh[2][2], bl[2][2];
+      {
+        const int jb = j0 + (g >> 1);
+        const bool vb = jb < cnt;
+        const int js = vb ? jb : j0;
+        const int hb = (hf - s_box[js].y1 >= s_box[js].roi_h) ? 1 : 0;          // min(idx_h, 1)
+        load_b_frag(cofs + (size_t)s_det[js] * 128 + (hb * 2 + (g & 1)) * 32, t, vb, bh, bl);
+      }
+      // C side: accumulator columns 2t, 2t+1 = detection slot t, idx_w 0 / 1
+      const int jc = j0 + t;
+      const bool vc = jc < cnt;
+      const int js = vc ? jc : j0;
+      const BoxP b = s_box[js];
+      const int n = s_det[js];
+      RowSel rsel;
+      rsel.row_in = vc & (hf >= b.y1) & (hf < b.y2);
+      rsel.rare = rsel.row_in & (hf - b.y1 >= b.roi_h + b.roi_h);
+      rsel.x0f = tile_x0;
+      OT* dst = out + ((size_t)n * H + h) * W + x0t + g;
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const float run_x0 = tile_x0 + (float)(m * 16), run_x1 = run_x0 + 15.f;
+        const bool any_in = __any_sync(0xffffffffu, rsel.row_in & (run_x1 >= b.x1) & (run_x0 < b.x2));
+        const int c0 = m * 16 + g;
+        float v0 = 0.f, v1 = 0.f;
+        if (any_in) {                                      // warp-uniform: the MMAs are executed by all 32 lanes
+          uint32_t a[2][4];
+          load_a_frag(a_row + m * 1024, a_sw, a);
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            mma_f16f32(acc, a[ks], bh[ks]);
+            mma_f16f32(acc, a[ks], bl[ks]);
+          }
+          bool rare;
+          run_values(acc, b, rsel, c0, v0, v1, rare);
+          if (rare) {
+            v0 = pixel_value_cold(s_p, p_row + m * 16, tile_x0 + (float)c0, hf, &s_box[js], cofs + (size_t)n * 128);
+            v1 = pixel_value_cold(s_p, p_row + m * 16 + 8, tile_x0 + (float)(c0 + 8), hf, &s_box[js], cofs + (size_t)n * 128);
+          }
+        }
+        if (vc) {
+          if (c0 < SCa) store1<OT>(dst + m * 16, v0);
+          if (c0 + 8 < SCa) store1<OT>(dst + m * 16 + 8, v1);
+        }
+      }
+    }
+  }
+}
+
+// Fused resize + threshold + bit-pack, tensor-core dots.  Same tiling / listing / phase 2 as mask_fused_pack_kernel; the
+// listed detections are processed FOUR at a time: phase 1 walks (window row, 16-pixel run) units round-robin over the
+// warps (the scalar kernel gave each warp whole rows: 10 rows on 8 warps, 66 columns on 32 lanes) and writes four value
+// tiles, phase 2 packs them; two barriers per group of four instead of one per detection.
+template <bool HWC>
+__global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_mma_kernel(
+    const __half* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes, float sx1, float sy1,
+    float sx2, float sy2, uint32_t* __restrict__ out, int H, int W, int N, int out_h, int out_w, int words, Resize rs,
+    int TY, int TW, int win_cap, float thr) {
+  extern __shared__ __align__(16) unsigned char mf_smem[];
+  unsigned char* s_p = mf_smem;                                                        // [win_cap] swizzled pixels
+  float* s_val = reinterpret_cast<float*>(mf_smem + (size_t)win_cap * 64);              // [4][win_cap]
+  BoxP* s_box = reinterpret_cast<BoxP*>(s_val + 4 * win_cap);                          // [MF_LIST]
+  RowC* s_row = reinterpret_cast<RowC*>(s_box + MF_LIST);                              // [MF_TY_MAX]
+  int* s_det = reinterpret_cast<int*>(s_row + MF_TY_MAX);                              // [MF_LIST]
+  int* s_cnt = s_det + MF_LIST;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int y_first = blockIdx.y * TY, wq_first = blockIdx.x * TW;
+  const int vh = min(out_h, rs.full_h), vw = min(out_w, rs.full_w);
+  const int y_last = min(y_first + TY, vh) - 1;
+  const int x_first = wq_first * 32, x_last = min(x_first + TW * 32, vw) - 1;
+  if (y_last < y_first || x_last < x_first) return;
+  int ys0, ys1, xs0, xs1, t0, t1;
+  float tl;
+  src_index(rs.ry, y_first, H, ys0, t1, tl);
+  src_index(rs.ry, y_last, H, t0, ys1, tl);
+  src_index(rs.rx, x_first, W, xs0, t1, tl);
+  src_index(rs.rx, x_last, W, t0, xs1, tl);
+  const int SRa = ys1 - ys0 + 1, SCa = xs1 - xs0 + 1;
+  const int MT = (SCa + 15) >> 4, n_units = SRa * MT;       // (window row, 16-pixel run) units; a partial last run reads
+                                                            // the next row's (or the value tiles') bytes and discards them
+
+  stage_window<__half, HWC>(protos, s_p, H, W, ys0, xs0, SRa, SCa, MF_THREADS);
+  if (threadIdx.x <= y_last - y_first) {
+    RowC rc;
+    src_index(rs.ry, y_first + threadIdx.x, H, rc.y0, rc.y1, rc.ly);
+    rc.o0 = (rc.y0 - ys0) * SCa;
+    rc.o1 = (rc.y1 - ys0) * SCa;
+    s_row[threadIdx.x] = rc;
+  }
+
+  const int wcol = warp % TW, rstep = (MF_THREADS / 32) / TW, rfirst = warp / TW;
+  const int x = x_first + wcol * 32 + lane;
+  int cx0, cx1;
+  float lx;
+  {
+    int xa, xb;
+    src_index(rs.rx, min(x, x_last), W, xa, xb, lx);
+    cx0 = xa - xs0; cx1 = xb - xs0;
+  }
+  const float hx = 1.f - lx;
+  const bool x_ok = x <= x_last;
+  const bool word_ok = x_first + wcol * 32 <= x_last;
+  const float wsrc_lo = (float)(xs0 + __shfl_sync(0xffffffffu, cx0, 0));
+  const float wsrc_hi = (float)(xs0 + __shfl_sync(0xffffffffu, cx1, min(31, x_last - (x_first + wcol * 32))));
+  const float win_x0 = (float)xs0, win_x1 = (float)xs1, win_y0 = (float)ys0, win_y1 = (float)ys1;
+  const uint32_t sp_addr = smem_addr(s_p) + 4 * t;
+  // first unit of this warp (units advance by the warp count)
+  const int u_r0 = warp / MT, u_m0 = warp - u_r0 * MT;
+  const int u_dr = (MF_THREADS / 32) / MT, u_dm = (MF_THREADS / 32) - u_dr * MT;
+
+  for (int n0 = 0; n0 < N; n0 += MF_LIST) {
+    const int nb = min(MF_LIST, N - n0);
+    __syncthreads();                                   // window / row table staged; previous pass done with s_box, s_val
+    if (threadIdx.x == 0) *s_cnt = 0;
+    __syncthreads();
+    if (threadIdx.x < nb) {
+      const float* b = boxes + (size_t)(n0 + threadIdx.x) * 4;
+      BoxP bp;
+      bp.x1 = b[0] * sx1; bp.y1 = b[1] * sy1; bp.x2 = b[2] * sx2; bp.y2 = b[3] * sy2;
+      if (win_x1 >= bp.x1 && win_x0 < bp.x2 && win_y1 >= bp.y1 && win_y0 < bp.y2) {
+        bp.roi_w = (float)(((double)(bp.x2 - bp.x1) + 0.1) / 2);
+        bp.roi_h = (float)(((double)(bp.y2 - bp.y1) + 0.1) / 2);
+        bp.pad0 = bp.pad1 = 0.f;
+        const int pos = atomicAdd(s_cnt, 1);
+        s_box[pos] = bp;
+        s_det[pos] = n0 + threadIdx.x;
+      }
+    }
+    __syncthreads();
+    const int cnt = *s_cnt;
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      const int nd = min(4, cnt - j0);
+      // ---- phase 1: value tiles of detections j0 .. j0 + nd - 1 (0 outside the roi)
+      {
+        // B side: column n = g -> detection slot g >> 1, idx_w = g & 1; both row halves, selected per unit
+        uint32_t bh0[2][2], bl0[2][2], bh1[2][2], bl1[2][2];
+        const int jb = j0 + (g >> 1);
+        const bool vb = jb < cnt;
+        const int jsb = vb ? jb : j0;
+        const float bb_y1 = s_box[jsb].y1, bb_roi_h = s_box[jsb].roi_h;
+        {
+          const float* cb = cofs + (size_t)s_det[jsb] * 128 + (g & 1) * 32;
+          load_b_frag(cb, t, vb, bh0, bl0);
+          load_b_frag(cb + 64, t, vb, bh1, bl1);
+        }
+        // C side: detection slot t
+        const int jc = j0 + t;
+        const bool vc = jc < cnt;
+        const int jsc = vc ? jc : j0;
+        const BoxP b = s_box[jsc];
+        const float roi_h2 = b.roi_h + b.roi_h;
+        float* val = s_val + t * win_cap;
+        int r = u_r0, m = u_m0;
+        for (int u = warp; u < n_units; u += MF_THREADS / 32) {
+          const float hf = win_y0 + (float)r;
+          RowSel rsel;
+          rsel.row_in = vc & (hf >= b.y1) & (hf < b.y2);
+          rsel.rare = rsel.row_in & (hf - b.y1 >= roi_h2);
+          rsel.x0f = win_x0;
+          const float run_x0 = win_x0 + (float)(m * 16), run_x1 = run_x0 + 15.f;
+          const bool any_in = __any_sync(0xffffffffu, rsel.row_in & (run_x1 >= b.x1) & (run_x0 < b.x2));
+          const int c0 = m * 16 + g;
+          const int p0 = r * SCa + c0;
+          float v0 = 0.f, v1 = 0.f;
+          if (any_in) {                                    // warp-uniform
+            const bool hb = (hf - bb_y1) >= bb_roi_h;      // row half of this row in the roi of the B-side detection
+            uint32_t a[2][4], bh[2][2], bl[2][2];
+            load_a_frag(sp_addr + (uint32_t)p0 * 64, (p0 >> 1) & 3, a);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                bh[ks][q] = hb ? bh1[ks][q] : bh0[ks][q];
+                bl[ks][q] = hb ? bl1[ks][q] : bl0[ks][q];
+              }
+            }
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              mma_f16f32(acc, a[ks], bh[ks]);
+              mma_f16f32(acc, a[ks], bl[ks]);
+            }
+            bool rare;
+            run_values(acc, b, rsel, c0, v0, v1, rare);
+            if (rare) {
+              const float* cof128 = cofs + (size_t)s_det[jsc] * 128;
+              v0 = pixel_value_cold(s_p, p0, win_x0 + (float)c0, hf, &s_box[jsc], cof128);
+              v1 = pixel_value_cold(s_p, p0 + 8, win_x0 + (float)(c0 + 8), hf, &s_box[jsc], cof128);
+            }
+          }
+          if (vc) {
+            if (c0 < SCa) val[p0] = v0;
+            if (c0 + 8 < SCa) val[p0 + 8] = v1;
+          }
+          r += u_dr; m += u_dm;
+          if (m >= MT) { m -= MT; ++r; }
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: lane = output pixel of one word; rows of this warp's word column (as in the scalar kernel)
+      for (int d = 0; d < nd; ++d) {
+        const BoxP b = s_box[j0 + d];
+        if (word_ok && wsrc_hi >= b.x1 && wsrc_lo < b.x2) {
+          const float* val = s_val + d * win_cap;
+          uint32_t* o = out + (size_t)s_det[j0 + d] * out_h * words + wq_first + wcol;
+          for (int y = y_first + rfirst; y <= y_last; y += rstep) {
+            const RowC rc = s_row[y - y_first];
+            if ((float)rc.y1 < b.y1 || (float)rc.y0 >= b.y2) continue;
+            const float hy = 1.f - rc.ly;
+            const float* r0 = val + rc.o0;
+            const float* r1 = val + rc.o1;
+            const float v = hy * (hx * r0[cx0] + lx * r0[cx1]) + rc.ly * (hx * r1[cx0] + lx * r1[cx1]);
+            const uint32_t bits = __ballot_sync(0xffffffffu, x_ok && v > thr);
+            if (lane == 0 && bits) o[(size_t)y * words] = bits;
+          }
+        }
+      }
+      __syncthreads();                                   // the next group's phase 1 overwrites the value tiles
+    }
+  }
+}
+
 // CropSplit operator (ops/crop/src/crop_split_cuda_kernel.cu:19-59), c == 2.
 template <typename T>
 __global__ void crop_split_kernel(const T* __restrict__ data, const T* __restrict__ rois, T* __restrict__ out,
@@ -533,6 +948,22 @@ __global__ void crop_mask_kernel(const T* __restrict__ data, const T* __restrict
 
 using namespace smb;
 
+// fp16 prototypes: tensor-core kernels (1, default) or the scalar-fmaf kernels (0); SMB_MASK_MMA overrides the default
+static int g_mask_mma = -1;
+static int mask_mma_enabled() {
+  if (g_mask_mma < 0) {
+    const char* e = getenv("SMB_MASK_MMA");
+    g_mask_mma = e ? (atoi(e) != 0) : SMB_MASK_MMA_DEFAULT;
+  }
+  return g_mask_mma;
+}
+
+extern "C" int smb_mask_set_tensor_dot(int on) {
+  const int prev = mask_mma_enabled();
+  if (on >= 0) g_mask_mma = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layout_hwc, const float* cofs,
                                  const float* boxes, const float* host_box_scale4, void* out, int out_dtype,
                                  int H, int W, int N, smb_stream_t stream) {
@@ -557,6 +988,20 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
   mask_assemble_kernel<PT, HWC, OT><<<grid, block, ma_smem, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, \
                                                                   (OT*)out, H, W, N)
   const int key = (protos_dtype << 2) | ((layout_hwc ? 1 : 0) << 1) | out_dtype;
+  if (protos_dtype == SMB_F16 && mask_mma_enabled()) {
+#define MAM_LAUNCH(HWC, OT)                                                                                              \
+  mask_assemble_mma_kernel<HWC, OT><<<grid, block, ma_smem, st>>>((const __half*)protos, cofs, boxes, s0, s1, s2, s3, \
+                                                                  (OT*)out, H, W, N)
+    switch (key & 3) {
+      case 0: MAM_LAUNCH(false, float); break;
+      case 1: MAM_LAUNCH(false, __half); break;
+      case 2: MAM_LAUNCH(true, float); break;
+      case 3: MAM_LAUNCH(true, __half); break;
+    }
+#undef MAM_LAUNCH
+    SMB_LAUNCH_OK("mask_assemble_mma_kernel");
+    return SMB_OK;
+  }
   switch (key) {
     case 0: MA_LAUNCH(float, false, float); break;
     case 1: MA_LAUNCH(float, false, __half); break;
@@ -663,13 +1108,28 @@ extern "C" int smb_mask_assemble_pack(const void* protos, int protos_dtype, int 
                 "pixels per 32-pixel word)", H, W, full_h, full_w, win_cap);
   dim3 grid(cdiv(cdiv(vw, 32), TW), cdiv(vh, TY)), block(MF_THREADS);
   const float s0 = host_box_scale4[0], s1 = host_box_scale4[1], s2 = host_box_scale4[2], s3 = host_box_scale4[3];
-  const size_t smem = (size_t)win_cap * (px_bytes + 8) + MF_LIST * (sizeof(BoxP) + sizeof(int)) + MF_TY_MAX * sizeof(RowC) + 16;
+  const bool mma = protos_dtype == SMB_F16 && mask_mma_enabled();
+  // value tiles: two (double-buffered, one detection each) for the scalar kernel, four (a group of detections) for the
+  // tensor-core kernel
+  const size_t smem = (size_t)win_cap * (px_bytes + (mma ? 16 : 8)) + MF_LIST * (sizeof(BoxP) + sizeof(int)) +
+                      MF_TY_MAX * sizeof(RowC) + 16;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    SMB_CUDA_OK(cudaFuncSetAttribute(mask_fused_pack_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  }
+  if (mma) {
+#define MFM_LAUNCH(HWC)                                                                                                  \
+  mask_fused_pack_mma_kernel<HWC><<<grid, block, smem, st>>>((const __half*)protos, cofs, boxes, s0, s1, s2, s3, out_bits, H, W, \
+                                                             N, out_h, out_w, words, rs, TY, TW, win_cap, thr)
+    if (layout_hwc) MFM_LAUNCH(true); else MFM_LAUNCH(false);
+#undef MFM_LAUNCH
+    SMB_LAUNCH_OK("mask_fused_pack_mma_kernel");
+    return SMB_OK;
   }
 #define MF_LAUNCH(PT, HWC)                                                                                          \
   mask_fused_pack_kernel<PT, HWC><<<grid, block, smem, st>>>((const PT*)protos, cofs, boxes, s0, s1, s2, s3, out_bits, H, W, \

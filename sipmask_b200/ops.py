@@ -295,6 +295,12 @@ def gather_track_feats(track_feats, det, count, scale_factor=1.0, feat_stride=8.
 
 # -------------------------------------------------------------------------------------- mask assembly
 @L.device_guard
+def set_mask_tensor_dot(on):
+    """fp16 prototypes: tensor-core (True) or scalar-fmaf (False) mask kernels for later calls (smb_mask_set_tensor_dot);
+    on=None only queries.  Returns the previous setting."""
+    return bool(L.lib().smb_mask_set_tensor_dot(-1 if on is None else int(bool(on))))
+
+
 def mask_assemble(protos, cofs, boxes, box_scale, layout='chw', out_dtype=torch.float32, out=None):
     """protos [32,H,W] ('chw') or [H,W,32] ('hwc'), fp32/fp16; cofs [N,128] fp32; boxes [N,4] fp32
     (image space); rois = boxes * box_scale (scalar or 4-vector).  Returns pos_masks [N,H,W]."""

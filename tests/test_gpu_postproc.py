@@ -16,6 +16,15 @@ def _oracle():
     return O, P, cbind
 
 
+@pytest.fixture(params=[False, True], ids=['scalar_dot', 'tensor_dot'])
+def mask_dot(request):
+    """Both families of mask kernels for fp16 prototypes: scalar fmaf and mma.sync (smb_mask_set_tensor_dot)."""
+    from sipmask_b200 import ops
+    prev = ops.set_mask_tensor_dot(request.param)
+    yield request.param
+    ops.set_mask_tensor_dot(prev)
+
+
 def _rand_dets(n, seed, size=200.0):
     rng = np.random.RandomState(seed)
     xy = rng.rand(n, 2) * size
@@ -122,8 +131,10 @@ def _iou(a, b):
 @pytest.mark.parametrize('H,W,N,layout,dtype', [(100, 168, 17, 'chw', torch.float32), (100, 168, 17, 'hwc', torch.float16),
                                                 (37, 53, 5, 'chw', torch.float16), (37, 53, 70, 'hwc', torch.float32),
                                                 (400, 672, 100, 'hwc', torch.float16)])
-def test_mask_assemble_matches_oracle(H, W, N, layout, dtype):
+def test_mask_assemble_matches_oracle(H, W, N, layout, dtype, mask_dot):
     from sipmask_b200 import ops, synth
+    if mask_dot and dtype != torch.float16:
+        pytest.skip('the tensor-core kernels take fp16 prototypes only (fp32 prototypes always run the scalar kernels)')
     O, P, cbind = _oracle()
     g = torch.Generator().manual_seed(H + N)
     protos = synth.prototypes(H, W, seed=N)
@@ -140,7 +151,9 @@ def test_mask_assemble_matches_oracle(H, W, N, layout, dtype):
     out = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float32)
     got = out.cpu().numpy()
     assert ((got == 0) == (ref == 0)).all()                              # crop geometry is exact
-    np.testing.assert_allclose(got, ref, atol=3e-6 if dtype == torch.float32 else 3e-6, rtol=0)
+    # scalar kernels: sequential fp32 fmaf like the oracle; tensor-core kernels: fp16 hi + lo coefficients (2^-22 relative
+    # per term) and the tensor core's own fp32 summation order
+    np.testing.assert_allclose(got, ref, atol=5e-6 if mask_dot else 3e-6, rtol=0)
     # x2 upsample + threshold
     m_ref = cbind.upsample2_thresh(ref, 0.4)
     m_dev = ops.mask_upsample2_threshold(out, (2 * H - 3, 2 * W - 1), 0.4).cpu().numpy()
@@ -159,6 +172,56 @@ def test_mask_assemble_matches_oracle(H, W, N, layout, dtype):
     # fp16 output variant
     out16 = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float16)
     np.testing.assert_allclose(out16.float().cpu().numpy(), ref, atol=1e-3, rtol=0)
+
+
+@pytest.mark.parametrize('H,W,N,layout', [(400, 672, 100, 'hwc'), (37, 53, 9, 'chw'), (64, 64, 150, 'hwc'), (9, 70, 6, 'hwc'),
+                                          (100, 168, 33, 'chw')])
+def test_mask_tensor_dot_matches_scalar_kernels(H, W, N, layout):
+    """mma.sync kernels vs the scalar-fmaf kernels on the same fp16 prototypes: identical crop geometry (which pixels are
+    non-zero), values within 2e-6, packed masks equal up to pixels sitting on the threshold.  Boxes include whole-image,
+    sub-pixel, integer-aligned and tile-straddling rois; N = 150 needs two list passes per tile."""
+    from sipmask_b200 import ops, synth
+    g = torch.Generator().manual_seed(7 * H + N)
+    protos = synth.prototypes(H, W, seed=N).half()
+    p_dev = (protos if layout == 'chw' else protos.permute(1, 2, 0)).contiguous().cuda()
+    cofs = torch.randn(N, 128, generator=g)
+    cofs[1] *= 40.0                                                     # large logits (both families lose ~1e-5 there)
+    cofs[2] *= 1e-3                                                     # tiny coefficients (fp16 lo part underflows)
+    cx, cy = torch.rand(N, generator=g) * W * 2, torch.rand(N, generator=g) * H * 2
+    bw, bh = torch.rand(N, generator=g) * W * 1.2 + 0.2, torch.rand(N, generator=g) * H * 1.2 + 0.2
+    boxes = torch.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1).clamp(min=0)
+    boxes[0] = torch.tensor([0.0, 0.0, 2.0 * W, 2.0 * H])              # whole image
+    boxes[3] = torch.tensor([16.0, 8.0, 48.0, 24.0])                    # integer-aligned in prototype space (x0.5)
+    boxes[4] = torch.tensor([30.2, 14.6, 30.9, 15.3])                   # smaller than one prototype pixel
+    boxes[5] = torch.tensor([2.0 * W - 40.0, 2.0 * H - 9.0, 2.0 * W + 50.0, 2.0 * H + 50.0])   # hangs over the corner
+    oh, ow = 2 * H - 1, 2 * W - 3
+    res = {}
+    prev = ops.set_mask_tensor_dot(None)
+    try:
+        for mode in (False, True):
+            ops.set_mask_tensor_dot(mode)
+            pos = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float32)
+            pos16 = ops.mask_assemble(p_dev, cofs.cuda(), boxes.cuda(), 0.5, layout=layout, out_dtype=torch.float16)
+            two = ops.unpack_mask_bits(ops.mask_upsample2_threshold_pack(pos, (oh, ow), 0.4), ow)
+            fused = ops.unpack_mask_bits(ops.mask_assemble_pack(p_dev, cofs.cuda(), boxes.cuda(), 0.5, (oh, ow), 0.4, layout=layout), ow)
+            fused_sf = ops.unpack_mask_bits(ops.mask_assemble_pack(p_dev, cofs.cuda(), boxes.cuda(), 0.5, (oh, ow), 0.4,
+                                                                   layout=layout, up=2.0 / 1.6667), ow)
+            res[mode] = [x.cpu().numpy() for x in (pos, pos16.float(), two, fused, fused_sf)]
+    finally:
+        ops.set_mask_tensor_dot(prev)
+    s_pos, s_pos16, s_two, s_fused, s_sf = res[False]
+    t_pos, t_pos16, t_two, t_fused, t_sf = res[True]
+    # crop geometry is exact (the tensor kernels' sigmoid flushes values below 1.2e-38 to 0, the scalar one keeps denormals)
+    assert (t_pos[s_pos == 0] == 0).all() and (t_pos[s_pos > 1e-30] > 0).all()
+    big = np.zeros(N, bool)
+    big[1] = True
+    np.testing.assert_allclose(t_pos[~big], s_pos[~big], atol=3e-6, rtol=0)
+    np.testing.assert_allclose(t_pos[big], s_pos[big], atol=2e-4, rtol=0)
+    np.testing.assert_allclose(t_pos16, s_pos16, atol=1.5e-3, rtol=0)
+    assert (t_fused != t_two).mean() < 1e-5                              # fused == two-step within the tensor family
+    assert (t_fused != s_fused).mean() < 2e-5                            # and across families up to threshold ties
+    assert (t_sf != s_sf).mean() < 2e-5
+    assert t_fused.any() and t_sf.any()
 
 
 def test_crop_split_operator_matches_oracle():
@@ -205,7 +268,7 @@ def test_postproc_reproduces_reference_fixture(golden_dir, name):
 
 @pytest.mark.parametrize('H,W,up', [(48, 62, 2.0), (48, 62, 2.0 / 1.6667), (50, 64, (2 / 1.3, 2 / 1.7)), (60, 41, 2.0 / 3.1),
                                     (37, 53, 2.0 / 0.8), (272, 272, 2.0)])
-def test_mask_resize_matches_torch_interpolate(H, W, up):
+def test_mask_resize_matches_torch_interpolate(H, W, up, mask_dot):
     """The general resize (scale_factor != 1): two-step kernels and the fused kernel against
     F.interpolate(pos_masks, scale_factor=2/scale_factor, mode='bilinear', align_corners=False) > 0.4
     (sipmask_head.py:629-633), both coordinate rules (PyTorch >= 1.6 given-factor, and recompute_scale_factor=True)."""
