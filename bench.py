@@ -282,7 +282,11 @@ def run_ours(args):
     pool = EnginePool(engs)
     # the single collective of the path: records are logged locally per image and gathered ONCE at the end
     # of the run, inside the timed region
-    log = sdist.RecordLog(max(args.steps, 1) * B, eng.max_num, dev, feat_dim=512 if vis else 0)
+    # one STEP = one image (batch) through EVERY forward in flight: nfl * B images per GPU (workload A: 6 images, ~5 ms),
+    # so the timed region of K = 20 steps is ~0.1 s instead of ~17 ms and the end-of-run gather / rank skew are measured
+    # against a region long enough to resolve them ("run-to-run noise ... same order as the scaling loss")
+    ips = nfl * B
+    log = sdist.RecordLog(max(args.steps, 1) * ips, eng.max_num, dev, feat_dim=512 if vis else 0)
     gathered = torch.empty((world,) + tuple(log.buf.shape), dtype=torch.float32, device=dev) if world > 1 else None
     if vis:
         from sipmask_b200.tracker import Tracker
@@ -302,7 +306,8 @@ def run_ours(args):
         log.reset()
 
     def step():
-        pool.step(consume)
+        for _ in range(nfl):
+            pool.step(consume)
 
     def step_finish():
         pool.flush(consume)
@@ -323,7 +328,9 @@ def run_ours(args):
     copy_done = []
 
     def step_e2e():
-        copy_done.append(runner.step(e2e_in, consume))
+        for _ in range(nfl):
+            copy_done.append(runner.step(e2e_in, consume))
+        del copy_done[:-1]
 
     def e2e_finish():
         runner.flush(consume)                  # the timed region ends when the last result is on the host
@@ -334,7 +341,7 @@ def run_ours(args):
         a short timed region would get no sample, so ROLL untimed steps of the same load run before and after it and
         the sampler stays on throughout (clocks.window says so)."""
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
-        roll = max(1, ROLL // B)
+        roll = max(1, ROLL // ips)
         if sample_clocks:
             # nvidia-smi needs ~0.3 s to start and samples every 100 ms: make each roll last >= 0.8 s of the same load
             # (short steps - workloads B / C - got no sample with a fixed count); every rank uses the same count
@@ -390,32 +397,33 @@ def run_ours(args):
     torch.cuda.synchronize()
     total_ms, clocks = timed(step, args.steps, sample_clocks=True, finish=step_finish)
     ms_per_step = total_ms / args.steps
-    value = world * B * 1000.0 / ms_per_step
+    value = world * ips * 1000.0 / ms_per_step
     for _ in range(3):
         step_e2e()
     e2e_finish()
     e2e_ms, _ = timed(step_e2e, args.steps, finish=e2e_finish)
-    e2e_value = world * B * 1000.0 / (e2e_ms / args.steps)
+    e2e_value = world * ips * 1000.0 / (e2e_ms / args.steps)
     last = runner.result(copy_done[-1])
     assert int(last['cnt'][0]) > 0
-    h2d, d2h = runner.h2d_bytes, runner.d2h_bytes
+    h2d, d2h = runner.h2d_bytes * nfl, runner.d2h_bytes * nfl
     ndet = int(eng.count[0].item())
 
     line = dict(metric='images/sec', value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f16',
                 data='synthetic',
                 config=dict(workload=wl['name'],
-                            parallelism='dp%d (one forward per GPU per step; detection records logged on the device and '
-                                        'all-gathered ONCE at the end of the run, inside the timed region)' % world,
+                            parallelism='dp%d (%d forward(s) in flight per GPU, one image batch through each per step; detection '
+                                        'records logged on the device and all-gathered ONCE at the end of the run, inside the '
+                                        'timed region)' % (world, nfl),
                             detections_per_image=ndet, cuda_graph=True, forwards_in_flight=nfl, batch_per_forward=B,
-                            images_per_step_per_gpu=B,
+                            images_per_step_per_gpu=ips,
                             l2='no flush: one step streams >= 1.3 GB of activations/masks through a 126 MB L2, so nothing but '
                                'weights can survive from the previous step'),
                 clocks=clocks, e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                                         ms_per_step=e2e_ms / args.steps,
                                         input='uint8 BGR HWC image from pinned host memory (resize/normalise/pad on the device)'
                                               if raw else 'fp32 NCHW batch from pinned host memory'),
-                gpu_launches=eng.n_launch * args.steps)
+                gpu_launches=eng.n_launch * nfl * args.steps)
     torch.cuda.synchronize()
 
     if rank == 0:
@@ -458,10 +466,13 @@ def run_ours(args):
         tr = traffic.get('conv_gemm_kernel', {})
         line['roofline'] = dict(bound='tensor', kernel='conv_gemm_kernel (%d launches/step)' % len(eng.conv_plans),
                                 achieved=tf, peak=peak_tf, unit='TFLOP/s', frac=tf / peak_tf,
-                                traffic=tr.get('dram_bytes_per_step'), traffic_source=tr.get('source'),
-                                peak_source=pk_kind + ' bf16_tflops_sustained', algorithmic_gflop_per_step=eng.conv_flops / 1e9,
-                                ms_per_step=conv_ms, share_of_step=conv_ms / ms_per_step,
-                                note='conv launches of %d forwards in flight replayed concurrently; time per forward' % nfl)
+                                traffic=tr.get('dram_bytes_per_step') * nfl if tr.get('dram_bytes_per_step') else None,
+                                traffic_source=tr.get('source'),
+                                peak_source=pk_kind + ' bf16_tflops_sustained', algorithmic_gflop_per_step=eng.conv_flops * nfl / 1e9,
+                                ms_per_step=conv_ms * nfl, share_of_step=conv_ms * nfl / ms_per_step,
+                                ms_per_forward=conv_ms,
+                                note='conv launches of %d forwards in flight replayed concurrently (one step = %d forwards)'
+                                     % (nfl, nfl))
         del graphs
         # ---- strictly serial reference point: ONE engine tuned for a single stream, one forward at a time
         if nfl > 1:
