@@ -13,6 +13,9 @@
 #ifndef SMB_MASK_MMA_DEFAULT
 #define SMB_MASK_MMA_DEFAULT 0
 #endif
+#ifndef SMB_MASK_TILE_DEFAULT
+#define SMB_MASK_TILE_DEFAULT 0
+#endif
 
 namespace smb {
 
@@ -584,11 +587,17 @@ __device__ __forceinline__ void run_values(const float (&acc)[4], const BoxP& b,
 // Dense pos_masks, tensor-core dots.  Same tiling / listing / zero-fill as mask_assemble_kernel; a warp owns one tile row
 // (its A fragments are re-read from shared memory per 16-pixel run and group: 8 LDS.32 against ~70 other instructions;
 // keeping the row's 32 fragment registers live cost a CTA per SM).
-template <bool HWC, typename OT>
-__global__ void __launch_bounds__(MA_THREADS2) mask_assemble_mma_kernel(
+// Tile = TH_ rows x TW_ pixels, TH_ * TW_ = 512 (8 x 64, 4 x 128 or 2 x 256): a warp owns one 64-pixel segment of one
+// tile row; wider tiles make the zero / value stores of a detection longer contiguous runs (256 / 512 / 1024 bytes).
+// 64 registers: four CTAs per SM, so the 550 - 600 CTAs of a 400 x 672 prototype map are ONE wave (at 80 registers the
+// second wave ran on a quarter of the SMs and the kernel took as long as the scalar one, profiles/r02_ncu_mask_mma_v1_summary.txt).
+template <bool HWC, typename OT, int TH_, int TW_>
+__global__ void __launch_bounds__(MA_THREADS2, 4) mask_assemble_mma_kernel(
     const __half* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes,
     float sx1, float sy1, float sx2, float sy2, OT* __restrict__ out, int H, int W, int N) {
-  extern __shared__ __align__(16) unsigned char s_p[];        // [MA_TH * MA_TW] swizzled pixels (32 KB)
+  static_assert(TH_ * TW_ == 512 && TW_ % 64 == 0 && TH_ * (TW_ / 64) == MA_THREADS2 / 32, "one warp per 64-pixel row segment");
+  constexpr int SEGS = TW_ / 64;                              // 64-pixel segments (warps) per tile row
+  extern __shared__ __align__(16) unsigned char s_p[];        // [TH_ * TW_] swizzled pixels (32 KB)
   __shared__ BoxP s_box[MA_LIST];
   __shared__ int s_det[MA_LIST];
   __shared__ int s_cnt;
@@ -596,20 +605,23 @@ __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_mma_kernel(
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int y0t = blockIdx.y * MA_TH, x0t = blockIdx.x * MA_TW;
-  const int SRa = min(MA_TH, H - y0t), SCa = min(MA_TW, W - x0t);
+  const int y0t = blockIdx.y * TH_, x0t = blockIdx.x * TW_;
+  const int SRa = min(TH_, H - y0t), SCa = min(TW_, W - x0t);
   stage_window<__half, HWC>(protos, s_p, H, W, y0t, x0t, SRa, SCa, MA_THREADS2);
-  const int h = y0t + warp;
-  const bool row_ok = warp < SRa;
+  const int wrow = warp / SEGS, wseg = (warp % SEGS) * 64;   // this warp's tile row and first tile column
+  const int h = y0t + wrow;
+  const bool row_ok = wrow < SRa && wseg < SCa;
   const float hf = (float)h;
   const float tile_x0 = (float)x0t, tile_x1 = (float)(x0t + SCa - 1), tile_y0 = (float)y0t, tile_y1 = (float)(y0t + SRa - 1);
-  const int zr = threadIdx.x >> 4, zc = (threadIdx.x & 15) * 4;
+  const float seg_x0 = (float)(x0t + wseg);
+  // zero-fill role: thread t < 128 owns 4 pixels: row t / (TW_ / 4), columns 4 * (t % (TW_ / 4)) ..
+  const int zr = threadIdx.x / (TW_ / 4), zc = (threadIdx.x % (TW_ / 4)) * 4;
   const bool z_vec = threadIdx.x < 128 && zr < SRa && zc + 3 < SCa && ((W & 3) == 0);
   const bool z_tail = threadIdx.x < 128 && zr < SRa && !z_vec && zc < SCa;
-  const int MT = (SCa + 15) >> 4;                           // 16-pixel runs of a tile row (the last one may be partial:
-                                                            // its surplus rows read the next row's pixels and are discarded)
-  // fragment row g of run 0 of this warp's row: pixel p_row (run m adds 16 pixels = 1024 bytes, same swizzle key)
-  const int p_row = warp * SCa + g;
+  const int MT = min(4, (SCa - wseg + 15) >> 4);            // 16-pixel runs of this warp's segment (the last one may be
+                                                            // partial: its surplus rows read later pixels and are discarded)
+  // fragment row g of run 0 of this warp's segment: pixel p_row (run m adds 16 pixels = 1024 bytes, same swizzle key)
+  const int p_row = wrow * SCa + wseg + g;
   const uint32_t a_row = smem_addr(s_p) + (uint32_t)p_row * 64 + 4 * t;
   const int a_sw = (p_row >> 1) & 3;
 
@@ -672,11 +684,11 @@ __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_mma_kernel(
       RowSel rsel;
       rsel.row_in = vc & (hf >= b.y1) & (hf < b.y2);
       rsel.rare = rsel.row_in & (hf - b.y1 >= b.roi_h + b.roi_h);
-      rsel.x0f = tile_x0;
-      OT* dst = out + ((size_t)n * H + h) * W + x0t + g;
+      rsel.x0f = seg_x0;
+      OT* dst = out + ((size_t)n * H + h) * W + x0t + wseg + g;
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
-        const float run_x0 = tile_x0 + (float)(m * 16), run_x1 = run_x0 + 15.f;
+        const float run_x0 = seg_x0 + (float)(m * 16), run_x1 = run_x0 + 15.f;
         const bool any_in = __any_sync(0xffffffffu, rsel.row_in & (run_x1 >= b.x1) & (run_x0 < b.x2));
         const int c0 = m * 16 + g;
         float v0 = 0.f, v1 = 0.f;
@@ -692,13 +704,13 @@ __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_mma_kernel(
           bool rare;
           run_values(acc, b, rsel, c0, v0, v1, rare);
           if (rare) {
-            v0 = pixel_value_cold(s_p, p_row + m * 16, tile_x0 + (float)c0, hf, &s_box[js], cofs + (size_t)n * 128);
-            v1 = pixel_value_cold(s_p, p_row + m * 16 + 8, tile_x0 + (float)(c0 + 8), hf, &s_box[js], cofs + (size_t)n * 128);
+            v0 = pixel_value_cold(s_p, p_row + m * 16, seg_x0 + (float)c0, hf, &s_box[js], cofs + (size_t)n * 128);
+            v1 = pixel_value_cold(s_p, p_row + m * 16 + 8, seg_x0 + (float)(c0 + 8), hf, &s_box[js], cofs + (size_t)n * 128);
           }
         }
         if (vc) {
-          if (c0 < SCa) store1<OT>(dst + m * 16, v0);
-          if (c0 + 8 < SCa) store1<OT>(dst + m * 16 + 8, v1);
+          if (wseg + c0 < SCa) store1<OT>(dst + m * 16, v0);
+          if (wseg + c0 + 8 < SCa) store1<OT>(dst + m * 16 + 8, v1);
         }
       }
     }
@@ -709,18 +721,20 @@ __global__ void __launch_bounds__(MA_THREADS2) mask_assemble_mma_kernel(
 // listed detections are processed FOUR at a time: phase 1 walks (window row, 16-pixel run) units round-robin over the
 // warps (the scalar kernel gave each warp whole rows: 10 rows on 8 warps, 66 columns on 32 lanes) and writes four value
 // tiles, phase 2 packs them; two barriers per group of four instead of one per detection.
+// 64 registers and a 64-entry list: four CTAs per SM (57 KB each), the ~550 CTAs of an 800 x 1344 canvas are one wave.
+constexpr int MFM_LIST = 64;
 template <bool HWC>
-__global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_mma_kernel(
+__global__ void __launch_bounds__(MF_THREADS, 4) mask_fused_pack_mma_kernel(
     const __half* __restrict__ protos, const float* __restrict__ cofs, const float* __restrict__ boxes, float sx1, float sy1,
     float sx2, float sy2, uint32_t* __restrict__ out, int H, int W, int N, int out_h, int out_w, int words, Resize rs,
     int TY, int TW, int win_cap, float thr) {
   extern __shared__ __align__(16) unsigned char mf_smem[];
   unsigned char* s_p = mf_smem;                                                        // [win_cap] swizzled pixels
   float* s_val = reinterpret_cast<float*>(mf_smem + (size_t)win_cap * 64);              // [4][win_cap]
-  BoxP* s_box = reinterpret_cast<BoxP*>(s_val + 4 * win_cap);                          // [MF_LIST]
-  RowC* s_row = reinterpret_cast<RowC*>(s_box + MF_LIST);                              // [MF_TY_MAX]
-  int* s_det = reinterpret_cast<int*>(s_row + MF_TY_MAX);                              // [MF_LIST]
-  int* s_cnt = s_det + MF_LIST;
+  BoxP* s_box = reinterpret_cast<BoxP*>(s_val + 4 * win_cap);                          // [MFM_LIST]
+  RowC* s_row = reinterpret_cast<RowC*>(s_box + MFM_LIST);                              // [MF_TY_MAX]
+  int* s_det = reinterpret_cast<int*>(s_row + MF_TY_MAX);                              // [MFM_LIST]
+  int* s_cnt = s_det + MFM_LIST;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -768,8 +782,8 @@ __global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_mma_kernel(
   const int u_r0 = warp / MT, u_m0 = warp - u_r0 * MT;
   const int u_dr = (MF_THREADS / 32) / MT, u_dm = (MF_THREADS / 32) - u_dr * MT;
 
-  for (int n0 = 0; n0 < N; n0 += MF_LIST) {
-    const int nb = min(MF_LIST, N - n0);
+  for (int n0 = 0; n0 < N; n0 += MFM_LIST) {
+    const int nb = min(MFM_LIST, N - n0);
     __syncthreads();                                   // window / row table staged; previous pass done with s_box, s_val
     if (threadIdx.x == 0) *s_cnt = 0;
     __syncthreads();
@@ -989,9 +1003,17 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
                                                                   (OT*)out, H, W, N)
   const int key = (protos_dtype << 2) | ((layout_hwc ? 1 : 0) << 1) | out_dtype;
   if (protos_dtype == SMB_F16 && mask_mma_enabled()) {
-#define MAM_LAUNCH(HWC, OT)                                                                                              \
-  mask_assemble_mma_kernel<HWC, OT><<<grid, block, ma_smem, st>>>((const __half*)protos, cofs, boxes, s0, s1, s2, s3, \
-                                                                  (OT*)out, H, W, N)
+    static int tile = -1;                                    // SMB_MASK_TILE: 0 = 8 x 64, 1 = 4 x 128, 2 = 2 x 256 pixels
+    if (tile < 0) { const char* e = getenv("SMB_MASK_TILE"); tile = e ? atoi(e) : SMB_MASK_TILE_DEFAULT; if (tile < 0 || tile > 2) tile = 0; }
+#define MAM_LAUNCH3(HWC, OT, TH_, TW_)                                                                                   \
+  mask_assemble_mma_kernel<HWC, OT, TH_, TW_><<<dim3(cdiv(W, TW_), cdiv(H, TH_)), block, 512 * 64, st>>>(                \
+      (const __half*)protos, cofs, boxes, s0, s1, s2, s3, (OT*)out, H, W, N)
+#define MAM_LAUNCH(HWC, OT)                                  \
+  do {                                                       \
+    if (tile == 1) MAM_LAUNCH3(HWC, OT, 4, 128);             \
+    else if (tile == 2) MAM_LAUNCH3(HWC, OT, 2, 256);        \
+    else MAM_LAUNCH3(HWC, OT, 8, 64);                        \
+  } while (0)
     switch (key & 3) {
       case 0: MAM_LAUNCH(false, float); break;
       case 1: MAM_LAUNCH(false, __half); break;
@@ -999,6 +1021,7 @@ extern "C" int smb_mask_assemble(const void* protos, int protos_dtype, int layou
       case 3: MAM_LAUNCH(true, __half); break;
     }
 #undef MAM_LAUNCH
+#undef MAM_LAUNCH3
     SMB_LAUNCH_OK("mask_assemble_mma_kernel");
     return SMB_OK;
   }
@@ -1098,7 +1121,9 @@ extern "C" int smb_mask_assemble_pack(const void* protos, int protos_dtype, int 
   const int px_budget = (int)((48 * 1024) / px_bytes);
   auto win_rows = [&](int ty) { return (int)ceilf((float)(ty - 1) * rs.ry) + 2; };
   auto win_cols = [&](int tw) { return (int)ceilf((float)(tw * 32 - 1) * rs.rx) + 2; };
-  int TW = 4, TY = MF_TY_MAX;
+  static int ty_max = -1;                                    // SMB_MASK_FUSED_TY: output rows per tile (1 .. 16, default 16)
+  if (ty_max < 0) { const char* e = getenv("SMB_MASK_FUSED_TY"); ty_max = e ? atoi(e) : MF_TY_MAX; if (ty_max < 1 || ty_max > MF_TY_MAX) ty_max = MF_TY_MAX; }
+  int TW = 4, TY = ty_max;
   while (TW > 1 && win_rows(TY) * win_cols(TW) > px_budget) TW >>= 1;
   while (TY > 1 && win_rows(TY) * win_cols(TW) > px_budget) TY >>= 1;
   // rounded up to a multiple of 4 pixels: the arrays carved out of shared memory after the window (s_val, s_box, ...) are
@@ -1111,7 +1136,7 @@ extern "C" int smb_mask_assemble_pack(const void* protos, int protos_dtype, int 
   const bool mma = protos_dtype == SMB_F16 && mask_mma_enabled();
   // value tiles: two (double-buffered, one detection each) for the scalar kernel, four (a group of detections) for the
   // tensor-core kernel
-  const size_t smem = (size_t)win_cap * (px_bytes + (mma ? 16 : 8)) + MF_LIST * (sizeof(BoxP) + sizeof(int)) +
+  const size_t smem = (size_t)win_cap * (px_bytes + (mma ? 16 : 8)) + (mma ? MFM_LIST : MF_LIST) * (sizeof(BoxP) + sizeof(int)) +
                       MF_TY_MAX * sizeof(RowC) + 16;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
