@@ -11,7 +11,7 @@
 #include "common.cuh"
 
 #ifndef SMB_MASK_MMA_DEFAULT
-#define SMB_MASK_MMA_DEFAULT 0
+#define SMB_MASK_MMA_DEFAULT 1
 #endif
 #ifndef SMB_MASK_TILE_DEFAULT
 #define SMB_MASK_TILE_DEFAULT 0
