@@ -236,7 +236,7 @@ def run_reference(args):
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload=wl['name'], detections=ndet, images_timed=n_timed, step_times_s=[round(t, 3) for t in ts],
-                            host_threads=tinfo),
+                            images_per_step_per_gpu=1, host_threads=tinfo),
                 cpu_baseline=dict(value=val, unit='images/s', cores=threads, kind='port', sample=sample),
                 e2e=dict(value=val, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))

@@ -483,9 +483,11 @@ __global__ void __launch_bounds__(MF_THREADS) mask_fused_pack_kernel(
 //        (uniform along a row, so each B column is chosen per (detection, row) by the lanes that own it),
 //   D  = for every pixel the logits of both idx_w halves of four detections; the epilogue keeps the one the pixel's own
 //        cell selects, applies the sigmoid and the crop.
-// The fp32 coefficients enter as fp16 hi + fp16 lo (c = hi + lo to 22 mantissa bits; two MMAs into one accumulator), the
-// prototypes are fp16 already, products and accumulation are fp32: the logit agrees with the sequential-fmaf kernels to
-// ~1e-6 relative; the geometry (which pixels are inside, which cell) is computed exactly as before.
+// The fp32 coefficients enter as fp16 hi + fp16 lo (two MMAs into one accumulator): c = hi + lo to 22 mantissa bits for
+// |c| >= 0.125, below that lo is an fp16 subnormal and the error is absolute, <= 2^-25 per coefficient.  The prototypes
+// are fp16 already, products and accumulation are fp32: the logit stays within 2^-21 * sum|p c| + 2^-24 * sum|p| of the
+// exact dot product, the same order as the sequential-fmaf kernels (numpy model: tests/test_host_logic.py); the geometry
+// (which pixels are inside, which cell) is computed exactly as before.
 // Scalar kernels: ~140 instructions per in-box pixel and detection; here ~75 per 16 pixels x 4 detections.
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {

@@ -56,3 +56,53 @@ def test_record_log_single_process():
     g = log.gather()
     assert g.shape == (1, 3, 5, 11)
     assert g[0, 0, 0, 0] == 3 and g[0, 1, 0, 0] == 1 and g[0, :, :, 6].sum() == 6 and g[0, 0, 0, 7] == 3
+
+
+def test_crop_cell_index_needs_no_division():
+    """The tensor-core mask kernels pick the CropSplit cell with `(w - x1) >= roi_w` instead of the reference's
+    `(int)((w - x1) / roi_w)` (crop_split_cuda_kernel.cu:50-51).  The two agree for every float32 pair with a >= 0, b > 0:
+    IEEE division rounds to nearest, so the truncated quotient is >= 1 exactly when a >= b and >= 2 exactly when a >= 2b
+    (`crop_idx` in mask_assemble.cu).  Checked on random pairs and on the neighbours of b and 2b, where it could break."""
+    rng = np.random.RandomState(0)
+    b = np.concatenate([rng.uniform(0.05, 700.0, 200000), 2.0 ** rng.randint(-4, 10, 1000), rng.uniform(0.05, 1.0, 50000)]).astype(np.float32)
+    cands = [rng.uniform(0.0, 3.0, b.size).astype(np.float32) * b]
+    for k in (1.0, 2.0):
+        t = (np.float32(k) * b).astype(np.float32)
+        cands += [t, np.nextafter(t, np.float32(0)), np.nextafter(t, np.float32(1e9)),
+                  np.nextafter(np.nextafter(t, np.float32(0)), np.float32(0))]
+    for a in cands:
+        a = a.astype(np.float32)
+        q = (a / b).astype(np.float32)                       # IEEE float32 division, round to nearest even
+        idx = q.astype(np.int32)                             # truncation, as the C cast
+        fast = (a >= b).astype(np.int32) + (a >= (b + b)).astype(np.int32)
+        low = idx <= 2
+        assert (np.minimum(idx, 2)[low] == fast[low]).all()
+        assert ((idx >= 1) == (a >= b)).all() and ((idx >= 2) == (a >= b + b)).all()
+
+
+def test_fp16_hi_lo_coefficient_split_keeps_fp32_logits():
+    """The tensor-core mask kernels feed the fp32 coefficients as fp16 hi + fp16 lo (load_b_frag in mask_assemble.cu):
+    hi = fp16(c), lo = fp16(c - hi): 22 mantissa bits for |c| >= 0.125; below that lo is an fp16 subnormal and the error is
+    absolute, <= 2^-25 per coefficient.  A numpy model of that split with fp32 accumulation stays within
+    2^-21 * sum|p c| + 2^-24 * sum|p| of the float64 dot product - the same order as the sequential fp32 fmaf of the scalar
+    kernels - including tiny coefficients and coefficients clamped at the fp16 range."""
+    rng = np.random.RandomState(1)
+    p = np.maximum(rng.randn(4096, 32), 0).astype(np.float16)                  # prototypes: fp16 storage
+    for scale in (1.0, 1e-3, 40.0, 3e4):
+        c = (rng.randn(4096, 32) * scale).astype(np.float32)
+        cc = np.clip(c, -65000.0, 65000.0)
+        hi = cc.astype(np.float16)
+        lo = (cc - hi.astype(np.float32)).astype(np.float16)
+        assert np.isfinite(hi.astype(np.float32)).all()
+        exact = (p.astype(np.float64) * cc.astype(np.float64)).sum(1)
+        acc = np.zeros(4096, np.float32)
+        for k in range(32):                                                    # fp32 accumulation of exact fp16 x fp16 products
+            acc = acc + p[:, k].astype(np.float32) * hi[:, k].astype(np.float32)
+            acc = acc + p[:, k].astype(np.float32) * lo[:, k].astype(np.float32)
+        bound = (np.abs(p.astype(np.float64) * cc.astype(np.float64))).sum(1) * 2.0 ** -21 + \
+            np.abs(p.astype(np.float64)).sum(1) * 2.0 ** -24 + 1e-9
+        assert (np.abs(acc.astype(np.float64) - exact) <= bound).all(), scale
+        seq = np.zeros(4096, np.float32)
+        for k in range(32):                                                    # the scalar kernels' arithmetic
+            seq = seq + p[:, k].astype(np.float32) * cc[:, k]
+        assert (np.abs(seq.astype(np.float64) - exact) <= bound).all(), scale
