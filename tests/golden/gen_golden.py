@@ -173,12 +173,15 @@ def gen_head_case(name, stacked_convs, gn, ssd_flag, sizes, img_shape, scale_fac
     print(name, 'dets', det_bboxes.shape[0], 'labels', sorted(set(det_labels.tolist()))[:10])
 
 
-def gen_backbone_case(name, seed=1):
+def gen_backbone_case(name, seed=1, depth=50, stage_with_dcn=(False, False, False, False)):
+    """ResNet(depth, caffe, eval BN) + FPN.  stage_with_dcn: the `++` configs' DeformConvPack blocks
+    (configs/sipmask/sipmask++_r101_caffe_fpn_ssd_6x.py:13-14, resnet.py:146-168,288-291)."""
     from mmdet.models.backbones.resnet import ResNet
     from mmdet.models.necks.fpn import FPN
-    net = ResNet(depth=50, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
-                 norm_cfg=dict(type='BN', requires_grad=False), style='caffe')
-    sd = synth.backbone_state_dict(50, seed, prefix='')
+    dcn = dict(type='DCN', deformable_groups=1, fallback_on_stride=False) if any(stage_with_dcn) else None
+    net = ResNet(depth=depth, num_stages=4, out_indices=(0, 1, 2, 3), frozen_stages=1,
+                 norm_cfg=dict(type='BN', requires_grad=False), style='caffe', dcn=dcn, stage_with_dcn=tuple(stage_with_dcn))
+    sd = synth.backbone_state_dict(depth, seed, prefix='', stage_with_dcn=tuple(stage_with_dcn))
     net.load_state_dict(sd, strict=True)
     net.eval()
     fpn = FPN(in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1, add_extra_convs=True,
@@ -278,6 +281,8 @@ if __name__ == '__main__':
     gen_head_case('ref_head_ssd2', 2, False, True, sizes, (96, 128, 3),
                   np.array([1.0, 1.0, 1.0, 1.0], np.float32), 0.1, seed=5)
     gen_backbone_case('ref_backbone_r50_64x96')
+    gen_backbone_case('ref_backbone_r101_64x96', seed=4, depth=101)
+    gen_backbone_case('ref_backbone_r50_dcn_64x96', seed=6, stage_with_dcn=(False, True, True, True))
     # scale_factor != 1 and ori_shape != img_shape (rescale=True): boxes are divided by the scale factor and the masks are
     # interpolated by 2/scale_factor into ori-image space (sipmask_head.py:587-588,623,629-633,648-654)
     gen_head_case('ref_head_gn4_sf', 4, True, False, sizes, (96, 125, 3), 1.6667, 0.05, seed=3, ori_shape=(58, 75, 3))

@@ -168,12 +168,19 @@ def test_rescoring_matches_reference(golden_dir):
     assert ((inter + 1e-9) / (union + 1e-9)).min() >= 0.999
 
 
-def test_backbone_fpn_match_reference(golden_dir):
-    g = _load(golden_dir, 'ref_backbone_r50_64x96.npz')
-    net = M.ResNet(50)
-    net.load_state_dict(synth.backbone_state_dict(50, 1, prefix=''), strict=True)
+@pytest.mark.parametrize('name,depth,seed,dcn', [('ref_backbone_r50_64x96', 50, 1, (False,) * 4),
+                                                 ('ref_backbone_r101_64x96', 101, 4, (False,) * 4),
+                                                 ('ref_backbone_r50_dcn_64x96', 50, 6, (False, True, True, True))])
+def test_backbone_fpn_match_reference(golden_dir, name, depth, seed, dcn):
+    """Oracle ResNet + FPN vs the unmodified reference modules on the same weights / image: ResNet-50, ResNet-101 (config 3)
+    and the `++` backbone with DeformConvPack in stages 2-4 (block 0 and every third block, resnet.py:288-291; the
+    reference's DCN native call is bound to oracle.ops.deform_conv, which tests/test_gpu_ref_cuda.py pins against the
+    reference CUDA kernel)."""
+    g = _load(golden_dir, name + '.npz')
+    net = M.ResNet(depth, dcn)
+    net.load_state_dict(synth.backbone_state_dict(depth, seed, prefix='', stage_with_dcn=dcn), strict=True)
     fpn = M.FPN()
-    fpn.load_state_dict(synth.neck_state_dict(2, prefix=''), strict=True)
+    fpn.load_state_dict(synth.neck_state_dict(seed + 1, prefix=''), strict=True)
     net.eval(), fpn.eval()
     with torch.no_grad():
         c = net(torch.from_numpy(g['img']))
