@@ -182,8 +182,14 @@ def oracle_step(net, img, wl):
         meta = dict(img_shape=shape, ori_shape=shape, scale_factor=1.0, is_first=False)
         det, lab, masks, ids = P.vis_get_bboxes(outs, meta, test_cfg(wl), oracle_step.tracker, rescale=True)
         return dict(det_bboxes=det)
-    with torch.no_grad():
-        cls, box, ctr, cof, fm = net(img)
+    t0 = time.perf_counter()
+    with torch.no_grad():                                  # per-stage split of the CPU forward
+        c = net.backbone(img)
+        t1 = time.perf_counter()
+        p = net.neck(c)
+        t2 = time.perf_counter()
+        cls, box, ctr, cof, fm = net.bbox_head(p)
+    t3 = time.perf_counter()
     real_nms = O.nms
     O.nms = lambda dets, thr, cmp_ge=False, plus_one=True: cbind.nms(dets, thr, int(cmp_ge), int(plus_one))
     shape = (wl['H'], wl['img_w'], 3)
@@ -193,6 +199,7 @@ def oracle_step(net, img, wl):
                                   (8, 16, 32, 64, 128), shape, shape, sf, test_cfg(wl), rescale=True, ssd_flag=wl['ssd'])
     finally:
         O.nms = real_nms
+    res['stage_s'] = dict(backbone=t1 - t0, fpn=t2 - t1, head=t3 - t2, postproc=time.perf_counter() - t3)
     return res
 
 
@@ -213,11 +220,15 @@ def cpu_reference(wl, steps, warmup, threads, budget_s=150.0):
     for _ in range(n_warm):
         oracle_step(net, img, wl)
     n_timed = max(1, min(steps, int(0.8 * budget_s / max(t_probe, 1e-3))))
-    ts = []
+    ts, stages = [], []
     for _ in range(n_timed):
         t0 = time.perf_counter()
         res = oracle_step(net, img, wl)
         ts.append(time.perf_counter() - t0)
+        stages.append(res.get('stage_s'))
+    cpu_reference.stage_split = None
+    if all(stages):                                        # median per stage over the timed images (not for the VIS workload)
+        cpu_reference.stage_split = {k: round(statistics.median(st[k] for st in stages), 4) for k in stages[0]}
     return statistics.median(ts), int(res['det_bboxes'].shape[0]), n_timed, ts, 1 + n_warm
 
 
@@ -237,7 +248,8 @@ def run_reference(args):
                 vs_baseline=None, dtype='f32', data='synthetic',
                 config=dict(workload=wl['name'], detections=ndet, images_timed=n_timed, step_times_s=[round(t, 3) for t in ts],
                             images_per_step_per_gpu=1, host_threads=tinfo),
-                cpu_baseline=dict(value=val, unit='images/s', cores=threads, kind='port', sample=sample),
+                cpu_baseline=dict(value=val, unit='images/s', cores=threads, kind='port', sample=sample,
+                                  stage_split_s=cpu_reference.stage_split),
                 e2e=dict(value=val, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -501,6 +513,7 @@ def run_ours(args):
             threads, tinfo = host_threads()
             sec, _, n_timed, ts, n_warm = cpu_reference(wl, 3, 1, threads, budget_s=25.0)
             line['cpu_baseline'] = dict(value=1.0 / sec, unit='images/s', cores=threads, kind='port', host_threads=tinfo,
+                                        stage_split_s=cpu_reference.stage_split,
                                         sample='%d whole %dx%d image(s) timed (median) after %d warm-up, through the oracle (PyTorch '
                                                'CPU fp32 restatement of the reference forward incl. get_bboxes)' % (n_timed, H, W, n_warm))
         else:
