@@ -249,7 +249,7 @@ def run_reference(args):
                 config=dict(workload=wl['name'], detections=ndet, images_timed=n_timed, step_times_s=[round(t, 3) for t in ts],
                             images_per_step_per_gpu=1, host_threads=tinfo),
                 cpu_baseline=dict(value=val, unit='images/s', cores=threads, kind='port', sample=sample,
-                                  stage_split_s=cpu_reference.stage_split),
+                                  stage_split_s=cpu_reference.stage_split, torch=__import__('torch').__version__),
                 e2e=dict(value=val, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -513,7 +513,7 @@ def run_ours(args):
             threads, tinfo = host_threads()
             sec, _, n_timed, ts, n_warm = cpu_reference(wl, 3, 1, threads, budget_s=25.0)
             line['cpu_baseline'] = dict(value=1.0 / sec, unit='images/s', cores=threads, kind='port', host_threads=tinfo,
-                                        stage_split_s=cpu_reference.stage_split,
+                                        stage_split_s=cpu_reference.stage_split, torch=torch.__version__,
                                         sample='%d whole %dx%d image(s) timed (median) after %d warm-up, through the oracle (PyTorch '
                                                'CPU fp32 restatement of the reference forward incl. get_bboxes)' % (n_timed, H, W, n_warm))
         else:
