@@ -194,12 +194,14 @@ def oracle_step(net, img, wl):
     O.nms = lambda dets, thr, cmp_ge=False, plus_one=True: cbind.nms(dets, thr, int(cmp_ge), int(plus_one))
     shape = (wl['H'], wl['img_w'], 3)
     sf = np.ones(4, dtype=np.float32) if wl['ssd'] else 1.0
+    post = {}
     try:
         res = P.get_bboxes_single([t[0] for t in cls], [t[0] for t in box], [t[0] for t in ctr], [t[0] for t in cof], fm[0],
-                                  (8, 16, 32, 64, 128), shape, shape, sf, test_cfg(wl), rescale=True, ssd_flag=wl['ssd'])
+                                  (8, 16, 32, 64, 128), shape, shape, sf, test_cfg(wl), rescale=True, ssd_flag=wl['ssd'], timing=post)
     finally:
         O.nms = real_nms
-    res['stage_s'] = dict(backbone=t1 - t0, fpn=t2 - t1, head=t3 - t2, postproc=time.perf_counter() - t3)
+    res['stage_s'] = dict(backbone=t1 - t0, fpn=t2 - t1, head=t3 - t2, decode_nms=post.get('decode_nms', 0.0),
+                          mask_assembly=post.get('mask_assembly', 0.0), paste=post.get('paste', 0.0))
     return res
 
 

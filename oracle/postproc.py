@@ -88,9 +88,13 @@ def assemble_masks(feat_mask, det_cofs, det_boxes, box_scale, up=2.0, thr=0.4, u
 
 def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask, strides,
                       img_shape, ori_shape, scale_factor, cfg, rescale=False, ssd_flag=False,
-                      num_classes=80, cmp_ge=False, mask_thr=0.4, head=None, legacy_interp=False):
+                      num_classes=80, cmp_ge=False, mask_thr=0.4, head=None, legacy_interp=False, timing=None):
     """Returns dict(det_bboxes [k,5], det_labels [k], idxs_keep [k], pos_masks [k,Hm,Wm],
-    masks [k,Hi,Wi] uint8 pasted to ori/img shape, mask_scores or None)."""
+    masks [k,Hi,Wi] uint8 pasted to ori/img shape, mask_scores or None).  `timing`: optional dict that receives the wall
+    time of the stages (decode_nms / mask_assembly = 4 x matmul + sigmoid + CropSplit + resize + threshold / paste) for the
+    CPU baseline of bench.py."""
+    import time
+    _t0 = time.perf_counter()
     boxes, scores, ctr, cofs, _ = decode_candidates(
         cls_scores, bbox_preds, centernesses, cof_preds, strides, img_shape,
         cfg.get('nms_pre', -1), num_classes)
@@ -110,6 +114,9 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
             iou_threshold=cfg['nms']['iou_thr'], score_thr=cfg['score_thr'])
     out = dict(det_bboxes=det_bboxes, det_labels=det_labels, idxs_keep=idxs,
                pos_masks=None, masks=None, mask_scores=None)
+    _t1 = time.perf_counter()
+    if timing is not None:
+        timing['decode_nms'] = _t1 - _t0
     if det_bboxes.shape[0] > 0:
         scale = 2
         if rescale is None:
@@ -121,6 +128,7 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
         pos_masks, masks = assemble_masks(feat_mask, det_cofs, det_bboxes[:, :4], box_scale, up, mask_thr,
                                           legacy_interp=legacy_interp)
         out['pos_masks'] = pos_masks
+        _t2 = time.perf_counter()
         tgt = ori_shape if rescale else img_shape
         k = masks.shape[0]
         im = np.zeros((k, tgt[0], tgt[1]), dtype=np.uint8)              # :648-654
@@ -128,6 +136,9 @@ def get_bboxes_single(cls_scores, bbox_preds, centernesses, cof_preds, feat_mask
         ww = min(masks.shape[2], tgt[1])
         im[:, :hh, :ww] = masks.numpy()[:, :hh, :ww]
         out['masks'] = im
+        if timing is not None:
+            timing['mask_assembly'] = _t2 - _t1
+            timing['paste'] = time.perf_counter() - _t2
         if head is not None and getattr(head, 'rescoring_flag', False):  # :635-643
             pred_iou = pos_masks.unsqueeze(1)
             pred_iou = head.convs_scoring(pred_iou)
